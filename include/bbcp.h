@@ -1,0 +1,171 @@
+/*
+ * bbcp.h -- C ABI of the B200 batched Boolean-constraint-propagation engine (libbbcp.so).
+ *
+ * This is the drop-in boundary for ONE path of the reference solver (IntelSAT / "Topor"): propagating
+ * many independent probes or cubes to their unit-propagation fixpoint over one shared, read-only clause
+ * database. Every entry point names the reference interface it stands in for (file:line relative to the
+ * reference tree). Conventions follow the reference's own C ABI (ToporIpasir.cc:118-178): opaque handle,
+ * int32 DIMACS literals, integer return codes, no exceptions, sticky status, caller-owned buffers.
+ *
+ * There is no CPU propagation path behind this ABI: every propagate/probe/solve call runs the CUDA
+ * kernels (sm_100a) and fails with BBCP_ERR_CUDA when no device is usable.
+ */
+#ifndef BBCP_H
+#define BBCP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bbcp_handle bbcp_handle;
+
+/* return / status codes. Sticky ones mirror TToporStatus (ToporExternalTypes.hpp:13-49):
+ * CONTRADICTORY ~ STATUS_CONTRADICTORY, ERR_ALLOC ~ STATUS_ALLOC_FAILED,
+ * ERR_INDEX_TOO_NARROW ~ STATUS_INDEX_TOO_NARROW (TopiConflictAnalysis.cc:67-71). */
+enum {
+    BBCP_OK = 0,
+    BBCP_CONTRADICTORY = 1,         /* the clause database is unsatisfiable by unit propagation at level 0 */
+    BBCP_ERR_ALLOC = -1,
+    BBCP_ERR_CUDA = -2,             /* no device / CUDA failure (message in bbcp_error_string) */
+    BBCP_ERR_INDEX_TOO_NARROW = -3, /* database exceeds the 32-bit slot / clause indices */
+    BBCP_ERR_STATE = -4,            /* call not valid in this state (e.g. propagate before finalize) */
+    BBCP_ERR_ARG = -5
+};
+
+/* per probe / per cube result flag */
+enum {
+    BBCP_FLAG_OK = 0,          /* fixpoint reached without conflict; implied set valid */
+    BBCP_FLAG_CONFLICT = 1,    /* unit propagation derives a conflict (a failed literal for a depth-1 probe) */
+    BBCP_FLAG_TRIVIAL_L0 = 2,  /* every literal of the cube is already true at level 0 (Topi.cc:851-865) */
+    BBCP_FLAG_FALSE_L0 = 3,    /* some literal of the cube is false at level 0 (Topi.cc:853-860) */
+    BBCP_FLAG_UNMAPPED = 4     /* the cube names a variable that occurs in no kept clause; not propagated */
+};
+
+/* option bits */
+enum {
+    BBCP_OPT_IMPLIED = 1u,     /* produce the per-probe implied-literal sets (else flags + bitmaps only) */
+    BBCP_OPT_NO_LEN_PRUNE = 2u /* diagnostic: scan ternary/long rows even while only one literal is assigned */
+};
+
+typedef struct {
+    uint32_t flags;            /* BBCP_OPT_* ; default BBCP_OPT_IMPLIED */
+    uint32_t small_trail;      /* per-probe shared-memory trail capacity of the first-tier kernel (0 = auto) */
+    uint64_t out_capacity;     /* device capacity for implied literals per launch, in literals (0 = auto) */
+} bbcp_opts;
+
+typedef struct {
+    uint64_t n;                /* probes / cubes in the batch */
+    uint64_t n_implied;        /* total implied literals (length of impl_lits) */
+    uint64_t n_ok, n_conflict, n_skipped; /* flag 0 / flag 1 / flags 2,3,4 */
+    uint64_t n_large;          /* probes that overflowed shared memory and ran in the global-state kernel */
+    uint64_t props_all;        /* literals dequeued and propagated (every trail literal of every probe) */
+    uint64_t props_ref;        /* of those, literals whose negation has a non-empty row: the reference's
+                                  m_Implications convention (TopiBcp.cc:193-198) */
+    uint64_t slots;            /* 8-byte row slots examined */
+    uint64_t clause_fetches;   /* long clauses fetched from the arena */
+    uint64_t kernel_bytes;     /* algorithmic bytes moved by the propagate kernels ("bytes model") */
+    float kernel_ms;           /* device time of the propagate kernels of this call (CUDA events) */
+    float total_ms;            /* device time of the whole call incl. result compaction */
+    uint32_t launches;         /* kernels launched by this call */
+    uint32_t reserved;
+} bbcp_batch_info;
+
+typedef struct {
+    int32_t max_var;           /* probe universe = +1,-1,...,+max_var,-max_var */
+    uint64_t n_mapped_vars, n_level0;
+    uint64_t n_bin, n_tern, n_long, n_long_lits;   /* clauses kept after level-0 simplification */
+    uint64_t row_slots, arena_words;
+    uint64_t device_bytes;
+    uint32_t db_version;
+    uint32_t reserved;
+} bbcp_db_info;
+
+/* ---- lifetime: CTopor ctor/dtor (Topor.hpp:31, Topor.cc:12,29-33); ipasir_init/release (ToporIpasir.cc:118-131) */
+bbcp_handle *bbcp_create(int32_t nvars_hint);
+void bbcp_release(bbcp_handle *h);
+/* choose the CUDA device before finalize (default: the current device of the calling thread) */
+int bbcp_set_device(bbcp_handle *h, int device);
+
+/* ---- clause intake: CTopor::AddClause (Topor.hpp:33-38) -> CTopi::AddUserClause (Topi.cc:377-653);
+ *      ipasir_add (ToporIpasir.cc:14-25). 0 terminates a clause; reading stops at the first 0. */
+int bbcp_add(bbcp_handle *h, int32_t lit_or_zero);
+int bbcp_add_clause(bbcp_handle *h, const int32_t *lits, size_t n);
+int bbcp_add_clauses(bbcp_handle *h, const int32_t *words, uint64_t nwords); /* stream of 0-terminated clauses */
+
+/* ---- finalize: what Solve does before search (Topi.cc:1127-1160: ReserveVarAndLitData + level-0 BCP),
+ *      here: normalise (A12), level-0 unit propagation ON THE DEVICE, level-0 simplification, build the
+ *      CSR rows + clause arena, upload. Returns BBCP_OK or BBCP_CONTRADICTORY (sticky) or an error. */
+int bbcp_finalize(bbcp_handle *h);
+/* host-only half of finalize (normalise + build rows, no level-0 propagation, no device): lets CPU-only
+ * tests inspect the database layout. */
+int bbcp_host_prepare(bbcp_handle *h);
+int bbcp_get_db_info(const bbcp_handle *h, bbcp_db_info *out);
+/* external literals assigned at level 0, ascending |var|; returns the count */
+uint64_t bbcp_level0_lits(const bbcp_handle *h, int32_t *out, uint64_t cap);
+/* row of internal literal ilit (= 2*var + neg) as built on the host: copies up to cap words of
+ * [nbin, ntern, nlong, bins..., tern pairs..., long (blocker, clause lits...)...]; returns words needed */
+uint64_t bbcp_host_row(const bbcp_handle *h, uint32_t ilit, uint32_t *out, uint64_t cap);
+
+/* ---- status: CTopor::IsError / GetStatusExplanation (Topor.hpp:111-114) */
+int bbcp_status(const bbcp_handle *h);
+const char *bbcp_error_string(const bbcp_handle *h);
+
+/* ---- the hot path: batched BCP to fixpoint. Stands in for one
+ *      NewDecLevel/Assign/BCP()/Backtrack(0) round of the reference per probe (TopiBcp.cc:103-410,
+ *      TopiAsg.cc:46-139, TopiBacktrack.cc:18-53) and for HandleAssumptions/AssignAssumptions per cube
+ *      (Topi.cc:797-938, 715-769). Host buffers in; results stay on the device until fetched. */
+int bbcp_propagate_batch(bbcp_handle *h, const int32_t *lits, const uint64_t *off, uint64_t ncubes,
+                         const bbcp_opts *opts, bbcp_batch_info *info);
+/* probe universe indices [first, last): index i is literal (i/2+1) * (i odd ? -1 : +1) */
+int bbcp_probe_range(bbcp_handle *h, uint64_t first, uint64_t last, const bbcp_opts *opts, bbcp_batch_info *info);
+int bbcp_probe_all(bbcp_handle *h, const bbcp_opts *opts, bbcp_batch_info *info);
+/* same as bbcp_propagate_batch with the cube arrays already resident in device memory */
+int bbcp_propagate_batch_device(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint64_t ncubes,
+                                uint64_t nlits, const bbcp_opts *opts, bbcp_batch_info *info);
+
+/* ---- results of the last batch, device -> caller buffers */
+int bbcp_fetch_flags(bbcp_handle *h, uint8_t *flag /* n */);
+int bbcp_fetch_implied(bbcp_handle *h, uint64_t *impl_off /* n+1 */, int32_t *impl_lits /* n_implied */);
+/* failed-literal bitmap (bit 2*var+neg set <=> that literal is a failed literal found by a depth-1 probe so
+ * far) and unit bitmap (the negations). nwords32 = bbcp_bitmap_words(). Bitmaps accumulate over calls until
+ * bbcp_clear_bitmaps. */
+uint64_t bbcp_bitmap_words(const bbcp_handle *h);
+int bbcp_fetch_bitmaps(bbcp_handle *h, uint32_t *failed, uint32_t *unit);
+int bbcp_clear_bitmaps(bbcp_handle *h);
+/* device addresses of the two bitmaps, for an on-stream NCCL all-gather / all-reduce by the caller */
+void *bbcp_device_failed_bitmap(bbcp_handle *h);
+void *bbcp_device_unit_bitmap(bbcp_handle *h);
+/* device addresses of the last batch's results (flag u8[n]; impl_off u64[n+1]; impl_lits i32[n_implied]) */
+void *bbcp_device_flags(bbcp_handle *h);
+void *bbcp_device_impl_off(bbcp_handle *h);
+void *bbcp_device_impl_lits(bbcp_handle *h);
+/* the CUDA stream (cudaStream_t) every kernel of this handle is launched on */
+void *bbcp_stream(bbcp_handle *h);
+/* blocks until the handle's stream is idle */
+int bbcp_sync(bbcp_handle *h);
+
+/* ---- single-cube convenience path with the Topor / IPASIR conventions:
+ *      ipasir_assume / ipasir_solve / ipasir_val (ToporIpasir.cc:27-68), CTopor::Solve(assumps)
+ *      (Topor.hpp:48), GetLitValue (Topor.hpp:80), GetLitDecLevel (Topor.hpp:88), Backtrack (Topor.hpp:68).
+ *      bbcp_solve returns 20 when unit propagation of the assumptions derives a conflict, 10 when every
+ *      mapped variable got assigned without conflict, else 0 (fixpoint reached; the search the reference
+ *      would start here is out of scope). Assumptions are cleared by bbcp_solve as in IPASIR. */
+int bbcp_assume(bbcp_handle *h, int32_t lit);
+int bbcp_solve(bbcp_handle *h);
+/* value of lit after the last bbcp_solve: 1 satisfied, -1 unsatisfied, 0 unassigned, 2 don't-care (variable
+ * occurs in no clause): TToporLitVal (ToporExternalTypes.hpp:81-87) */
+int bbcp_val(bbcp_handle *h, int32_t lit);
+/* 0 for level-0 literals, 1 for literals assigned by the last solve's cube, -1 if unassigned */
+int bbcp_declevel(bbcp_handle *h, int32_t lit);
+int bbcp_backtrack(bbcp_handle *h, int32_t level);
+
+/* ---- counters: CTopor::GetPropagations (Topor.hpp:107-108, Topi.cc:1427-1431): props_ref summed over all calls */
+uint64_t bbcp_propagations(const bbcp_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,668 @@
+// bbcp_capi.cu -- the C ABI of include/bbcp.h: handle, device memory, launch orchestration, result fetch,
+// and the Topor/IPASIR-style single-cube path. No propagation happens on the host.
+#include "../../include/bbcp.h"
+#include "bbcp_db.h"
+#include "bbcp_device.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bbcp;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    // grow-only; contents are not preserved
+    bool reserve(size_t need, bool zero = false)
+    {
+        if (need <= bytes && p) return true;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        size_t want = need + need / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            want = need;
+            if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+        }
+        bytes = want;
+        if (zero) cudaMemset(p, 0, bytes);
+        return true;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct CastU64 {
+    __host__ __device__ uint64_t operator()(const uint32_t &x) const { return (uint64_t)x; }
+};
+
+// misc device words: [0..C_N) counters, then cursor, then (u32) ticket, overflow_count
+constexpr int MISC_CURSOR = C_N;
+constexpr int MISC_U32 = C_N + 1;       // as u32 index: 2*MISC_U32 = ticket, +1 = overflow_count
+constexpr int MISC_WORDS64 = C_N + 2;
+
+}  // namespace
+
+struct bbcp_handle {
+    HostDb db;
+    int status = BBCP_OK;
+    std::string err;
+    int device = -1;
+    bool prepared = false, finalized = false, device_ready = false;
+    uint32_t db_version = 0;
+    int sm_count = 148;
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+
+    DevBuf d_hdr, d_slots, d_arena, d_varinfo, d_failed, d_unit;
+    uint64_t bitmap_words = 0;
+    uint64_t device_db_bytes = 0;
+
+    DevBuf d_flag, d_raw_off, d_len, d_out, d_off, d_impl, d_cube_lits, d_cube_off, d_overflow, d_misc, d_lbits, d_ltrail, d_cubtmp;
+    unsigned long long *h_misc = nullptr;   // pinned
+    uint32_t large_workers = 0;
+
+    uint64_t last_n = 0, last_n_implied = 0;
+    bool have_batch = false;
+    uint64_t total_props = 0;
+
+    std::vector<int32_t> assumps;
+    std::vector<int8_t> solve_val;   // per var after bbcp_solve: 0 unassigned, 1 true, -1 false (level > 0)
+    bool solved = false;
+
+    int fail(int code, const std::string &msg)
+    {
+        if (code < 0 || code == BBCP_CONTRADICTORY) status = code;
+        err = msg;
+        return code;
+    }
+    bool cuda_ok(cudaError_t e, const char *what)
+    {
+        if (e == cudaSuccess) return true;
+        fail(BBCP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        cudaGetLastError();
+        return false;
+    }
+};
+
+namespace {
+
+bool ensure_device(bbcp_handle *h)
+{
+    if (h->device_ready) return true;
+    int ndev = 0;
+    if (!h->cuda_ok(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount")) return false;
+    if (ndev == 0) { h->fail(BBCP_ERR_CUDA, "no CUDA device: this engine has no CPU path"); return false; }
+    if (h->device < 0) { if (!h->cuda_ok(cudaGetDevice(&h->device), "cudaGetDevice")) return false; }
+    if (!h->cuda_ok(cudaSetDevice(h->device), "cudaSetDevice")) return false;
+    cudaDeviceProp prop;
+    if (!h->cuda_ok(cudaGetDeviceProperties(&prop, h->device), "cudaGetDeviceProperties")) return false;
+    h->sm_count = prop.multiProcessorCount;
+    if (!h->cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+    for (auto &e : h->ev) if (!h->cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return false;
+    if (!h->cuda_ok(cudaMallocHost(&h->h_misc, MISC_WORDS64 * 8), "cudaMallocHost")) return false;
+    h->device_ready = true;
+    return true;
+}
+
+bool upload(bbcp_handle *h, DevBuf &b, const void *src, size_t bytes)
+{
+    if (!b.reserve(bytes ? bytes : 16)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (database)"); return false; }
+    if (bytes && !h->cuda_ok(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream), "upload")) return false;
+    return true;
+}
+
+bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo)
+{
+    HostDb &db = h->db;
+    if (!upload(h, h->d_hdr, db.hdr.data(), db.hdr.size() * sizeof(RowHdr))) return false;
+    if (!upload(h, h->d_slots, db.slots.data(), db.slots.size() * sizeof(Slot))) return false;
+    if (!upload(h, h->d_arena, db.arena.data(), db.arena.size() * 4)) return false;
+    if (!upload(h, h->d_varinfo, varinfo.data(), varinfo.size())) return false;
+    h->bitmap_words = (2 * ((uint64_t)db.max_var + 1) + 31) / 32;
+    if (!h->d_failed.reserve(h->bitmap_words * 4) || !h->d_unit.reserve(h->bitmap_words * 4)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (bitmaps)"); return false; }
+    cudaMemsetAsync(h->d_failed.p, 0, h->bitmap_words * 4, h->stream);
+    cudaMemsetAsync(h->d_unit.p, 0, h->bitmap_words * 4, h->stream);
+    if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "upload sync")) return false;
+    h->device_db_bytes = db.hdr.size() * sizeof(RowHdr) + db.slots.size() * sizeof(Slot) + db.arena.size() * 4 + varinfo.size() + 2 * h->bitmap_words * 4;
+    return true;
+}
+
+DbView db_view(const bbcp_handle *h)
+{
+    DbView v;
+    v.hdr = h->d_hdr.as<uint4>();
+    v.slots = h->d_slots.as<uint2>();
+    v.arena = h->d_arena.as<uint4>();
+    v.varinfo = h->d_varinfo.as<uint8_t>();
+    v.max_var = h->db.max_var;
+    v.nvars_words16 = (uint32_t)(((uint64_t)h->db.max_var + 1 + 15) / 16);
+    return v;
+}
+
+uint32_t pow2_at_least(uint32_t x) { uint32_t p = 32; while (p < x) p <<= 1; return p; }
+
+// The whole device-side batch. cube arrays already on the device (nullptr = probe universe from `first`).
+int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint64_t first, uint64_t n,
+              const bbcp_opts *uopts, bbcp_batch_info *info)
+{
+    bbcp_opts opts;
+    opts.flags = BBCP_OPT_IMPLIED; opts.small_trail = 0; opts.out_capacity = 0;
+    if (uopts) opts = *uopts;
+    if (n > 0xfffffff0ull) return h->fail(BBCP_ERR_ARG, "batch too large (split it)");
+    bbcp_batch_info bi;
+    memset(&bi, 0, sizeof(bi));
+    bi.n = n;
+    h->have_batch = false;
+
+    const size_t n1 = (size_t)n + 1;
+    if (!h->d_flag.reserve(n1) || !h->d_raw_off.reserve(n1 * 8) || !h->d_len.reserve(n1 * 4) || !h->d_off.reserve(n1 * 8) ||
+        !h->d_overflow.reserve(n1 * 4) || !h->d_misc.reserve(MISC_WORDS64 * 8))
+        return h->fail(BBCP_ERR_ALLOC, "device allocation failed (batch buffers)");
+
+    uint32_t cap = opts.small_trail ? pow2_at_least(opts.small_trail) : 512;
+    if (cap > 8192) cap = 8192;
+    const bool implied = (opts.flags & BBCP_OPT_IMPLIED) != 0;
+    uint64_t out_cap = implied ? (opts.out_capacity ? opts.out_capacity : std::max<uint64_t>(1u << 20, 8 * n)) : 0;
+
+    DbView dbv = db_view(h);
+    BatchView b;
+    memset(&b, 0, sizeof(b));
+    b.cube_lits = d_lits;
+    b.cube_off = d_off;
+    b.first = first;
+    b.n = n;
+    b.flag = h->d_flag.as<uint8_t>();
+    b.raw_off = h->d_raw_off.as<uint64_t>();
+    b.len = h->d_len.as<uint32_t>();
+    b.failed = h->d_failed.as<uint32_t>();
+    b.unit = h->d_unit.as<uint32_t>();
+    b.counters = h->d_misc.as<unsigned long long>();
+    b.out_cursor = h->d_misc.as<unsigned long long>() + MISC_CURSOR;
+    b.ticket = h->d_misc.as<unsigned int>() + 2 * MISC_U32;
+    b.overflow_count = h->d_misc.as<uint32_t>() + 2 * MISC_U32 + 1;
+    b.overflow_list = h->d_overflow.as<uint32_t>();
+    b.opts = opts.flags;
+
+    const int bps = small_blocks_per_sm(cap);
+    if (bps <= 0) return h->fail(BBCP_ERR_CUDA, "first-tier kernel does not fit (shared memory)");
+    const uint64_t chunks = (n + 31) / 32;
+
+    cudaEventRecord(h->ev[0], h->stream);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        if (!h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (implied literals)");
+        b.out_lits = h->d_out.as<int32_t>();
+        b.out_cap = out_cap;
+        b.worklist = nullptr;
+        b.nwork = 0;
+        cudaMemsetAsync(h->d_misc.p, 0, MISC_WORDS64 * 8, h->stream);
+        bi.launches = 0;
+        if (n) {
+            int blocks = (int)std::min<uint64_t>((uint64_t)bps * h->sm_count, (chunks + SMALL_WARPS - 1) / SMALL_WARPS);
+            launch_small(dbv, b, cap, std::max(blocks, 1), h->stream);
+            ++bi.launches;
+        }
+        cudaMemcpyAsync(h->h_misc, h->d_misc.p, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "first-tier kernel")) return BBCP_ERR_CUDA;
+        const uint32_t n_over = reinterpret_cast<uint32_t *>(h->h_misc)[2 * MISC_U32 + 1];
+        if (n_over) {
+            // second tier: per-warp global slabs sized for the whole variable range
+            const size_t per_worker = (size_t)dbv.nvars_words16 * 4 + ((size_t)dbv.max_var + 1) * 4;
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            uint64_t workers = std::min<uint64_t>({(uint64_t)h->sm_count * 8 * LARGE_WARPS, (uint64_t)((n_over + LARGE_WARPS - 1) / LARGE_WARPS) * LARGE_WARPS,
+                                                   std::max<uint64_t>(LARGE_WARPS, (free_b / 2 + h->d_lbits.bytes + h->d_ltrail.bytes) / std::max<size_t>(per_worker, 1))});
+            workers = std::max<uint64_t>(LARGE_WARPS, workers / LARGE_WARPS * LARGE_WARPS);
+            if (workers > h->large_workers || !h->d_lbits.p) {
+                h->d_lbits.release();
+                h->d_ltrail.release();
+                if (!h->d_lbits.reserve(workers * dbv.nvars_words16 * 4, true) || !h->d_ltrail.reserve(workers * ((size_t)dbv.max_var + 1) * 4))
+                    return h->fail(BBCP_ERR_ALLOC, "device allocation failed (second-tier state)");
+                h->large_workers = (uint32_t)workers;
+            }
+            LargeState ls;
+            ls.bits = h->d_lbits.as<uint32_t>();
+            ls.trail = h->d_ltrail.as<uint32_t>();
+            b.worklist = b.overflow_list;
+            b.nwork = n_over;
+            cudaMemsetAsync(b.ticket, 0, 4, h->stream);
+            launch_large(dbv, b, ls, (int)(std::min<uint64_t>(workers, h->large_workers) / LARGE_WARPS), h->stream);
+            ++bi.launches;
+            cudaMemcpyAsync(h->h_misc, h->d_misc.p, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
+            if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "second-tier kernel")) return BBCP_ERR_CUDA;
+        }
+        const uint64_t cursor = h->h_misc[MISC_CURSOR];
+        if (cursor <= out_cap) { bi.n_implied = cursor; break; }
+        // implied-literal buffer too small: redo the batch with room for everything that was asked for
+        out_cap = std::max<uint64_t>(cursor + cursor / 8, out_cap * 2);
+        if (attempt == 7) return h->fail(BBCP_ERR_ALLOC, "implied-literal buffer keeps overflowing");
+    }
+    cudaEventRecord(h->ev[1], h->stream);
+
+    bi.props_all = h->h_misc[C_PROPS_ALL];
+    bi.props_ref = h->h_misc[C_PROPS_REF];
+    bi.slots = h->h_misc[C_SLOTS];
+    bi.clause_fetches = h->h_misc[C_CLAUSE_FETCH];
+    bi.n_large = h->h_misc[C_LARGE];
+    bi.n_ok = h->h_misc[C_OK];
+    bi.n_conflict = h->h_misc[C_CONFLICT];
+    bi.n_skipped = h->h_misc[C_SKIPPED];
+    // bytes model: row headers + row slots + clause units + implied literals (kernel counters),
+    // plus the per-item result record (flag 1 + len 4 + raw_off 8) and the cube input
+    bi.kernel_bytes = h->h_misc[C_BYTES] + 13 * n;
+
+    if (implied && n) {
+        // canonical CSR: exclusive scan of the set sizes, then a gather out of allocation order
+        cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> in(b.len, CastU64());
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, h->d_off.as<uint64_t>(), (int)n, h->stream);
+        if (!h->d_cubtmp.reserve(tmp + 16) || !h->d_impl.reserve(std::max<uint64_t>(bi.n_implied, 4) * 4))
+            return h->fail(BBCP_ERR_ALLOC, "device allocation failed (compaction)");
+        cub::DeviceScan::ExclusiveSum(h->d_cubtmp.p, tmp, in, h->d_off.as<uint64_t>(), (int)n, h->stream);
+        cudaMemcpyAsync(h->d_off.as<uint64_t>() + n, b.out_cursor, 8, cudaMemcpyDeviceToDevice, h->stream);
+        launch_gather(b, h->d_off.as<uint64_t>(), h->d_impl.as<int32_t>(), h->stream);
+        bi.launches += 2;
+    } else {
+        cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
+    }
+    cudaEventRecord(h->ev[2], h->stream);
+    if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "batch")) return BBCP_ERR_CUDA;
+    cudaEventElapsedTime(&bi.kernel_ms, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&bi.total_ms, h->ev[0], h->ev[2]);
+    h->last_n = n;
+    h->last_n_implied = bi.n_implied;
+    h->have_batch = true;
+    h->total_props += bi.props_ref;
+    if (info) *info = bi;
+    return BBCP_OK;
+}
+
+int need_final(bbcp_handle *h)
+{
+    if (!h) return BBCP_ERR_ARG;
+    if (h->status < 0) return h->status;
+    if (!h->finalized) return h->fail(BBCP_ERR_STATE, "bbcp_finalize has not been called");
+    if (h->status == BBCP_CONTRADICTORY) return BBCP_CONTRADICTORY;
+    return BBCP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+bbcp_handle *bbcp_create(int32_t nvars_hint)
+{
+    bbcp_handle *h = new (std::nothrow) bbcp_handle();
+    if (h && nvars_hint > 0) h->db.raw.reserve((size_t)nvars_hint * 4);
+    return h;
+}
+
+void bbcp_release(bbcp_handle *h)
+{
+    if (!h) return;
+    if (h->device_ready) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_varinfo, &h->d_failed, &h->d_unit, &h->d_flag, &h->d_raw_off, &h->d_len,
+                          &h->d_out, &h->d_off, &h->d_impl, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_misc, &h->d_lbits,
+                          &h->d_ltrail, &h->d_cubtmp})
+            b->release();
+        if (h->h_misc) cudaFreeHost(h->h_misc);
+        for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    delete h;
+}
+
+int bbcp_set_device(bbcp_handle *h, int device)
+{
+    if (!h) return BBCP_ERR_ARG;
+    if (h->device_ready) return h->fail(BBCP_ERR_STATE, "device already in use by this handle");
+    h->device = device;
+    return BBCP_OK;
+}
+
+static int intake_guard(bbcp_handle *h)
+{
+    if (!h) return BBCP_ERR_ARG;
+    if (h->status < 0) return h->status;
+    // clauses added after a finalize make the device snapshot stale: the next finalize rebuilds it
+    h->finalized = false;
+    h->prepared = false;
+    return BBCP_OK;
+}
+
+int bbcp_add(bbcp_handle *h, int32_t lit)
+{
+    int rc = intake_guard(h);
+    if (rc) return rc;
+    if (lit == INT32_MIN) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, "literal out of range");
+    h->db.pending.push_back(lit);
+    if (lit == 0) {
+        h->db.add_words(h->db.pending.data(), h->db.pending.size());
+        h->db.pending.clear();
+    }
+    return BBCP_OK;
+}
+
+int bbcp_add_clause(bbcp_handle *h, const int32_t *lits, size_t n)
+{
+    int rc = intake_guard(h);
+    if (rc) return rc;
+    size_t m = 0;
+    while (m < n && lits[m] != 0) {
+        if (lits[m] == INT32_MIN) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, "literal out of range");
+        ++m;
+    }
+    h->db.add_words(lits, m);
+    const int32_t z = 0;
+    h->db.add_words(&z, 1);
+    return BBCP_OK;
+}
+
+int bbcp_add_clauses(bbcp_handle *h, const int32_t *words, uint64_t nwords)
+{
+    int rc = intake_guard(h);
+    if (rc) return rc;
+    if (nwords && words[nwords - 1] != 0) return h->fail(BBCP_ERR_ARG, "clause stream must end with 0");
+    for (uint64_t i = 0; i < nwords; ++i) if (words[i] == INT32_MIN) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, "literal out of range");
+    h->db.add_words(words, nwords);
+    return BBCP_OK;
+}
+
+int bbcp_host_prepare(bbcp_handle *h)
+{
+    if (!h) return BBCP_ERR_ARG;
+    if (h->status < 0) return h->status;
+    h->db.normalise();
+    if (h->db.contradictory) { h->prepared = true; return h->fail(BBCP_CONTRADICTORY, "AddClause: the clause set is contradictory at intake"); }
+    const std::string e = h->db.build_rows();
+    if (!e.empty()) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, e);
+    h->prepared = true;
+    if (h->status == BBCP_CONTRADICTORY) h->status = BBCP_OK;
+    return BBCP_OK;
+}
+
+int bbcp_finalize(bbcp_handle *h)
+{
+    if (!h) return BBCP_ERR_ARG;
+    if (h->status < 0) return h->status;
+    h->status = BBCP_OK;
+    h->finalized = false;
+    h->have_batch = false;
+    h->solved = false;
+    if (!ensure_device(h)) return h->status;
+    cudaSetDevice(h->device);
+    int rc = bbcp_host_prepare(h);
+    if (rc == BBCP_CONTRADICTORY) { h->finalized = true; ++h->db_version; return rc; }
+    if (rc) return rc;
+    HostDb &db = h->db;
+    if (!db.units.empty()) {
+        // level-0 unit propagation on the device: the unit clauses form one cube over the un-simplified
+        // database (Topi.cc:1137-1160 runs BCP() at level 0 before anything else)
+        std::vector<uint8_t> mapped_only(db.varinfo);
+        for (auto &v : mapped_only) v &= 4;
+        if (!upload_db(h, mapped_only)) return h->status;
+        std::vector<int32_t> cube(db.units.size());
+        for (size_t i = 0; i < cube.size(); ++i) cube[i] = (db.units[i] & 1) ? -(int32_t)(db.units[i] >> 1) : (int32_t)(db.units[i] >> 1);
+        const uint64_t off[2] = {0, cube.size()};
+        h->finalized = true;  // the snapshot is usable for this internal batch
+        bbcp_batch_info bi;
+        rc = bbcp_propagate_batch(h, cube.data(), off, 1, nullptr, &bi);
+        h->finalized = false;
+        if (rc) return rc;
+        uint8_t flag = 0;
+        if (bbcp_fetch_flags(h, &flag)) return h->status;
+        if (flag == BBCP_FLAG_CONFLICT) { h->finalized = true; ++h->db_version; return h->fail(BBCP_CONTRADICTORY, "level-0 unit propagation derives a conflict"); }
+        std::vector<uint64_t> ioff(2);
+        std::vector<int32_t> lits(std::max<uint64_t>(bi.n_implied, 1));
+        if (bbcp_fetch_implied(h, ioff.data(), lits.data())) return h->status;
+        for (uint64_t i = 0; i < bi.n_implied; ++i) {
+            const int32_t l = lits[i];
+            const uint32_t v = (uint32_t)(l < 0 ? -l : l);
+            db.varinfo[v] = (db.varinfo[v] & ~3) | (l < 0 ? 2 : 1);
+        }
+        if (!db.simplify_level0()) return h->fail(BBCP_ERR_STATE, "internal: level-0 fixpoint left a unit clause");
+        const std::string e = db.build_rows();
+        if (!e.empty()) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, e);
+        h->total_props = 0;
+    }
+    if (!upload_db(h, db.varinfo)) return h->status;
+    h->finalized = true;
+    h->have_batch = false;
+    ++h->db_version;
+    return BBCP_OK;
+}
+
+int bbcp_get_db_info(const bbcp_handle *h, bbcp_db_info *out)
+{
+    if (!h || !out) return BBCP_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    out->max_var = h->db.max_var;
+    out->n_mapped_vars = h->db.n_mapped();
+    out->n_level0 = h->db.n_level0();
+    out->n_bin = h->db.n_bin;
+    out->n_tern = h->db.n_tern;
+    out->n_long = h->db.n_long;
+    out->n_long_lits = h->db.n_long_lits;
+    out->row_slots = h->db.slots.size();
+    out->arena_words = h->db.arena.size();
+    out->device_bytes = h->device_db_bytes;
+    out->db_version = h->db_version;
+    return BBCP_OK;
+}
+
+uint64_t bbcp_level0_lits(const bbcp_handle *h, int32_t *out, uint64_t cap)
+{
+    if (!h) return 0;
+    uint64_t n = 0;
+    for (size_t v = 1; v < h->db.varinfo.size(); ++v) {
+        const uint8_t val = h->db.varinfo[v] & 3;
+        if (!val) continue;
+        if (out && n < cap) out[n] = val == 1 ? (int32_t)v : -(int32_t)v;
+        ++n;
+    }
+    return n;
+}
+
+uint64_t bbcp_host_row(const bbcp_handle *h, uint32_t ilit, uint32_t *out, uint64_t cap)
+{
+    if (!h || !h->prepared || ilit >= h->db.hdr.size()) return 0;
+    const RowHdr &r = h->db.hdr[ilit];
+    std::vector<uint32_t> w = {r.nbin, r.ntern, r.nlong};
+    const Slot *s = h->db.slots.data() + r.start;
+    for (uint32_t i = 0; i < r.nbin; ++i) w.push_back((i & 1) ? s[i / 2].y : s[i / 2].x);
+    s += (r.nbin + 1) / 2;
+    for (uint32_t i = 0; i < r.ntern; ++i) { w.push_back(s[i].x); w.push_back(s[i].y); }
+    s += r.ntern;
+    for (uint32_t i = 0; i < r.nlong; ++i) {
+        w.push_back(s[i].x);
+        const uint32_t *c = h->db.arena.data() + (size_t)s[i].y * 4;
+        for (uint32_t k = 0; k <= c[0]; ++k) w.push_back(c[k]);
+    }
+    for (size_t i = 0; i < w.size() && i < cap; ++i) out[i] = w[i];
+    return w.size();
+}
+
+int bbcp_status(const bbcp_handle *h) { return h ? h->status : BBCP_ERR_ARG; }
+const char *bbcp_error_string(const bbcp_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int bbcp_propagate_batch_device(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint64_t ncubes, uint64_t nlits,
+                                const bbcp_opts *opts, bbcp_batch_info *info)
+{
+    int rc = need_final(h);
+    if (rc) return rc;
+    (void)nlits;
+    cudaSetDevice(h->device);
+    return run_batch(h, d_lits, d_off, 0, ncubes, opts, info);
+}
+
+int bbcp_propagate_batch(bbcp_handle *h, const int32_t *lits, const uint64_t *off, uint64_t ncubes, const bbcp_opts *opts,
+                         bbcp_batch_info *info)
+{
+    int rc = need_final(h);
+    if (rc) return rc;
+    if (!off) return h->fail(BBCP_ERR_ARG, "cube offsets missing");
+    cudaSetDevice(h->device);
+    const uint64_t nlits = off[ncubes];
+    if (!h->d_cube_lits.reserve(std::max<uint64_t>(nlits, 4) * 4) || !h->d_cube_off.reserve((ncubes + 1) * 8))
+        return h->fail(BBCP_ERR_ALLOC, "device allocation failed (cubes)");
+    if (nlits) cudaMemcpyAsync(h->d_cube_lits.p, lits, nlits * 4, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(h->d_cube_off.p, off, (ncubes + 1) * 8, cudaMemcpyHostToDevice, h->stream);
+    return run_batch(h, h->d_cube_lits.as<int32_t>(), h->d_cube_off.as<uint64_t>(), 0, ncubes, opts, info);
+}
+
+int bbcp_probe_range(bbcp_handle *h, uint64_t first, uint64_t last, const bbcp_opts *opts, bbcp_batch_info *info)
+{
+    int rc = need_final(h);
+    if (rc) return rc;
+    const uint64_t universe = 2ull * (uint64_t)h->db.max_var;
+    if (first > last || last > universe) return h->fail(BBCP_ERR_ARG, "probe range outside the universe");
+    cudaSetDevice(h->device);
+    return run_batch(h, nullptr, nullptr, first, last - first, opts, info);
+}
+
+int bbcp_probe_all(bbcp_handle *h, const bbcp_opts *opts, bbcp_batch_info *info)
+{
+    if (!h) return BBCP_ERR_ARG;
+    return bbcp_probe_range(h, 0, 2ull * (uint64_t)h->db.max_var, opts, info);
+}
+
+int bbcp_fetch_flags(bbcp_handle *h, uint8_t *flag)
+{
+    if (!h || !h->have_batch) return h ? h->fail(BBCP_ERR_STATE, "no batch results") : BBCP_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->last_n && !h->cuda_ok(cudaMemcpyAsync(flag, h->d_flag.p, h->last_n, cudaMemcpyDeviceToHost, h->stream), "fetch flags")) return BBCP_ERR_CUDA;
+    return h->cuda_ok(cudaStreamSynchronize(h->stream), "fetch flags") ? BBCP_OK : BBCP_ERR_CUDA;
+}
+
+int bbcp_fetch_implied(bbcp_handle *h, uint64_t *impl_off, int32_t *impl_lits)
+{
+    if (!h || !h->have_batch) return h ? h->fail(BBCP_ERR_STATE, "no batch results") : BBCP_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (!h->cuda_ok(cudaMemcpyAsync(impl_off, h->d_off.p, (h->last_n + 1) * 8, cudaMemcpyDeviceToHost, h->stream), "fetch offsets")) return BBCP_ERR_CUDA;
+    if (h->last_n_implied && !h->cuda_ok(cudaMemcpyAsync(impl_lits, h->d_impl.p, h->last_n_implied * 4, cudaMemcpyDeviceToHost, h->stream), "fetch implied")) return BBCP_ERR_CUDA;
+    return h->cuda_ok(cudaStreamSynchronize(h->stream), "fetch implied") ? BBCP_OK : BBCP_ERR_CUDA;
+}
+
+uint64_t bbcp_bitmap_words(const bbcp_handle *h) { return h ? (2 * ((uint64_t)h->db.max_var + 1) + 31) / 32 : 0; }
+
+int bbcp_fetch_bitmaps(bbcp_handle *h, uint32_t *failed, uint32_t *unit)
+{
+    int rc = need_final(h);
+    if (rc) return rc;
+    cudaSetDevice(h->device);
+    if (failed) cudaMemcpyAsync(failed, h->d_failed.p, h->bitmap_words * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (unit) cudaMemcpyAsync(unit, h->d_unit.p, h->bitmap_words * 4, cudaMemcpyDeviceToHost, h->stream);
+    return h->cuda_ok(cudaStreamSynchronize(h->stream), "fetch bitmaps") ? BBCP_OK : BBCP_ERR_CUDA;
+}
+
+int bbcp_clear_bitmaps(bbcp_handle *h)
+{
+    int rc = need_final(h);
+    if (rc) return rc;
+    cudaSetDevice(h->device);
+    cudaMemsetAsync(h->d_failed.p, 0, h->bitmap_words * 4, h->stream);
+    cudaMemsetAsync(h->d_unit.p, 0, h->bitmap_words * 4, h->stream);
+    return h->cuda_ok(cudaStreamSynchronize(h->stream), "clear bitmaps") ? BBCP_OK : BBCP_ERR_CUDA;
+}
+
+void *bbcp_device_failed_bitmap(bbcp_handle *h) { return h ? h->d_failed.p : nullptr; }
+void *bbcp_device_unit_bitmap(bbcp_handle *h) { return h ? h->d_unit.p : nullptr; }
+void *bbcp_device_flags(bbcp_handle *h) { return h && h->have_batch ? h->d_flag.p : nullptr; }
+void *bbcp_device_impl_off(bbcp_handle *h) { return h && h->have_batch ? h->d_off.p : nullptr; }
+void *bbcp_device_impl_lits(bbcp_handle *h) { return h && h->have_batch ? h->d_impl.p : nullptr; }
+void *bbcp_stream(bbcp_handle *h) { return h ? (void *)h->stream : nullptr; }
+int bbcp_sync(bbcp_handle *h)
+{
+    if (!h || !h->device_ready) return BBCP_ERR_STATE;
+    cudaSetDevice(h->device);
+    return h->cuda_ok(cudaStreamSynchronize(h->stream), "sync") ? BBCP_OK : BBCP_ERR_CUDA;
+}
+
+int bbcp_assume(bbcp_handle *h, int32_t lit)
+{
+    if (!h) return BBCP_ERR_ARG;
+    if (lit == 0 || lit == INT32_MIN) return h->fail(BBCP_ERR_ARG, "bad assumption literal");
+    h->assumps.push_back(lit);
+    return BBCP_OK;
+}
+
+int bbcp_solve(bbcp_handle *h)
+{
+    if (!h) return 0;
+    std::vector<int32_t> cube;
+    cube.swap(h->assumps);
+    if (h->status == BBCP_OK && !h->finalized) bbcp_finalize(h);
+    if (h->status == BBCP_CONTRADICTORY) return 20;
+    if (need_final(h)) return 0;
+    h->solve_val.assign((size_t)h->db.max_var + 1, 0);
+    h->solved = false;
+    // assumptions on variables that occur in no clause are free variables (the reference creates them in
+    // Solve, Topi.cc:1117-1125): they cannot propagate, only contradict each other
+    std::vector<int32_t> dev_cube;
+    std::vector<std::pair<int32_t, int8_t>> free_vals;
+    for (int32_t l : cube) {
+        const int32_t v = l < 0 ? -l : l;
+        if (v <= h->db.max_var && (h->db.varinfo[v] & 4)) { dev_cube.push_back(l); continue; }
+        const int8_t want = l < 0 ? -1 : 1;
+        for (auto &fv : free_vals) if (fv.first == v && fv.second != want) return 20;
+        free_vals.emplace_back(v, want);
+    }
+    const uint64_t off[2] = {0, dev_cube.size()};
+    bbcp_batch_info bi;
+    if (bbcp_propagate_batch(h, dev_cube.data(), off, 1, nullptr, &bi)) return 0;
+    uint8_t flag = 0;
+    if (bbcp_fetch_flags(h, &flag)) return 0;
+    if (flag == BBCP_FLAG_CONFLICT || flag == BBCP_FLAG_FALSE_L0) return 20;
+    std::vector<uint64_t> ioff(2);
+    std::vector<int32_t> lits(std::max<uint64_t>(bi.n_implied, 1));
+    if (bbcp_fetch_implied(h, ioff.data(), lits.data())) return 0;
+    for (uint64_t i = 0; i < bi.n_implied; ++i) h->solve_val[lits[i] < 0 ? -lits[i] : lits[i]] = lits[i] < 0 ? -1 : 1;
+    for (auto &fv : free_vals) if (fv.first <= h->db.max_var) h->solve_val[fv.first] = fv.second;
+    h->solved = true;
+    return bi.n_implied + h->db.n_level0() == h->db.n_mapped() ? 10 : 0;
+}
+
+int bbcp_val(bbcp_handle *h, int32_t lit)
+{
+    if (!h || lit == 0 || lit == INT32_MIN) return 0;
+    const int32_t v = lit < 0 ? -lit : lit;
+    const int sign = lit < 0 ? -1 : 1;
+    if (v > h->db.max_var || h->db.varinfo.size() <= (size_t)v) return 2;
+    const uint8_t vi = h->db.varinfo[v];
+    if (vi & 3) return ((vi & 3) == 1 ? 1 : -1) * sign;
+    if (h->solved && h->solve_val[v]) return h->solve_val[v] * sign;
+    return (vi & 4) ? 0 : 2;
+}
+
+int bbcp_declevel(bbcp_handle *h, int32_t lit)
+{
+    if (!h || lit == 0 || lit == INT32_MIN) return -1;
+    const int32_t v = lit < 0 ? -lit : lit;
+    if (v > h->db.max_var || h->db.varinfo.size() <= (size_t)v) return -1;
+    if (h->db.varinfo[v] & 3) return 0;
+    if (h->solved && h->solve_val[v]) return 1;
+    return -1;
+}
+
+int bbcp_backtrack(bbcp_handle *h, int32_t level)
+{
+    if (!h) return BBCP_ERR_ARG;
+    if (level <= 0) { h->solved = false; }
+    return BBCP_OK;
+}
+
+uint64_t bbcp_propagations(const bbcp_handle *h) { return h ? h->total_props : 0; }
+
+}  // extern "C"

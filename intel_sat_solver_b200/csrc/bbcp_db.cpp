@@ -1,0 +1,223 @@
+// bbcp_db.cpp -- see bbcp_db.h. Host-only code (no CUDA): unit-testable on a CPU box.
+#include "bbcp_db.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace bbcp {
+
+void HostDb::add_words(const int32_t *w, uint64_t n)
+{
+    raw.insert(raw.end(), w, w + n);
+    for (uint64_t i = 0; i < n; ++i) {
+        // INT32_MIN cannot be negated; it is rejected by the C ABI before it gets here
+        const int32_t a = w[i] < 0 ? -w[i] : w[i];
+        if (a > max_var) max_var = a;
+    }
+}
+
+// One pass over the user clauses in the order they were added, with the observable behaviour of
+// AddUserClause (Topi.cc:377-653):
+//   - an empty clause makes the instance contradictory (451-456);
+//   - literals false under the units added SO FAR are dropped before anything else (487-491);
+//   - duplicate literals are dropped, a tautology drops the clause and un-maps the variables that were
+//     first seen in it (493-510, 434-443);
+//   - all literals dropped => contradictory (552-557); one literal left => level-0 assignment, propagated
+//     later (590-619); otherwise the clause is kept (621).
+// A variable is "mapped" iff some kept (or unit) clause mentions it.
+void HostDb::normalise()
+{
+    const size_t nv = (size_t)max_var + 1;
+    varinfo.assign(nv, 0);
+    cls.clear();
+    units.clear();
+    ncls = 0;
+    contradictory = false;
+    std::vector<int64_t> stamp(nv, 0);
+    std::vector<uint32_t> cur, fresh;
+    int64_t counter = 0;
+    const size_t n = raw.size();
+    size_t s = 0;
+    while (s < n && !contradictory) {
+        size_t e = s;
+        while (e < n && raw[e] != 0) ++e;
+        if (e == s) { contradictory = true; break; }
+        ++counter;
+        cur.clear();
+        fresh.clear();
+        bool taut = false;
+        for (size_t i = s; i < e; ++i) {
+            const int32_t l = raw[i];
+            const uint32_t v = (uint32_t)(l < 0 ? -l : l);
+            const uint32_t il = 2u * v + (l < 0);
+            if (!(varinfo[v] & 4)) { varinfo[v] |= 4; fresh.push_back(v); }
+            const uint8_t val = varinfo[v] & 3;
+            if (val && ((val == 1) == (l < 0))) continue;  // false at level 0
+            const int64_t me = (l < 0) ? -counter : counter;
+            if (stamp[v] == me) continue;
+            if (stamp[v] == -me) { taut = true; break; }
+            stamp[v] = me;
+            cur.push_back(il);
+        }
+        s = e + 1;
+        if (taut) {
+            for (uint32_t v : fresh) { varinfo[v] &= ~4; stamp[v] = 0; }
+            continue;
+        }
+        if (cur.empty()) { contradictory = true; break; }
+        if (cur.size() == 1) {
+            const uint32_t il = cur[0], v = il >> 1;
+            if ((varinfo[v] & 3) == 0) {
+                varinfo[v] |= (il & 1) ? 2 : 1;
+                units.push_back(il);
+            }
+            continue;
+        }
+        cls.push_back((uint32_t)cur.size());
+        cls.insert(cls.end(), cur.begin(), cur.end());
+        ++ncls;
+    }
+}
+
+bool HostDb::simplify_level0()
+{
+    size_t r = 0, w = 0;
+    uint64_t kept = 0;
+    const size_t n = cls.size();
+    while (r < n) {
+        const uint32_t len = cls[r];
+        const size_t hdr_pos = w++;
+        uint32_t out = 0;
+        bool sat = false;
+        for (uint32_t i = 0; i < len; ++i) {
+            const uint32_t il = cls[r + 1 + i];
+            const uint8_t val = varinfo[il >> 1] & 3;
+            if (val == 0) { cls[w++] = il; ++out; }
+            else if ((val == 1) == ((il & 1) == 0)) sat = true;
+        }
+        r += 1 + len;
+        if (sat) { w = hdr_pos; continue; }
+        if (out < 2) return false;
+        cls[hdr_pos] = out;
+        ++kept;
+    }
+    cls.resize(w);
+    ncls = kept;
+    return true;
+}
+
+std::string HostDb::build_rows()
+{
+    const size_t nl = 2 * ((size_t)max_var + 1);
+    hdr.assign(nl, RowHdr{0, 0, 0, 0});
+    n_bin = n_tern = n_long = n_long_lits = 0;
+
+    // pass 1: occurrences per literal
+    std::vector<uint32_t> bcount(nl + 1, 0);
+    uint64_t arena_words = 4;  // unit 0 is never a valid clause reference
+    for (size_t r = 0; r < cls.size();) {
+        const uint32_t len = cls[r];
+        const uint32_t *c = &cls[r + 1];
+        if (len == 2) { ++bcount[c[0]]; ++bcount[c[1]]; }
+        else if (len == 3) { ++hdr[c[0]].ntern; ++hdr[c[1]].ntern; ++hdr[c[2]].ntern; ++n_tern; }
+        else {
+            for (uint32_t i = 0; i < len; ++i) ++hdr[c[i]].nlong;
+            ++n_long;
+            n_long_lits += len;
+            arena_words += (1 + (uint64_t)len + 3) & ~3ull;
+        }
+        r += 1 + len;
+    }
+    if (arena_words / 4 >= 0xffffffffull) return "clause arena exceeds the 32-bit clause index";
+
+    // binary rows: gather, sort, unique -- a duplicate binary clause is kept once
+    // (TopiConflictAnalysis.cc:25-41 with the default /bcp/existing_bin_wl_start = 1)
+    std::vector<uint64_t> boff(nl + 1, 0);
+    for (size_t l = 0; l < nl; ++l) boff[l + 1] = boff[l] + bcount[l];
+    std::vector<uint32_t> bins(boff[nl]);
+    {
+        std::vector<uint64_t> pos(boff.begin(), boff.end() - 1);
+        for (size_t r = 0; r < cls.size();) {
+            const uint32_t len = cls[r];
+            if (len == 2) {
+                const uint32_t a = cls[r + 1], b = cls[r + 2];
+                bins[pos[a]++] = b;
+                bins[pos[b]++] = a;
+            }
+            r += 1 + len;
+        }
+    }
+    uint64_t total_bins = 0;
+    for (size_t l = 0; l < nl; ++l) {
+        uint32_t *b = bins.data() + boff[l], *e = bins.data() + boff[l + 1];
+        if (e - b > 1) {
+            std::sort(b, e);
+            e = std::unique(b, e);
+        }
+        hdr[l].nbin = (uint32_t)(e - b);
+        total_bins += hdr[l].nbin;
+    }
+    n_bin = total_bins / 2;
+
+    // row extents
+    uint64_t nslots = 0;
+    for (size_t l = 0; l < nl; ++l) {
+        if (nslots > 0xffffffffull) return "rows exceed the 32-bit slot index";
+        hdr[l].start = (uint32_t)nslots;
+        nslots += (uint64_t)((hdr[l].nbin + 1) / 2) + hdr[l].ntern + hdr[l].nlong;
+    }
+    if (nslots > 0xffffffffull) return "rows exceed the 32-bit slot index";
+    slots.assign(nslots, Slot{0, 0});
+    arena.assign(arena_words, 0);
+
+    // fill: binary part
+    for (size_t l = 0; l < nl; ++l) {
+        const uint32_t *b = bins.data() + boff[l];
+        Slot *row = slots.data() + hdr[l].start;
+        for (uint32_t i = 0; i < hdr[l].nbin; ++i) {
+            if (i & 1) row[i / 2].y = b[i]; else row[i / 2].x = b[i];
+        }
+    }
+    bins.clear();
+    bins.shrink_to_fit();
+    // fill: ternary and long parts
+    std::vector<uint32_t> tpos(nl), lpos(nl);
+    for (size_t l = 0; l < nl; ++l) {
+        tpos[l] = hdr[l].start + (hdr[l].nbin + 1) / 2;
+        lpos[l] = tpos[l] + hdr[l].ntern;
+    }
+    uint64_t aw = 4;
+    for (size_t r = 0; r < cls.size();) {
+        const uint32_t len = cls[r];
+        const uint32_t *c = &cls[r + 1];
+        if (len == 3) {
+            slots[tpos[c[0]]++] = Slot{c[1], c[2]};
+            slots[tpos[c[1]]++] = Slot{c[0], c[2]};
+            slots[tpos[c[2]]++] = Slot{c[0], c[1]};
+        } else if (len > 3) {
+            const uint32_t cref = (uint32_t)(aw / 4);
+            arena[aw] = len;
+            std::memcpy(&arena[aw + 1], c, (size_t)len * 4);
+            for (uint32_t i = 0; i < len; ++i) slots[lpos[c[i]]++] = Slot{c[(i + 1) % len], cref};
+            aw += (1 + (uint64_t)len + 3) & ~3ull;
+        }
+        r += 1 + len;
+    }
+    return "";
+}
+
+uint64_t HostDb::n_mapped() const
+{
+    uint64_t n = 0;
+    for (uint8_t v : varinfo) n += (v >> 2) & 1;
+    return n;
+}
+
+uint64_t HostDb::n_level0() const
+{
+    uint64_t n = 0;
+    for (uint8_t v : varinfo) n += (v & 3) != 0;
+    return n;
+}
+
+}  // namespace bbcp

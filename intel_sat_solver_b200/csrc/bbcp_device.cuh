@@ -1,0 +1,72 @@
+// bbcp_device.cuh -- device-side views shared by the kernels and the host launcher.
+//
+// Database layout in HBM (built by bbcp_db.cpp, read-only for every probe):
+//   hdr[ilit]   uint4 {start, nbin, ntern, nlong}: the row scanned when internal literal `ilit` becomes
+//               FALSE (the reference indexes m_Watches[Negate(p)] the same way, TopiBcp.cc:192).
+//   slots[]     8-byte slots. Row = ceil(nbin/2) binary slots {other, other|0}  (Topi.hpp:1952-1962 keeps
+//               4-byte binary entries too), then ntern ternary slots {a, b} (the clause is ilit v a v b,
+//               held inline: no arena fetch), then nlong long slots {blocker, clause16} -- one per OCCURRENCE
+//               of ilit in a clause of >= 4 literals, blocker = the next literal of that clause.
+//   arena[]     16-byte units; clause = [size, l0, l1, ...] padded with 0 to a multiple of 4 words.
+//   varinfo[v]  bits 0-1: level-0 value of var v (0 none, 1 true, 2 false); bit 2: mapped.
+// Internal literal = 2*var + neg with var = the external (DIMACS) variable.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bbcp {
+
+struct DbView {
+    const uint4 *hdr;
+    const uint2 *slots;
+    const uint4 *arena;
+    const uint8_t *varinfo;
+    int32_t max_var;
+    uint32_t nvars_words16;    // words of a 2-bit-per-var dense assignment: ceil((max_var+1)/16)
+};
+
+enum Counter { C_PROPS_ALL = 0, C_PROPS_REF, C_SLOTS, C_CLAUSE_FETCH, C_BYTES, C_LARGE, C_OK, C_CONFLICT, C_SKIPPED, C_N };
+
+struct BatchView {
+    // input: cubes (external literals) or, when cube_off == nullptr, the probe universe
+    const int32_t *cube_lits;
+    const uint64_t *cube_off;
+    uint64_t first;             // universe index of item 0 (probe mode)
+    uint64_t n;                 // items in the batch
+    const uint32_t *worklist;   // large tier: the item indices to run (nullptr = all items)
+    uint32_t nwork;
+    // output
+    uint8_t *flag;              // [n]
+    uint64_t *raw_off;          // [n] position of the item's implied set in out_lits
+    uint32_t *len;              // [n] size of the implied set
+    int32_t *out_lits;          // external literals, sorted by |var| inside each set
+    uint64_t out_cap;
+    unsigned long long *out_cursor;
+    uint32_t *failed, *unit;    // bitmaps over internal literals (probe mode only)
+    unsigned long long *counters;
+    uint32_t *overflow_list;    // items that did not fit the shared-memory state
+    uint32_t *overflow_count;
+    unsigned int *ticket;       // dynamic chunk scheduler
+    uint32_t opts;
+};
+
+constexpr uint32_t OPT_IMPLIED = 1u;
+constexpr uint32_t OPT_NO_LEN_PRUNE = 2u;
+constexpr uint8_t FLAG_OK = 0, FLAG_CONFLICT = 1, FLAG_TRIVIAL_L0 = 2, FLAG_FALSE_L0 = 3, FLAG_UNMAPPED = 4;
+constexpr uint8_t FLAG_OVERFLOW = 250;      // internal: re-run in the global-state tier
+constexpr uint8_t FLAG_OUT_OVERFLOW = 251;  // internal: implied-literal buffer full, re-run in a later launch
+
+struct LargeState {
+    uint32_t *bits;    // [workers][nvars_words16] 2 bits per var, all zero between probes
+    uint32_t *trail;   // [workers][max_var + 1]
+};
+
+void launch_small(const DbView &db, const BatchView &b, uint32_t trail_cap, int blocks, cudaStream_t s);
+void launch_large(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s);
+void launch_gather(const BatchView &b, const uint64_t *off, int32_t *dst, cudaStream_t s);
+size_t small_smem_bytes(uint32_t trail_cap);
+int small_blocks_per_sm(uint32_t trail_cap);
+constexpr int SMALL_WARPS = 4;   // warps (= concurrent probes) per CTA, first tier
+constexpr int LARGE_WARPS = 4;
+
+}  // namespace bbcp

@@ -1,0 +1,691 @@
+// bbcp_kernels.cu -- batched BCP to fixpoint on sm_100a. Hand-written CUDA; no tensor cores (there is no
+// dense contraction on this path), the bound is HBM/L2 gather bandwidth and load latency.
+//
+// What one probe/cube does here replaces one NewDecLevel/Assign/BCP()/Backtrack(0) round of the reference
+// (TopiBcp.cc:103-410, TopiAsg.cc:46-139, TopiBacktrack.cc:18-53):
+//   * the database is immutable and shared by all probes; the per-probe state is a sparse assignment
+//     (open-addressed hash set of true literals) and a trail, both in shared memory (first tier), or a dense
+//     2-bit-per-variable assignment and a trail in a per-warp global slab (second tier, any size);
+//   * the trail is also the propagation queue; it is consumed breadth-first, 32 literals per step, one
+//     literal per lane for the row-header gather, then the union of the 32 rows is flattened and scanned
+//     32 eight-byte slots at a time (coalesced within a row);
+//   * rows are OCCURRENCE lists (every clause is listed under each of its literals), so no watch has to
+//     move: assignments inside one probe only grow, hence a clause can be judged from scratch whenever one
+//     of its literals becomes false, and the visit made for its last-falsified literal sees every earlier
+//     assignment. This replaces FindBestWLCand/SwapCurrWatch/WLAddLongWatch/WLRemoveLongWatch
+//     (TopiBcp.cc:27-72, TopiWL.cc:115-208), which mutate shared rows;
+//   * binary clauses are 4-byte entries as in the reference (Topi.hpp:1952-1962); ternary clauses are held
+//     inline in the row ({a,b} per occurrence), long clauses as {blocker, clause} with the reference's
+//     cached-literal short-cut (TopiBcp.cc:255-259);
+//   * duplicate implications found in the same step are collapsed with __match_any_sync, the insertion into
+//     the hash set (atomicCAS) is the linearisation point that detects x / not-x conflicts;
+//   * while exactly one literal is assigned, only binary clauses can become unit, so the first step of a
+//     depth-1 probe reads the binary part of its row only ("length pruning"); a probe whose literal has no
+//     binary clause ends right there. The triage of 32 consecutive probes is done one probe per lane, with
+//     coalesced header loads and one aggregated output allocation per warp.
+// A conflict ends the probe (NewContradiction's same-level branch, TopiBcp.cc:141-158); only the flag is
+// part of the contract for conflicting probes.
+#include "bbcp_device.cuh"
+
+namespace bbcp {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+__device__ __forceinline__ int32_t to_ext(uint32_t il) { return (il & 1u) ? -(int32_t)(il >> 1) : (int32_t)(il >> 1); }
+
+// ---------------------------------------------------------------- per-probe state, first tier (shared memory)
+struct SmemState {
+    uint32_t *hash;    // [1 << log_hs] true literals, 0 = empty
+    uint32_t *trail;   // [cap]
+    uint16_t *tslot;   // [cap] hash slot of each trail entry (for the O(|trail|) clean-up)
+    uint32_t log_hs, cap;
+
+    __device__ __forceinline__ uint32_t h(uint32_t var) const { return (var * 0x9E3779B1u) >> (32 - log_hs); }
+    // 0 unassigned, 1 true, 2 false
+    __device__ __forceinline__ int lookup(uint32_t lit) const
+    {
+        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
+        uint32_t s = h(var);
+        for (;;) {
+            const uint32_t k = hash[s];
+            if (k == 0) return 0;
+            if ((k >> 1) == var) return k == lit ? 1 : 2;
+            s = (s + 1) & mask;
+        }
+    }
+    // 0 newly assigned, 1 already true, 2 already false (conflict)
+    __device__ __forceinline__ int insert(uint32_t lit, uint32_t &slot)
+    {
+        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
+        uint32_t s = h(var);
+        for (;;) {
+            const uint32_t old = atomicCAS(&hash[s], 0u, lit);
+            if (old == 0) { slot = s; return 0; }
+            if ((old >> 1) == var) return old == lit ? 1 : 2;
+            s = (s + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ uint32_t tget(uint32_t i) const { return trail[i]; }
+    __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t slot) { trail[i] = lit; tslot[i] = (uint16_t)slot; }
+    __device__ __forceinline__ void cleanup(uint32_t tail)
+    {
+        for (uint32_t i = lane_id(); i < tail; i += 32) hash[tslot[i]] = 0;
+        __syncwarp();
+    }
+    // after an overflow some table entries have no trail entry: wipe everything
+    __device__ __forceinline__ void wipe()
+    {
+        for (uint32_t i = lane_id(); i < (1u << log_hs); i += 32) hash[i] = 0;
+        __syncwarp();
+    }
+};
+
+// ---------------------------------------------------------------- per-probe state, second tier (global slab)
+struct GmemState {
+    uint32_t *bits;   // 2 bits per var: 1 = var true, 2 = var false
+    uint32_t *trail;
+    uint32_t cap;
+
+    __device__ __forceinline__ int lookup(uint32_t lit) const
+    {
+        const uint32_t var = lit >> 1;
+        const uint32_t o = (__ldcg(&bits[var >> 4]) >> ((var & 15u) * 2u)) & 3u;
+        if (o == 0) return 0;
+        return (o == 1u) == ((lit & 1u) == 0u) ? 1 : 2;
+    }
+    __device__ __forceinline__ int insert(uint32_t lit, uint32_t &slot)
+    {
+        const uint32_t var = lit >> 1, sh = (var & 15u) * 2u, bit = (lit & 1u) ? 2u : 1u;
+        const uint32_t o = (atomicOr(&bits[var >> 4], bit << sh) >> sh) & 3u;
+        slot = 0;
+        if (o == 0) return 0;
+        return o == bit ? 1 : 2;
+    }
+    __device__ __forceinline__ uint32_t tget(uint32_t i) const { return __ldcg(&trail[i]); }
+    __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t) { __stcg(&trail[i], lit); }
+    __device__ __forceinline__ void cleanup(uint32_t tail)
+    {
+        for (uint32_t i = lane_id(); i < tail; i += 32) {
+            const uint32_t var = __ldcg(&trail[i]) >> 1;
+            atomicAnd(&bits[var >> 4], ~(3u << ((var & 15u) * 2u)));
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void wipe() {}  // cannot overflow: the trail holds every variable
+};
+
+struct WarpCounters {
+    unsigned long long props_all = 0, props_ref = 0, slots = 0, fetches = 0, bytes = 0;
+    uint32_t n_ok = 0, n_conf = 0, n_skip = 0;
+    __device__ void flush(unsigned long long *c)
+    {
+        if (lane_id() == 0) {
+            if (props_all) atomicAdd(&c[C_PROPS_ALL], props_all);
+            if (props_ref) atomicAdd(&c[C_PROPS_REF], props_ref);
+            if (slots) atomicAdd(&c[C_SLOTS], slots);
+            if (fetches) atomicAdd(&c[C_CLAUSE_FETCH], fetches);
+            if (bytes) atomicAdd(&c[C_BYTES], bytes);
+            if (n_ok) atomicAdd(&c[C_OK], (unsigned long long)n_ok);
+            if (n_conf) atomicAdd(&c[C_CONFLICT], (unsigned long long)n_conf);
+            if (n_skip) atomicAdd(&c[C_SKIPPED], (unsigned long long)n_skip);
+        }
+    }
+};
+
+// Commit one round of candidate implications (one candidate literal per lane, 0 = none). Warp-converged.
+// Returns 0 ok, 1 conflict, 2 state overflow.
+template <class S>
+__device__ __forceinline__ int commit(S &st, uint32_t cand, uint32_t &tail)
+{
+    const bool has = cand != 0;
+    // same literal implied by several clauses in this step: keep the lowest lane (deterministic trail order)
+    const unsigned same = __match_any_sync(FULL, has ? cand : (0x80000000u | (uint32_t)lane_id()));
+    const bool leader = has && (lane_id() == __ffs(same) - 1);
+    uint32_t slot = 0;
+    const int r = leader ? st.insert(cand, slot) : 1;
+    const bool any_conf = __any_sync(FULL, r == 2);
+    const unsigned newm = __ballot_sync(FULL, leader && r == 0);
+    const uint32_t nnew = __popc(newm);
+    if (tail + nnew > st.cap) return 2;  // caller wipes the whole table: the new entries are not on the trail
+    if (leader && r == 0) st.tset(tail + __popc(newm & lanemask_lt()), cand, slot);
+    tail += nnew;
+    return any_conf ? 1 : 0;
+}
+
+// Judge a long clause (>= 4 literals) from scratch: TopiBcp.cc:262-367 without the watch bookkeeping.
+// Returns the literal to imply (0 = none); sets confl when every literal is false.
+template <class S>
+__device__ __forceinline__ uint32_t visit_long(const DbView &db, const S &st, uint32_t cref, bool &confl, uint32_t &units16)
+{
+    const uint4 *cp = db.arena + cref;
+    uint4 w = __ldg(cp);
+    const uint32_t size = w.x;
+    uint32_t nfree = 0, cand = 0, i = 0;
+    bool sat = false;
+    units16 = 1;
+    uint32_t l[4] = {w.y, w.z, w.w, 0};
+    int have = 3;
+    for (;;) {
+        for (int k = 0; k < have && i < size; ++k, ++i) {
+            const int v = st.lookup(l[k]);
+            if (v == 1) { sat = true; break; }
+            if (v == 0) { ++nfree; cand = l[k]; }
+        }
+        if (sat || nfree >= 2 || i >= size) break;
+        w = __ldg(++cp);
+        ++units16;
+        l[0] = w.x; l[1] = w.y; l[2] = w.z; l[3] = w.w;
+        have = 4;
+    }
+    if (sat || nfree >= 2) return 0;
+    if (nfree == 0) { confl = true; return 0; }
+    return cand;
+}
+
+// Breadth-first unit propagation of trail[0..tail) to fixpoint. Returns 0 fixpoint, 1 conflict, 2 overflow.
+template <class S>
+__device__ int propagate(const DbView &db, S &st, uint32_t &tail, bool prune, WarpCounters &wc)
+{
+    const int lane = lane_id();
+    uint32_t head = 0;
+    while (head < tail) {
+        const uint32_t B = min(32u, tail - head);
+        const uint32_t p = lane < (int)B ? st.tget(head + lane) : 0u;
+        uint4 hd = make_uint4(0, 0, 0, 0);
+        if (lane < (int)B) hd = __ldg(&db.hdr[p ^ 1u]);
+        // while a single literal is assigned only binary clauses can become unit
+        const bool bins_only = prune && tail == 1;
+        const uint32_t nb2 = (hd.y + 1u) >> 1;
+        const uint32_t cnt = bins_only ? nb2 : nb2 + hd.z + hd.w;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t excl = incl - cnt;
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        wc.props_all += B;
+        wc.props_ref += __popc(__ballot_sync(FULL, (hd.y | hd.z | hd.w) != 0));
+        wc.slots += total;
+        wc.bytes += 16ull * B + 8ull * total;
+
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t g = base + lane;
+            const bool active = g < total;
+            // owner row of slot g: the largest lane i with excl_i <= g
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const int mid = lo + step;
+                const uint32_t e = __shfl_sync(FULL, excl, mid & 31);
+                if (mid < 32 && e <= g) lo = mid;
+            }
+            const uint32_t r_start = __shfl_sync(FULL, hd.x, lo);
+            const uint32_t r_nb2 = (__shfl_sync(FULL, hd.y, lo) + 1u) >> 1;
+            const uint32_t r_nt = __shfl_sync(FULL, hd.z, lo);
+            const uint32_t k = g - __shfl_sync(FULL, excl, lo);
+            uint32_t c0 = 0, c1 = 0;
+            bool confl = false;
+            uint32_t fetched16 = 0;
+            if (active) {
+                const uint2 s = __ldg(&db.slots[r_start + k]);
+                if (k < r_nb2) {
+                    // binary clauses (TopiBcp.cc:207-246)
+                    int v = st.lookup(s.x);
+                    if (v == 0) c0 = s.x; else if (v == 2) confl = true;
+                    if (s.y) {
+                        v = st.lookup(s.y);
+                        if (v == 0) c1 = s.y; else if (v == 2) confl = true;
+                    }
+                } else if (k < r_nb2 + r_nt) {
+                    // inline ternary clause (falsified literal, s.x, s.y)
+                    const int va = st.lookup(s.x);
+                    if (va != 1) {
+                        const int vb = st.lookup(s.y);
+                        if (vb != 1) {
+                            if (va == 2 && vb == 2) confl = true;
+                            else if (va == 2) c0 = s.y;
+                            else if (vb == 2) c0 = s.x;
+                        }
+                    }
+                } else {
+                    // long clause: cached literal first (TopiBcp.cc:255-259), then the clause itself
+                    if (st.lookup(s.x) != 1) c0 = visit_long(db, st, s.y, confl, fetched16);
+                }
+            }
+            const unsigned fm = __ballot_sync(FULL, fetched16 != 0);
+            if (fm) {
+                uint32_t f = fetched16;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) f += __shfl_xor_sync(FULL, f, d);
+                wc.fetches += __popc(fm);
+                wc.bytes += 16ull * f;
+            }
+            if (__any_sync(FULL, confl)) return 1;
+            if (__any_sync(FULL, c0 != 0)) {
+                const int r = commit(st, c0, tail);
+                if (r) return r;
+            }
+            if (__any_sync(FULL, c1 != 0)) {
+                const int r = commit(st, c1, tail);
+                if (r) return r;
+            }
+            __syncwarp();
+        }
+        head += B;
+    }
+    return 0;
+}
+
+// Load a cube into the (empty) state with the semantics of HandleAssumptions (Topi.cc:797-938).
+// Returns the flag to report if the cube is decided here (2,3,4 or 1), FLAG_OVERFLOW, or 0xff = propagate.
+template <class S>
+__device__ int load_cube(const DbView &db, S &st, const int32_t *lits, uint32_t n, uint32_t &tail)
+{
+    const int lane = lane_id();
+    bool unmapped = false, false_l0 = false, conflict = false, overflow = false;
+    tail = 0;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t cand = 0;
+        if (i < n) {
+            const int32_t l = lits[i];
+            const uint32_t v = (uint32_t)(l < 0 ? -l : l);
+            if (l != 0) {
+                const uint8_t vi = (int32_t)v <= db.max_var ? db.varinfo[v] : 0;
+                if (!(vi & 4)) unmapped = true;
+                else if ((vi & 3) == 0) cand = 2u * v + (l < 0);
+                else if (((vi & 3) == 1) == (l < 0)) false_l0 = true;  // var true & negative literal, or var false & positive
+            }
+        }
+        if (!overflow && !conflict) {
+            const int r = commit(st, cand, tail);
+            if (r == 1) conflict = true;
+            if (r == 2) overflow = true;
+        }
+        __syncwarp();
+    }
+    if (overflow) { st.wipe(); tail = 0; }
+    if (__any_sync(FULL, unmapped)) return FLAG_UNMAPPED;
+    if (__any_sync(FULL, false_l0)) return FLAG_FALSE_L0;
+    if (overflow) return FLAG_OVERFLOW;
+    if (conflict) return FLAG_CONFLICT;
+    if (tail == 0) return FLAG_TRIVIAL_L0;
+    return 0xff;
+}
+
+// warp bitonic sort of a[0..n2) ascending, n2 a power of two (shared or global memory)
+__device__ void bitonic_sort(uint32_t *a, uint32_t n2)
+{
+    const int lane = lane_id();
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = lane; t < n2 / 2; t += 32) {
+                // t-th compare-exchange pair of this stage
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t ixj = i | j;
+                const bool up = (i & k) == 0;
+                const uint32_t x = a[i], y = a[ixj];
+                if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// allocate `count` output literals for this warp (uniform); returns ~0 if the buffer is full
+__device__ __forceinline__ unsigned long long out_alloc(const BatchView &b, uint32_t count)
+{
+    unsigned long long base = 0;
+    if (lane_id() == 0) base = atomicAdd(b.out_cursor, (unsigned long long)count);
+    base = __shfl_sync(FULL, base, 0);
+    return base + count <= b.out_cap ? base : ~0ull;
+}
+
+__device__ __forceinline__ void mark_failed(const BatchView &b, uint32_t ilit)
+{
+    atomicOr(&b.failed[ilit >> 5], 1u << (ilit & 31));
+    atomicOr(&b.unit[(ilit ^ 1u) >> 5], 1u << ((ilit ^ 1u) & 31));
+}
+
+struct Item {
+    const int32_t *lits;
+    uint32_t n;
+    int32_t probe_lit;  // probe mode: the single literal (lits == nullptr)
+};
+
+__device__ __forceinline__ Item get_item(const BatchView &b, uint64_t item)
+{
+    Item it;
+    if (b.cube_off) {
+        const uint64_t o = b.cube_off[item];
+        it.lits = b.cube_lits + o;
+        it.n = (uint32_t)(b.cube_off[item + 1] - o);
+        it.probe_lit = 0;
+    } else {
+        const uint64_t idx = b.first + item;
+        const int32_t v = (int32_t)(idx / 2 + 1);
+        it.probe_lit = (idx & 1) ? -v : v;
+        it.lits = nullptr;
+        it.n = 1;
+    }
+    return it;
+}
+
+// load_cube for probe mode (a single literal, no memory to read)
+template <class S>
+__device__ int load_probe(const DbView &db, S &st, int32_t l, uint32_t &tail)
+{
+    const uint32_t v = (uint32_t)(l < 0 ? -l : l);
+    const uint8_t vi = (int32_t)v <= db.max_var ? db.varinfo[v] : 0;
+    tail = 0;
+    if (!(vi & 4)) return FLAG_UNMAPPED;
+    if ((vi & 3) != 0) return (((vi & 3) == 1) == (l < 0)) ? FLAG_FALSE_L0 : FLAG_TRIVIAL_L0;
+    const int r = commit(st, lane_id() == 0 ? 2u * v + (l < 0) : 0u, tail);
+    __syncwarp();
+    return r == 2 ? FLAG_OVERFLOW : 0xff;
+}
+
+// ---------------------------------------------------------------- first tier: shared-memory state
+__device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, const Item &it, int res, uint32_t tail,
+                             WarpCounters &wc)
+{
+    const int lane = lane_id();
+    if (res == 2) st.wipe(); else st.cleanup(tail);
+    uint8_t flag;
+    uint32_t len = 0;
+    unsigned long long off = 0;
+    if (res == 2) {
+        flag = FLAG_OVERFLOW;
+        if (lane == 0) b.overflow_list[atomicAdd(b.overflow_count, 1u)] = (uint32_t)item;
+    } else if (res == 1) {
+        flag = FLAG_CONFLICT;
+        if (!b.cube_off && lane == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
+    } else {
+        flag = FLAG_OK;
+        if (b.opts & OPT_IMPLIED) {
+            uint32_t n2 = 1;
+            while (n2 < tail) n2 <<= 1;
+            for (uint32_t i = tail + lane; i < n2; i += 32) st.trail[i] = 0xffffffffu;
+            __syncwarp();
+            if (tail > 1) bitonic_sort(st.trail, n2);
+            off = out_alloc(b, tail);
+            if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
+            else {
+                len = tail;
+                for (uint32_t i = lane; i < tail; i += 32) b.out_lits[off + i] = to_ext(st.trail[i]);
+                wc.bytes += 4ull * tail;
+            }
+        }
+    }
+    if (lane == 0) { b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off; }
+    wc.n_ok += flag == FLAG_OK;
+    wc.n_conf += flag == FLAG_CONFLICT;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(SMALL_WARPS * 32)
+k_small(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t cap)
+{
+    extern __shared__ uint32_t smem[];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t hs = 1u << log_hs;
+    const uint32_t per_warp = hs + cap + cap / 2;  // words: hash, trail, tslot (u16)
+    SmemState st;
+    st.hash = smem + warp * per_warp;
+    st.trail = st.hash + hs;
+    st.tslot = reinterpret_cast<uint16_t *>(st.trail + cap);
+    st.log_hs = log_hs;
+    st.cap = cap;
+    for (uint32_t i = lane; i < hs; i += 32) st.hash[i] = 0;
+    __syncwarp();
+
+    const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
+    const bool probe_mode = b.cube_off == nullptr;
+    WarpCounters wc;
+    for (;;) {
+        unsigned chunk = 0;
+        if (lane == 0) chunk = atomicAdd(b.ticket, 1u);
+        chunk = __shfl_sync(FULL, chunk, 0);
+        const uint64_t base = (uint64_t)chunk * 32;
+        if (base >= b.n) break;
+        const uint64_t item = base + lane;
+        const bool valid = item < b.n;
+        unsigned deep = __ballot_sync(FULL, valid);
+        if (probe_mode) {
+            // triage, one probe per lane: consecutive probes read consecutive row headers
+            const uint64_t idx = b.first + item;
+            const uint32_t v = (uint32_t)(idx / 2 + 1), neg = (uint32_t)(idx & 1);
+            uint8_t flag = 0xff;
+            bool shallow = false, nonempty = false;
+            if (valid) {
+                const uint8_t vi = db.varinfo[v];
+                if (!(vi & 4)) flag = FLAG_UNMAPPED;
+                else if ((vi & 3) != 0) flag = (((vi & 3) == 1) == (neg != 0)) ? FLAG_FALSE_L0 : FLAG_TRIVIAL_L0;
+                else if (prune) {
+                    const uint4 hd = __ldg(&db.hdr[(2u * v + neg) ^ 1u]);
+                    shallow = hd.y == 0;   // no binary clause on the negation: nothing can be implied
+                    nonempty = (hd.z | hd.w) != 0;
+                    if (shallow) flag = FLAG_OK;
+                }
+            }
+            const unsigned sm = __ballot_sync(FULL, shallow);
+            const unsigned decided = __ballot_sync(FULL, flag != 0xff);
+            wc.n_skip += __popc(__ballot_sync(FULL, flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED));
+            if (sm) {
+                // every shallow probe implies exactly itself
+                const uint32_t ns = __popc(sm);
+                wc.n_ok += ns;  // (an output-buffer overflow makes the host redo the batch)
+                wc.props_all += ns;
+                wc.props_ref += __popc(__ballot_sync(FULL, shallow && nonempty));
+                wc.bytes += 16ull * ns;
+                unsigned long long off = 0;
+                uint32_t len = 0;
+                if (b.opts & OPT_IMPLIED) {
+                    const unsigned long long o = out_alloc(b, ns);
+                    if (shallow) {
+                        if (o == ~0ull) flag = FLAG_OUT_OVERFLOW;
+                        else {
+                            off = o + __popc(sm & lanemask_lt());
+                            len = 1;
+                            b.out_lits[off] = neg ? -(int32_t)v : (int32_t)v;
+                        }
+                    }
+                    wc.bytes += 4ull * ns;
+                }
+                if (shallow) { b.len[item] = len; b.raw_off[item] = off; }
+            }
+            if (valid && flag != 0xff) {
+                b.flag[item] = flag;
+                if (!shallow) { b.len[item] = 0; b.raw_off[item] = 0; }
+            }
+            deep &= ~decided;
+        }
+        // warp-cooperative propagation of the remaining items of this chunk, one at a time
+        while (deep) {
+            const int j = __ffs(deep) - 1;
+            deep &= deep - 1;
+            const uint64_t it_idx = base + j;
+            const Item it = get_item(b, it_idx);
+            uint32_t tail = 0;
+            int f = probe_mode ? load_probe(db, st, it.probe_lit, tail) : load_cube(db, st, it.lits, it.n, tail);
+            int res;
+            if (f == 0xff) res = propagate(db, st, tail, prune, wc);
+            else if (f == FLAG_OVERFLOW) res = 2;
+            else if (f == FLAG_CONFLICT) res = 1;
+            else {
+                st.cleanup(tail);
+                if (lane == 0) { b.flag[it_idx] = (uint8_t)f; b.len[it_idx] = 0; b.raw_off[it_idx] = 0; }
+                ++wc.n_skip;
+                __syncwarp();
+                continue;
+            }
+            finish_small(b, st, it_idx, it, res, tail, wc);
+        }
+    }
+    wc.flush(b.counters);
+}
+
+// ---------------------------------------------------------------- second tier: global-slab state, any size
+__global__ void __launch_bounds__(LARGE_WARPS * 32)
+k_large(const DbView db, const BatchView b, const LargeState ls)
+{
+    const int lane = lane_id();
+    const uint32_t gw = blockIdx.x * LARGE_WARPS + (threadIdx.x >> 5);
+    GmemState st;
+    st.bits = ls.bits + (size_t)gw * db.nvars_words16;
+    st.trail = ls.trail + (size_t)gw * ((size_t)db.max_var + 1);
+    st.cap = (uint32_t)db.max_var + 1;
+    const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
+    const bool probe_mode = b.cube_off == nullptr;
+    WarpCounters wc;
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(b.ticket, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= b.nwork) break;
+        const uint64_t item = b.worklist ? b.worklist[t] : t;
+        const Item it = get_item(b, item);
+        uint32_t tail = 0;
+        int f = probe_mode ? load_probe(db, st, it.probe_lit, tail) : load_cube(db, st, it.lits, it.n, tail);
+        int res = 0;
+        if (f == 0xff) res = propagate(db, st, tail, prune, wc);
+        else if (f == FLAG_CONFLICT) res = 1;
+        uint8_t flag = (uint8_t)f;
+        uint32_t len = 0;
+        unsigned long long off = 0;
+        if (f == 0xff || f == FLAG_CONFLICT) {
+            if (res == 1) {
+                flag = FLAG_CONFLICT;
+                if (probe_mode && lane == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
+            } else {
+                flag = FLAG_OK;
+                if (b.opts & OPT_IMPLIED) {
+                    off = out_alloc(b, tail);
+                    if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
+                    else {
+                        // ordered emission: sweep the dense assignment between the smallest and largest assigned var
+                        len = tail;
+                        uint32_t vmin = 0xffffffffu, vmax = 0;
+                        for (uint32_t i = lane; i < tail; i += 32) {
+                            const uint32_t var = st.tget(i) >> 1;
+                            vmin = min(vmin, var);
+                            vmax = max(vmax, var);
+                        }
+#pragma unroll
+                        for (int d = 16; d; d >>= 1) {
+                            vmin = min(vmin, __shfl_xor_sync(FULL, vmin, d));
+                            vmax = max(vmax, __shfl_xor_sync(FULL, vmax, d));
+                        }
+                        unsigned long long w = off;
+                        for (uint32_t wbase = vmin >> 4; wbase <= (vmax >> 4); wbase += 32) {
+                            const uint32_t wi = wbase + lane;
+                            const uint32_t word = wi <= (vmax >> 4) ? __ldcg(&st.bits[wi]) : 0u;
+                            const uint32_t nz = (word | (word >> 1)) & 0x55555555u;  // one bit per assigned var
+                            const uint32_t c = __popc(nz);
+                            uint32_t incl = c;
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const uint32_t x = __shfl_up_sync(FULL, incl, d);
+                                if (lane >= d) incl += x;
+                            }
+                            unsigned long long o = w + (incl - c);
+                            uint32_t m = nz;
+                            while (m) {
+                                const int bpos = __ffs(m) - 1;
+                                m &= m - 1;
+                                const uint32_t var = wi * 16u + (uint32_t)(bpos >> 1);
+                                const bool isneg = ((word >> bpos) & 3u) == 2u;
+                                b.out_lits[o++] = isneg ? -(int32_t)var : (int32_t)var;
+                            }
+                            w += __shfl_sync(FULL, incl, 31);
+                        }
+                        wc.bytes += 4ull * tail + 4ull * ((vmax >> 4) - (vmin >> 4) + 1);
+                    }
+                }
+            }
+        }
+        st.cleanup(tail);
+        if (lane == 0) {
+            b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
+            atomicAdd(&b.counters[C_LARGE], 1ull);
+        }
+        wc.n_ok += flag == FLAG_OK;
+        wc.n_conf += flag == FLAG_CONFLICT;
+        wc.n_skip += flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED;
+        __syncwarp();
+    }
+    wc.flush(b.counters);
+}
+
+// ---------------------------------------------------------------- result compaction into canonical CSR order
+__global__ void k_gather(const BatchView b, const uint64_t *__restrict__ off, int32_t *__restrict__ dst)
+{
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = lane_id();
+    // short segments: one item per lane; long ones: the warp copies together
+    for (uint64_t base = warp * 32; base < b.n; base += nwarps * 32) {
+        const uint64_t item = base + lane;
+        uint32_t len = 0;
+        uint64_t src = 0, d = 0;
+        if (item < b.n) { len = b.len[item]; src = b.raw_off[item]; d = off[item]; }
+        if (len && len <= 4) {
+            for (uint32_t i = 0; i < len; ++i) dst[d + i] = b.out_lits[src + i];
+        }
+        unsigned big = __ballot_sync(FULL, len > 4);
+        while (big) {
+            const int j = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t l = __shfl_sync(FULL, len, j);
+            const uint64_t s = __shfl_sync(FULL, src, j), dd = __shfl_sync(FULL, d, j);
+            for (uint32_t i = lane; i < l; i += 32) dst[dd + i] = b.out_lits[s + i];
+        }
+    }
+}
+
+}  // namespace
+
+size_t small_smem_bytes(uint32_t cap)
+{
+    const uint32_t hs = 2 * cap;
+    return (size_t)SMALL_WARPS * (hs + cap + cap / 2) * 4;
+}
+
+static uint32_t ilog2(uint32_t x) { uint32_t l = 0; while ((1u << l) < x) ++l; return l; }
+
+int small_blocks_per_sm(uint32_t cap)
+{
+    int nb = 0;
+    cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(cap));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_small, SMALL_WARPS * 32, small_smem_bytes(cap));
+    return nb;
+}
+
+void launch_small(const DbView &db, const BatchView &b, uint32_t cap, int blocks, cudaStream_t s)
+{
+    const size_t smem = small_smem_bytes(cap);
+    cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_small<<<blocks, SMALL_WARPS * 32, smem, s>>>(db, b, ilog2(2 * cap), cap);
+}
+
+void launch_large(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s)
+{
+    k_large<<<blocks, LARGE_WARPS * 32, 0, s>>>(db, b, ls);
+}
+
+void launch_gather(const BatchView &b, const uint64_t *off, int32_t *dst, cudaStream_t s)
+{
+    const uint64_t warps = (b.n + 31) / 32;
+    int blocks = (int)((warps + 7) / 8);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_gather<<<blocks, 256, 0, s>>>(b, off, dst);
+}
+
+}  // namespace bbcp

@@ -1,6 +1,6 @@
-"""Binary file formats shared by the engine's tools, the bench and the oracle-side checkers.
+"""Binary file formats shared by the engine's tools, the bench and the test-side checkers.
 
-Formats (little-endian), mirrored in ``oracle/bcp_io.h``:
+Formats (little-endian; the test-side C tools read and write the same ones):
 
 * instance ``.bcnf``: u64 magic "BCNF0001", u64 nvars_hint, u64 nclauses, u64 nwords, i32 words[nwords]
   (clauses, each 0-terminated)

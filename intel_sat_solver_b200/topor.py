@@ -1,0 +1,210 @@
+"""Host-side mirror of the reference's public facade for the batched-BCP path.
+
+``BatchedTopor`` keeps the method names, argument meaning and value conventions of the reference's ``CTopor``
+(``Topor.hpp:26-121``) for the subset that sits on this path -- ``AddClause`` / ``Solve(assumps)`` /
+``GetLitValue`` / ``GetLitDecLevel`` / ``Backtrack`` / ``IsError`` / ``GetStatusExplanation`` /
+``GetPropagations`` -- and adds the batch entry points the GPU engine exists for (``ProbeAll``,
+``ProbeRange``, ``PropagateBatch``). Every call goes through the C ABI of ``include/bbcp.h`` (ctypes); no
+propagation is done in Python or on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import enum
+
+import numpy as np
+
+from . import _lib
+from ._lib import BatchInfo, DbInfo, Opts
+
+OPT_IMPLIED = 1
+OPT_NO_LEN_PRUNE = 2
+
+
+class TToporReturnVal(enum.IntEnum):
+    """ToporExternalTypes.hpp:52-78 (the values this path can produce)."""
+    RET_SAT = 0
+    RET_UNSAT = 1
+    RET_USER_INTERRUPT = 5   # fixpoint reached, search not run (what SetCbStopNow->VAL_STOP yields in the reference)
+    RET_EXOTIC_ERROR = 10
+
+
+class TToporLitVal(enum.IntEnum):
+    """ToporExternalTypes.hpp:81-87."""
+    VAL_SATISFIED = 0
+    VAL_UNSATISFIED = 1
+    VAL_UNASSIGNED = 2
+    VAL_DONT_CARE = 3
+
+
+class BbcpError(RuntimeError):
+    pass
+
+
+@dataclasses.dataclass
+class BatchResult:
+    info: dict
+    flag: np.ndarray | None = None       # u8[n]
+    impl_off: np.ndarray | None = None   # u64[n+1]
+    impl_lits: np.ndarray | None = None  # i32[impl_off[n]] external literals sorted by |var| per set
+
+    def implied(self, i: int) -> np.ndarray:
+        return self.impl_lits[int(self.impl_off[i]): int(self.impl_off[i + 1])]
+
+
+class BatchedTopor:
+    def __init__(self, varsNumHint: int = 0, device: int | None = None):
+        self._L = _lib.load()
+        self._h = self._L.bbcp_create(int(varsNumHint))
+        if not self._h:
+            raise BbcpError("bbcp_create failed")
+        if device is not None:
+            self._L.bbcp_set_device(self._h, int(device))
+        self._assumps: list[int] = []
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.bbcp_release(h)
+
+    # ---- CTopor-shaped surface -------------------------------------------------------------------------
+    def AddClause(self, lits) -> None:
+        """Topor.hpp:33-38: the span may be 0-terminated; reading stops at the first 0."""
+        a = np.ascontiguousarray(lits, dtype=np.int32)
+        self._L.bbcp_add_clause(self._h, a.ctypes.data, a.size)
+
+    def AddClauses(self, words: np.ndarray) -> None:
+        """Bulk form: one int32 stream of 0-terminated clauses."""
+        a = np.ascontiguousarray(words, dtype=np.int32)
+        self._check(self._L.bbcp_add_clauses(self._h, a.ctypes.data, a.size))
+
+    def Finalize(self) -> int:
+        rc = self._L.bbcp_finalize(self._h)
+        if rc < 0:
+            raise BbcpError(self.GetStatusExplanation())
+        return rc
+
+    def Solve(self, assumps=()) -> TToporReturnVal:
+        """Topor.hpp:48 restricted to propagation: RET_UNSAT iff unit propagation of the assumptions derives a
+        conflict, RET_SAT iff every variable got assigned, else RET_USER_INTERRUPT (fixpoint, no search)."""
+        for l in assumps:
+            if l == 0:
+                break
+            self._L.bbcp_assume(self._h, int(l))
+        r = self._L.bbcp_solve(self._h)
+        if self._L.bbcp_status(self._h) < 0:
+            return TToporReturnVal.RET_EXOTIC_ERROR
+        return {20: TToporReturnVal.RET_UNSAT, 10: TToporReturnVal.RET_SAT}.get(r, TToporReturnVal.RET_USER_INTERRUPT)
+
+    def GetLitValue(self, l: int) -> TToporLitVal:
+        v = self._L.bbcp_val(self._h, int(l))
+        return {1: TToporLitVal.VAL_SATISFIED, -1: TToporLitVal.VAL_UNSATISFIED, 0: TToporLitVal.VAL_UNASSIGNED}.get(v, TToporLitVal.VAL_DONT_CARE)
+
+    def GetLitDecLevel(self, l: int) -> int:
+        return self._L.bbcp_declevel(self._h, int(l))
+
+    def Backtrack(self, decLevel: int) -> None:
+        self._L.bbcp_backtrack(self._h, int(decLevel))
+
+    def IsError(self) -> bool:
+        return self._L.bbcp_status(self._h) < 0
+
+    def GetStatusExplanation(self) -> str:
+        return self._L.bbcp_error_string(self._h).decode()
+
+    def GetPropagations(self) -> int:
+        return self._L.bbcp_propagations(self._h)
+
+    # ---- batch surface ------------------------------------------------------------------------------------
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise BbcpError(f"bbcp error {rc}: {self.GetStatusExplanation()}")
+        return rc
+
+    @staticmethod
+    def _opts(implied=True, small_trail=0, out_capacity=0, no_len_prune=False) -> Opts:
+        return Opts((OPT_IMPLIED if implied else 0) | (OPT_NO_LEN_PRUNE if no_len_prune else 0), small_trail, out_capacity)
+
+    def _fetch(self, info: BatchInfo, implied: bool, fetch: bool) -> BatchResult:
+        res = BatchResult(info.as_dict())
+        if fetch:
+            res.flag = np.empty(info.n, dtype=np.uint8)
+            self._check(self._L.bbcp_fetch_flags(self._h, res.flag.ctypes.data))
+            if implied:
+                res.impl_off = np.empty(info.n + 1, dtype=np.uint64)
+                res.impl_lits = np.empty(max(info.n_implied, 1), dtype=np.int32)
+                self._check(self._L.bbcp_fetch_implied(self._h, res.impl_off.ctypes.data, res.impl_lits.ctypes.data))
+                res.impl_lits = res.impl_lits[: info.n_implied]
+        return res
+
+    def ProbeRange(self, first: int, last: int, implied=True, fetch=True, **kw) -> BatchResult:
+        info = BatchInfo()
+        o = self._opts(implied=implied, **kw)
+        self._check(self._L.bbcp_probe_range(self._h, first, last, C.byref(o), C.byref(info)))
+        return self._fetch(info, implied, fetch)
+
+    def ProbeAll(self, implied=True, fetch=True, **kw) -> BatchResult:
+        return self.ProbeRange(0, 2 * self.max_var, implied=implied, fetch=fetch, **kw)
+
+    def PropagateBatch(self, cube_lits, cube_off, implied=True, fetch=True, **kw) -> BatchResult:
+        lits = np.ascontiguousarray(cube_lits, dtype=np.int32)
+        off = np.ascontiguousarray(cube_off, dtype=np.uint64)
+        if lits.size == 0:
+            lits = np.zeros(1, dtype=np.int32)
+        info = BatchInfo()
+        o = self._opts(implied=implied, **kw)
+        self._check(self._L.bbcp_propagate_batch(self._h, lits.ctypes.data, off.ctypes.data, off.size - 1, C.byref(o), C.byref(info)))
+        return self._fetch(info, implied, fetch)
+
+    def Bitmaps(self) -> tuple[np.ndarray, np.ndarray]:
+        n = self._L.bbcp_bitmap_words(self._h)
+        failed, unit = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        self._check(self._L.bbcp_fetch_bitmaps(self._h, failed.ctypes.data, unit.ctypes.data))
+        return failed, unit
+
+    def ClearBitmaps(self) -> None:
+        self._check(self._L.bbcp_clear_bitmaps(self._h))
+
+    def FailedLiterals(self) -> np.ndarray:
+        """External literals whose depth-1 probe hit a conflict, ascending |var| (positive before negative)."""
+        failed, _ = self.Bitmaps()
+        bits = np.unpackbits(failed.view(np.uint8), bitorder="little")
+        il = np.nonzero(bits)[0]
+        return np.where(il & 1, -(il >> 1), il >> 1).astype(np.int32)
+
+    def Level0(self) -> np.ndarray:
+        n = self._L.bbcp_level0_lits(self._h, None, 0)
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        self._L.bbcp_level0_lits(self._h, out.ctypes.data, n)
+        return out[:n]
+
+    def DbInfo(self) -> dict:
+        d = DbInfo()
+        self._L.bbcp_get_db_info(self._h, C.byref(d))
+        return d.as_dict()
+
+    @property
+    def max_var(self) -> int:
+        return self.DbInfo()["max_var"]
+
+    @property
+    def status(self) -> int:
+        return self._L.bbcp_status(self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def lib(self):
+        return self._L
+
+    def HostPrepare(self) -> int:
+        return self._L.bbcp_host_prepare(self._h)
+
+    def HostRow(self, ilit: int) -> np.ndarray:
+        n = self._L.bbcp_host_row(self._h, ilit, None, 0)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self._L.bbcp_host_row(self._h, ilit, out.ctypes.data, n)
+        return out[:n]

@@ -1,0 +1,177 @@
+"""GPU parity tests (run with -m gpu on the B200 box). Everything goes through the C ABI (ctypes ->
+libbbcp.so -> CUDA kernels) and is compared bit-exactly with
+  * the committed golden vectors produced by the reference's own CTopi::BCP() (tests/golden/), and
+  * the checker binary run live on seeded synthetic instances of the BASELINE.json shapes
+    (oracle/_ref/ref_bcp = the reference itself when it travelled with the snapshot, else the C port).
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from intel_sat_solver_b200 import BatchedTopor, TToporLitVal, TToporReturnVal, fileio
+import gpu_util
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_for(words):
+    t = BatchedTopor()
+    t.AddClauses(words)
+    rc = t.Finalize()
+    return t, rc
+
+
+def test_all_goldens_probe_and_cube_parity(golden, golden_names):
+    n_probe = n_failed = n_cube = 0
+    for name in golden_names:
+        g = lambda k: golden[f"{name}/{k}"]
+        t, rc = engine_for(g("words"))
+        assert rc == int(g("status")[0]), name
+        if rc:
+            # sticky contradictory status: batches are refused with the same code (Topi.cc:182, 449, 1015)
+            assert t.lib.bbcp_probe_all(t.handle, None, None) == 1 and t.Solve([1]) == TToporReturnVal.RET_UNSAT
+            continue
+        assert np.array_equal(t.Level0(), g("level0")), name
+        res = t.ProbeAll()
+        gpu_util.assert_same_results(res, g("probe_flag"), g("probe_off"), g("probe_lits"), name + " probes")
+        # failed-literal set == the probes flagged 1
+        idx = np.nonzero(g("probe_flag") == 1)[0]
+        expect_failed = np.where(idx & 1, -(idx // 2 + 1), idx // 2 + 1).astype(np.int32)
+        assert sorted(t.FailedLiterals().tolist(), key=lambda l: (abs(l), l < 0)) == sorted(expect_failed.tolist(), key=lambda l: (abs(l), l < 0)), name
+        failed, unit = t.Bitmaps()
+        fb = np.unpackbits(failed.view(np.uint8), bitorder="little")
+        ub = np.unpackbits(unit.view(np.uint8), bitorder="little")
+        il = np.nonzero(fb)[0]
+        assert np.array_equal(np.nonzero(ub)[0], np.sort(il ^ 1)), name
+        res = t.PropagateBatch(g("cube_lits"), g("cube_off"))
+        gpu_util.assert_same_results(res, g("cube_flag"), g("cube_impl_off"), g("cube_impl_lits"), name + " cubes")
+        assert res.info["n_ok"] + res.info["n_conflict"] + res.info["n_skipped"] == res.info["n"], name
+        n_probe += int((g("probe_flag") <= 1).sum()); n_failed += idx.size; n_cube += g("cube_flag").size
+    assert n_probe > 14000 and n_failed >= 77 and n_cube > 5000
+
+
+def test_regression_corpus_totals(golden, golden_names):
+    """4,694 valid probes and 77 failed literals over regr_1..72."""
+    valid = failed = 0
+    for name in golden_names:
+        if not name.startswith("regr_"):
+            continue
+        t, rc = engine_for(golden[f"{name}/words"])
+        assert rc == 0
+        res = t.ProbeAll(implied=False)
+        valid += int((res.flag <= 1).sum())
+        failed += int((res.flag == 1).sum())
+        assert res.info["n_conflict"] == int((res.flag == 1).sum())
+    assert (valid, failed) == (4694, 77)
+
+
+@pytest.mark.parametrize("kw", [dict(small_trail=32), dict(no_len_prune=True), dict(out_capacity=64), dict(small_trail=32, out_capacity=16)])
+def test_option_variants_keep_results(golden, kw):
+    """Tiny shared-memory state (forces the global-state tier), no length pruning, and an implied-literal
+    buffer that overflows and regrows must all give the same bits."""
+    for name in ["regr_47", "regr_72", "fuzz_5", "fuzz_10", "hand_long", "hand_alias"]:
+        g = lambda k: golden[f"{name}/{k}"]
+        t, rc = engine_for(g("words"))
+        res = t.ProbeAll(**kw)
+        gpu_util.assert_same_results(res, g("probe_flag"), g("probe_off"), g("probe_lits"), f"{name} {kw}")
+        res = t.PropagateBatch(g("cube_lits"), g("cube_off"), **kw)
+        gpu_util.assert_same_results(res, g("cube_flag"), g("cube_impl_off"), g("cube_impl_lits"), f"{name} cubes {kw}")
+
+
+SHAPES = [
+    ("3sat", dict(n=20000, m=84000, seed=1), None),
+    ("aig", dict(frames=4, gates=3000, inputs=100, latches=100, window=300, seed=2), None),
+    ("comm", dict(n=20000, m=80000, comms=20, seed=3), dict(ncubes=2048, split=8, extra=12)),
+    ("plaw", dict(n=20000, m=80000, seed=5), None),
+]
+
+
+@pytest.mark.parametrize("kind,kw,cubekw", SHAPES, ids=[s[0] for s in SHAPES])
+def test_synthetic_shapes_against_checker(kind, kw, cubekw):
+    with tempfile.TemporaryDirectory() as d:
+        gkw = dict(kw)
+        if cubekw:
+            gkw.update(cubekw, cubes=os.path.join(d, "c.cubes"))
+        inst, _ = gpu_util.gen(kind, d, **gkw)
+        words = fileio.read_bcnf(inst)
+        t, rc = engine_for(words)
+        ref, _ = gpu_util.run_checker(inst)
+        assert rc == ref.status
+        res = t.ProbeAll()
+        gpu_util.assert_same_results(res, ref.flag, ref.off, ref.lits, kind)
+        # the reference counts a propagation only for literals whose negation ever had a row; on a
+        # non-conflicting probe that is order-independent up to rows allocated by watch moves, so only
+        # the looser invariant is asserted
+        assert res.info["props_all"] >= res.info["props_ref"] > 0
+        if cubekw:
+            import numpy as np
+            buf = np.fromfile(gkw["cubes"], dtype=np.uint64, count=3)
+            nc, nl = int(buf[1]), int(buf[2])
+            off = np.fromfile(gkw["cubes"], dtype=np.uint64, offset=24, count=nc + 1)
+            lits = np.fromfile(gkw["cubes"], dtype=np.int32, offset=24 + 8 * (nc + 1), count=nl)
+            cref, _ = gpu_util.run_checker(inst, gkw["cubes"])
+            res = t.PropagateBatch(lits, off)
+            gpu_util.assert_same_results(res, cref.flag, cref.off, cref.lits, kind + " cubes")
+        # the same instance through the tiny-state path (every deep probe takes the global-state tier)
+        res2 = t.ProbeAll(small_trail=32)
+        gpu_util.assert_same_results(res2, ref.flag, ref.off, ref.lits, kind + " tier2")
+        assert res2.info["n_large"] >= res.info["n_large"]
+
+
+def test_probe_range_shards_compose(golden):
+    g = lambda k: golden[f"fuzz_10/{k}"]
+    t, _ = engine_for(g("words"))
+    n = 2 * t.max_var
+    cuts = [0, n // 3, n // 3 + 1, n // 2, n]
+    flags, sizes, lits = [], [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        r = t.ProbeRange(a, b)
+        flags.append(r.flag); sizes.append(np.diff(r.impl_off)); lits.append(r.impl_lits)
+    assert np.array_equal(np.concatenate(flags), g("probe_flag"))
+    assert np.array_equal(np.concatenate(sizes), np.diff(g("probe_off")))
+    assert np.array_equal(np.concatenate(lits), g("probe_lits"))
+
+
+def test_topor_style_single_cube_api(golden):
+    """AddClause / Solve(assumps) / GetLitValue / GetLitDecLevel / Backtrack, checked against the golden
+    cube results (what the reference's public API yields with a stop callback, SURVEY.md 8c route B)."""
+    name = "regr_72"
+    g = lambda k: golden[f"{name}/{k}"]
+    words = g("words")
+    t = BatchedTopor()
+    cur = []
+    for w in words.tolist():
+        cur.append(w)
+        if w == 0:
+            t.AddClause(cur)
+            cur = []
+    level0 = set(g("level0").tolist())
+    off, lits, flag = g("cube_off"), g("cube_lits"), g("cube_flag")
+    ioff, ilits = g("cube_impl_off"), g("cube_impl_lits")
+    maxv = int(np.abs(words).max())
+    checked = 0
+    for i in range(min(flag.size, 40)):
+        cube = lits[int(off[i]):int(off[i + 1])].tolist()
+        if flag[i] == 4:
+            continue
+        r = t.Solve(cube)
+        if flag[i] in (1, 3):
+            assert r == TToporReturnVal.RET_UNSAT
+            continue
+        assert r in (TToporReturnVal.RET_USER_INTERRUPT, TToporReturnVal.RET_SAT)
+        implied = set(ilits[int(ioff[i]):int(ioff[i + 1])].tolist())
+        for v in range(1, maxv + 1):
+            val = t.GetLitValue(v)
+            if v in implied or v in level0:
+                assert val == TToporLitVal.VAL_SATISFIED
+                assert t.GetLitDecLevel(v) == (0 if v in level0 else 1)
+            elif -v in implied or -v in level0:
+                assert val == TToporLitVal.VAL_UNSATISFIED
+            else:
+                assert val in (TToporLitVal.VAL_UNASSIGNED, TToporLitVal.VAL_DONT_CARE)
+        t.Backtrack(0)
+        assert t.GetLitValue(next(iter(implied))) != TToporLitVal.VAL_SATISFIED if implied - level0 and not (set(map(abs, implied)) & set(map(abs, level0))) else True
+        checked += 1
+    assert checked > 10 and t.GetPropagations() > 0 and not t.IsError()

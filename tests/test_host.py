@@ -1,0 +1,162 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/bbcp.h declares; the
+clause normaliser and row builder agree with an independent Python model; the engine refuses to run
+without a CUDA device (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from intel_sat_solver_b200 import BatchedTopor, BbcpError, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "bbcp.h")).read()
+    declared = sorted(set(re.findall(r"\b(bbcp_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == _lib.exported_names()
+
+
+def py_normalise(words):
+    """Independent model of AddUserClause's observable result (Topi.cc:377-653)."""
+    unit_val, mapped, kept, contradictory = {}, set(), [], False
+    cur = []
+    for w in words.tolist():
+        if w != 0:
+            cur.append(w)
+            continue
+        clause, cur = cur, []
+        if contradictory:
+            continue
+        if not clause:
+            contradictory = True
+            continue
+        out, taut = [], False
+        fresh = [abs(l) for l in clause if abs(l) not in mapped]
+        seen_until = 0
+        for l in clause:
+            seen_until += 1
+            if unit_val.get(abs(l)) == -l // abs(l) * 1 and False:
+                pass
+            if abs(l) in unit_val and unit_val[abs(l)] != (l > 0):
+                continue
+            if l in out:
+                continue
+            if -l in out:
+                taut = True
+                break
+            out.append(l)
+        touched = {abs(l) for l in clause[:seen_until]}
+        if taut:
+            continue
+        mapped |= touched
+        if not out:
+            contradictory = True
+        elif len(out) == 1:
+            if abs(out[0]) not in unit_val:
+                unit_val[abs(out[0])] = out[0] > 0
+        else:
+            kept.append(out)
+    return kept, mapped, unit_val, contradictory
+
+
+def ilit(l):
+    return 2 * abs(l) + (l < 0)
+
+
+def check_rows(t, kept, max_var):
+    occ = {}
+    for c in kept:
+        for i, l in enumerate(c):
+            occ.setdefault(ilit(l), []).append((c, i))
+    for il in range(2, 2 * max_var + 2):
+        row = t.HostRow(il).tolist()
+        nbin, ntern, nlong = row[:3]
+        p = 3
+        bins = row[p:p + nbin]; p += nbin
+        terns = [tuple(row[p + 2 * i:p + 2 * i + 2]) for i in range(ntern)]; p += 2 * ntern
+        longs = []
+        for _ in range(nlong):
+            blocker, size = row[p], row[p + 1]
+            longs.append((blocker, tuple(row[p + 2:p + 2 + size])))
+            p += 2 + size
+        assert p == len(row)
+        exp_bins = sorted({ilit(c[1 - i]) for c, i in occ.get(il, []) if len(c) == 2})
+        assert bins == exp_bins, il
+        exp_terns = sorted(tuple(sorted(ilit(x) for k, x in enumerate(c) if k != i)) for c, i in occ.get(il, []) if len(c) == 3)
+        assert sorted(tuple(sorted(x)) for x in terns) == exp_terns, il
+        exp_longs = sorted((ilit(c[(i + 1) % len(c)]), tuple(ilit(x) for x in c)) for c, i in occ.get(il, []) if len(c) > 3)
+        assert sorted(longs) == exp_longs, il
+
+
+@pytest.mark.parametrize("name", ["regr_20", "regr_47", "regr_66", "hand_taut_dup", "hand_long", "hand_units", "hand_alias", "fuzz_3"])
+def test_normaliser_and_rows_match_python_model(golden, name):
+    words = golden[f"{name}/words"]
+    kept, mapped, unit_val, contradictory = py_normalise(words)
+    t = BatchedTopor()
+    t.AddClauses(words)
+    rc = t.HostPrepare()
+    assert (rc == 1) == contradictory
+    if contradictory:
+        return
+    info = t.DbInfo()
+    max_var = int(np.abs(words).max())
+    assert info["max_var"] == max_var
+    assert info["n_mapped_vars"] == len(mapped)
+    assert info["n_level0"] == len(unit_val)          # before level-0 propagation: the direct units only
+    assert info["n_tern"] == sum(len(c) == 3 for c in kept)
+    assert info["n_long"] == sum(len(c) > 3 for c in kept)
+    assert info["n_bin"] == len({frozenset(c) for c in kept if len(c) == 2})
+    check_rows(t, kept, max_var)
+
+
+@pytest.mark.parametrize("name,expect", [("hand_empty", 1), ("hand_unsat_units", 1), ("hand_units", 0)])
+def test_intake_contradictions(golden, name, expect):
+    t = BatchedTopor()
+    t.AddClauses(golden[f"{name}/words"])
+    assert t.HostPrepare() == expect
+
+
+def test_add_and_add_clause_agree_with_bulk():
+    words = np.array([1, -2, 3, 0, 2, 2, -4, 0, 5, 0, -5, 6, 7, 8, 0], dtype=np.int32)
+    a, b, c = BatchedTopor(), BatchedTopor(), BatchedTopor()
+    a.AddClauses(words)
+    for w in words.tolist():
+        b.lib.bbcp_add(b.handle, w)
+    cur = []
+    for w in words.tolist():
+        cur.append(w)
+        if w == 0:
+            c.AddClause(cur + [9, 9])  # reading stops at the first 0 (Topor.hpp:33-38)
+            cur = []
+    for t in (a, b, c):
+        assert t.HostPrepare() == 0
+    rows = [[t.HostRow(i).tolist() for i in range(2, 18)] for t in (a, b, c)]
+    assert rows[0] == rows[1] == rows[2]
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    t = BatchedTopor()
+    t.AddClause([1, 2, 0])
+    with pytest.raises(BbcpError):
+        t.Finalize()
+    assert t.IsError() and "CUDA" in t.GetStatusExplanation()
+    with pytest.raises(BbcpError):
+        t.ProbeAll()
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "intel_sat_solver_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in src.lower(), fn
