@@ -69,8 +69,8 @@ typedef struct {
     uint64_t kernel_bytes;     /* algorithmic bytes moved by the propagate kernels ("bytes model") */
     float kernel_ms;           /* device time of the propagate kernels of this call (CUDA events) */
     float total_ms;            /* device time of the whole call incl. result compaction */
-    uint32_t launches;         /* kernels launched by this call */
-    uint32_t reserved;
+    uint32_t launches;         /* kernels of this engine launched by the call (library scan kernels not counted) */
+    float tier1_ms;            /* device time of the first-tier propagate kernel alone (last attempt) */
 } bbcp_batch_info;
 
 typedef struct {

@@ -62,7 +62,7 @@ struct bbcp_handle {
     int sm_count = 148;
 
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
     DevBuf d_hdr, d_slots, d_arena, d_varinfo, d_failed, d_unit;
     uint64_t bitmap_words = 0;
@@ -209,7 +209,9 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         bi.launches = 0;
         if (n) {
             int blocks = (int)std::min<uint64_t>((uint64_t)bps * h->sm_count, (chunks + SMALL_WARPS - 1) / SMALL_WARPS);
+            cudaEventRecord(h->ev[3], h->stream);
             launch_small(dbv, b, cap, std::max(blocks, 1), h->stream);
+            cudaEventRecord(h->ev[4], h->stream);
             ++bi.launches;
         }
         cudaMemcpyAsync(h->h_misc, h->d_misc.p, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
@@ -271,7 +273,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         cub::DeviceScan::ExclusiveSum(h->d_cubtmp.p, tmp, in, h->d_off.as<uint64_t>(), (int)n, h->stream);
         cudaMemcpyAsync(h->d_off.as<uint64_t>() + n, b.out_cursor, 8, cudaMemcpyDeviceToDevice, h->stream);
         launch_gather(b, h->d_off.as<uint64_t>(), h->d_impl.as<int32_t>(), h->stream);
-        bi.launches += 2;
+        bi.launches += 1;  // (the scan is two library kernels, not counted)
     } else {
         cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
     }
@@ -279,6 +281,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "batch")) return BBCP_ERR_CUDA;
     cudaEventElapsedTime(&bi.kernel_ms, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&bi.total_ms, h->ev[0], h->ev[2]);
+    if (n) cudaEventElapsedTime(&bi.tier1_ms, h->ev[3], h->ev[4]);
     h->last_n = n;
     h->last_n_implied = bi.n_implied;
     h->have_batch = true;

@@ -356,7 +356,7 @@ __device__ __forceinline__ void mark_failed(const BatchView &b, uint32_t ilit)
 struct Item {
     const int32_t *lits;
     uint32_t n;
-    int32_t probe_lit;  // probe mode: the single literal (lits == nullptr)
+    int32_t probe_lit;  // depth-1 item: its literal (0 otherwise)
 };
 
 __device__ __forceinline__ Item get_item(const BatchView &b, uint64_t item)
@@ -366,7 +366,7 @@ __device__ __forceinline__ Item get_item(const BatchView &b, uint64_t item)
         const uint64_t o = b.cube_off[item];
         it.lits = b.cube_lits + o;
         it.n = (uint32_t)(b.cube_off[item + 1] - o);
-        it.probe_lit = 0;
+        it.probe_lit = it.n == 1 ? it.lits[0] : 0;  // a depth-1 cube is a probe
     } else {
         const uint64_t idx = b.first + item;
         const int32_t v = (int32_t)(idx / 2 + 1);
@@ -405,7 +405,7 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
         if (lane == 0) b.overflow_list[atomicAdd(b.overflow_count, 1u)] = (uint32_t)item;
     } else if (res == 1) {
         flag = FLAG_CONFLICT;
-        if (!b.cube_off && lane == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
+        if (it.probe_lit && lane == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
     } else {
         flag = FLAG_OK;
         if (b.opts & OPT_IMPLIED) {
@@ -457,14 +457,24 @@ k_small(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_
         const uint64_t item = base + lane;
         const bool valid = item < b.n;
         unsigned deep = __ballot_sync(FULL, valid);
-        if (probe_mode) {
-            // triage, one probe per lane: consecutive probes read consecutive row headers
-            const uint64_t idx = b.first + item;
-            const uint32_t v = (uint32_t)(idx / 2 + 1), neg = (uint32_t)(idx & 1);
+        {
+            // triage, one depth-1 item per lane: consecutive probes read consecutive row headers
+            int32_t lit = 0;
+            if (valid) {
+                if (probe_mode) {
+                    const uint64_t idx = b.first + item;
+                    const int32_t pv = (int32_t)(idx / 2 + 1);
+                    lit = (idx & 1) ? -pv : pv;
+                } else {
+                    const uint64_t o = b.cube_off[item];
+                    if (b.cube_off[item + 1] - o == 1) lit = b.cube_lits[o];
+                }
+            }
+            const uint32_t v = (uint32_t)(lit < 0 ? -lit : lit), neg = lit < 0;
             uint8_t flag = 0xff;
             bool shallow = false, nonempty = false;
-            if (valid) {
-                const uint8_t vi = db.varinfo[v];
+            if (lit != 0) {
+                const uint8_t vi = (int32_t)v <= db.max_var ? db.varinfo[v] : 0;
                 if (!(vi & 4)) flag = FLAG_UNMAPPED;
                 else if ((vi & 3) != 0) flag = (((vi & 3) == 1) == (neg != 0)) ? FLAG_FALSE_L0 : FLAG_TRIVIAL_L0;
                 else if (prune) {
@@ -500,7 +510,7 @@ k_small(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_
                 }
                 if (shallow) { b.len[item] = len; b.raw_off[item] = off; }
             }
-            if (valid && flag != 0xff) {
+            if (flag != 0xff) {
                 b.flag[item] = flag;
                 if (!shallow) { b.len[item] = 0; b.raw_off[item] = 0; }
             }
@@ -513,7 +523,7 @@ k_small(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_
             const uint64_t it_idx = base + j;
             const Item it = get_item(b, it_idx);
             uint32_t tail = 0;
-            int f = probe_mode ? load_probe(db, st, it.probe_lit, tail) : load_cube(db, st, it.lits, it.n, tail);
+            int f = it.probe_lit ? load_probe(db, st, it.probe_lit, tail) : load_cube(db, st, it.lits, it.n, tail);
             int res;
             if (f == 0xff) res = propagate(db, st, tail, prune, wc);
             else if (f == FLAG_OVERFLOW) res = 2;
@@ -552,7 +562,7 @@ k_large(const DbView db, const BatchView b, const LargeState ls)
         const uint64_t item = b.worklist ? b.worklist[t] : t;
         const Item it = get_item(b, item);
         uint32_t tail = 0;
-        int f = probe_mode ? load_probe(db, st, it.probe_lit, tail) : load_cube(db, st, it.lits, it.n, tail);
+        int f = it.probe_lit ? load_probe(db, st, it.probe_lit, tail) : load_cube(db, st, it.lits, it.n, tail);
         int res = 0;
         if (f == 0xff) res = propagate(db, st, tail, prune, wc);
         else if (f == FLAG_CONFLICT) res = 1;
@@ -562,7 +572,7 @@ k_large(const DbView db, const BatchView b, const LargeState ls)
         if (f == 0xff || f == FLAG_CONFLICT) {
             if (res == 1) {
                 flag = FLAG_CONFLICT;
-                if (probe_mode && lane == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
+                if (it.probe_lit && lane == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
             } else {
                 flag = FLAG_OK;
                 if (b.opts & OPT_IMPLIED) {

@@ -21,7 +21,7 @@ int main(int argc, char **argv)
 {
     if (argc < 2) { fprintf(stderr, "usage: %s <instance> --out f [--probe-all|--cubes f] [--shard i n] [--stride k] [--flags-only]\n", argv[0]); return 2; }
     const char *out = NULL, *cubes_path = NULL;
-    uint64_t shard_i = 0, shard_n = 1, stride = 1;
+    uint64_t shard_i = 0, shard_n = 1, stride = 1, repeat = 1;
     int flags_only = 0;
     for (int i = 2; i < argc; ++i) {
         if (!strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
@@ -30,6 +30,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--shard") && i + 2 < argc) { shard_i = strtoull(argv[i + 1], 0, 10); shard_n = strtoull(argv[i + 2], 0, 10); i += 2; }
         else if (!strcmp(argv[i], "--stride") && i + 1 < argc) stride = strtoull(argv[++i], 0, 10);
         else if (!strcmp(argv[i], "--flags-only")) flags_only = 1;
+        else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = strtoull(argv[++i], 0, 10);
         else { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
     }
     bcp_instance ins;
@@ -50,19 +51,26 @@ int main(int argc, char **argv)
     orc_level0_lits(o, l0, nl0);
     const uint64_t impl0 = orc_implications(o), asg0 = orc_assignments(o);
     double seconds = 0;
+    char slist[4096] = "";
+    int slen = 0;
     uint64_t ran = 0, conflicts = 0;
     if (!status) {
         const uint64_t lo = n * shard_i / shard_n, hi = n * (shard_i + 1) / shard_n;
-        const double t0 = now_s();
-        orc_run_cubes(o, cubes_path ? cubes.lits : NULL, cubes.off, n, lo, hi, stride, flag, props, off, flags_only ? NULL : &lits);
-        seconds = now_s() - t0;
+        for (uint64_t rep = 0; rep < repeat; ++rep) {
+            if (lits) { orc_free(lits); lits = NULL; }
+            const double t0 = now_s();
+            orc_run_cubes(o, cubes_path ? cubes.lits : NULL, cubes.off, n, lo, hi, stride, flag, props, off, flags_only ? NULL : &lits);
+            seconds = now_s() - t0;
+            slen += snprintf(slist + slen, sizeof(slist) - slen, "%s%.6f", rep ? ", " : "", seconds);
+            if (slen > (int)sizeof(slist) - 32) break;
+        }
         for (uint64_t i = 0; i < n; ++i) { ran += flag[i] != 255; conflicts += flag[i] == BCP_FLAG_CONFLICT; }
     } else nl0 = 0;
     const uint64_t impl = orc_implications(o) - impl0, asg = orc_assignments(o) - asg0;
     if (out && bcp_write_results(out, n, (uint64_t)status, flag, props, off, lits, l0, nl0, impl, asg, seconds)) { fprintf(stderr, "cannot write %s\n", out); return 4; }
-    printf("{\"status\": %d, \"n\": %llu, \"ran\": %llu, \"conflicts\": %llu, \"implications\": %llu, \"assignments\": %llu, \"implied_lits\": %llu, \"level0\": %llu, \"delayed_triggers\": 0, \"seconds\": %.6f}\n",
+    printf("{\"status\": %d, \"n\": %llu, \"ran\": %llu, \"conflicts\": %llu, \"implications\": %llu, \"assignments\": %llu, \"implied_lits\": %llu, \"level0\": %llu, \"delayed_triggers\": 0, \"seconds\": %.6f, \"seconds_list\": [%s]}\n",
            status, (unsigned long long)n, (unsigned long long)ran, (unsigned long long)conflicts, (unsigned long long)impl,
-           (unsigned long long)asg, (unsigned long long)off[n], (unsigned long long)nl0, seconds);
+           (unsigned long long)asg, (unsigned long long)off[n], (unsigned long long)nl0, seconds, slist);
     orc_release(o);
     return 0;
 }

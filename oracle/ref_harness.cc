@@ -20,7 +20,7 @@
 // literal found falsified => UNSAT.
 //
 // usage: ref_bcp <instance(.cnf text | .bcnf)> --out <file.bres>
-//                [--probe-all | --cubes <file.cubes>] [--shard i n] [--stride k] [--flags-only]
+//                [--probe-all | --cubes <file.cubes>] [--shard i n] [--stride k] [--flags-only] [--repeat r]
 //        prints one JSON line with counts and the probe-loop wall time.
 
 #include <chrono>
@@ -170,7 +170,7 @@ int main(int argc, char** argv)
     if (argc < 2) { fprintf(stderr, "usage: %s <instance> --out f [--probe-all|--cubes f] [--shard i n] [--stride k] [--flags-only]\n", argv[0]); return 2; }
     const char* inst = argv[1];
     const char* out = nullptr; const char* cubesPath = nullptr;
-    uint64_t shardI = 0, shardN = 1, stride = 1; bool flagsOnly = false;
+    uint64_t shardI = 0, shardN = 1, stride = 1, repeat = 1; bool flagsOnly = false;
     for (int i = 2; i < argc; ++i)
     {
         string a = argv[i];
@@ -180,6 +180,7 @@ int main(int argc, char** argv)
         else if (a == "--shard" && i + 2 < argc) { shardI = strtoull(argv[++i], 0, 10); shardN = strtoull(argv[++i], 0, 10); }
         else if (a == "--stride" && i + 1 < argc) stride = strtoull(argv[++i], 0, 10);
         else if (a == "--flags-only") flagsOnly = true;
+        else if (a == "--repeat" && i + 1 < argc) repeat = strtoull(argv[++i], 0, 10);
         else { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
     }
 
@@ -213,32 +214,40 @@ int main(int argc, char** argv)
     const uint64_t impl0 = h.Implications(), asg0 = h.Assignments();
     double seconds = 0;
 
+    string secondsList;
     if (ok)
     {
         h.CollectLevel0(level0);
         const uint64_t lo = n * shardI / shardN, hi = n * (shardI + 1) / shardN;
-        auto t0 = chrono::steady_clock::now();
-        for (uint64_t i = 0; i < n; ++i)
+        // --repeat R: R timed passes over the same probes in one process (Backtrack(0) restores the state);
+        // the results written are those of the last pass, `seconds` is the last pass, all passes are listed
+        for (uint64_t rep = 0; rep < repeat; ++rep)
         {
-            off[i] = implied.size();
-            if (i < lo || i >= hi || (i - lo) % stride != 0) continue;
-            const uint64_t before = h.Implications();
-            if (cubesPath)
+            implied.clear(); ran = 0; conflicts = 0;
+            auto t0 = chrono::steady_clock::now();
+            for (uint64_t i = 0; i < n; ++i)
             {
-                flag[i] = h.RunCube(cubes.lits + cubes.off[i], cubes.off[i + 1] - cubes.off[i], implied, !flagsOnly, tmp);
+                off[i] = implied.size();
+                if (i < lo || i >= hi || (i - lo) % stride != 0) continue;
+                const uint64_t before = h.Implications();
+                if (cubesPath)
+                {
+                    flag[i] = h.RunCube(cubes.lits + cubes.off[i], cubes.off[i + 1] - cubes.off[i], implied, !flagsOnly, tmp);
+                }
+                else
+                {
+                    const int32_t v = (int32_t)(i / 2 + 1);
+                    const int32_t l = (i & 1) ? -v : v;
+                    flag[i] = h.RunCube(&l, 1, implied, !flagsOnly, tmp);
+                }
+                props[i] = (uint32_t)(h.Implications() - before);
+                ++ran;
+                conflicts += flag[i] == BCP_FLAG_CONFLICT;
             }
-            else
-            {
-                const int32_t v = (int32_t)(i / 2 + 1);
-                const int32_t l = (i & 1) ? -v : v;
-                flag[i] = h.RunCube(&l, 1, implied, !flagsOnly, tmp);
-            }
-            props[i] = (uint32_t)(h.Implications() - before);
-            ++ran;
-            conflicts += flag[i] == BCP_FLAG_CONFLICT;
+            off[n] = implied.size();
+            seconds = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
+            secondsList += (rep ? ", " : "") + to_string(seconds);
         }
-        off[n] = implied.size();
-        seconds = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
     }
 
     const uint64_t implications = h.Implications() - impl0, assignments = h.Assignments() - asg0;
@@ -249,8 +258,8 @@ int main(int argc, char** argv)
             fprintf(stderr, "cannot write %s\n", out); return 4;
         }
     }
-    printf("{\"status\": %d, \"n\": %llu, \"ran\": %llu, \"conflicts\": %llu, \"implications\": %llu, \"assignments\": %llu, \"implied_lits\": %llu, \"level0\": %llu, \"delayed_triggers\": %llu, \"seconds\": %.6f}\n",
+    printf("{\"status\": %d, \"n\": %llu, \"ran\": %llu, \"conflicts\": %llu, \"implications\": %llu, \"assignments\": %llu, \"implied_lits\": %llu, \"level0\": %llu, \"delayed_triggers\": %llu, \"seconds\": %.6f, \"seconds_list\": [%s]}\n",
         ok ? 0 : 1, (unsigned long long)n, (unsigned long long)ran, (unsigned long long)conflicts, (unsigned long long)implications, (unsigned long long)assignments,
-        (unsigned long long)implied.size(), (unsigned long long)level0.size(), (unsigned long long)h.DelayedTriggers(), seconds);
+        (unsigned long long)implied.size(), (unsigned long long)level0.size(), (unsigned long long)h.DelayedTriggers(), seconds, secondsList.c_str());
     return 0;
 }

@@ -175,3 +175,22 @@ def test_topor_style_single_cube_api(golden):
         assert t.GetLitValue(next(iter(implied))) != TToporLitVal.VAL_SATISFIED if implied - level0 and not (set(map(abs, implied)) & set(map(abs, level0))) else True
         checked += 1
     assert checked > 10 and t.GetPropagations() > 0 and not t.IsError()
+
+
+def test_explicit_probe_list_equals_probe_universe(golden):
+    """Depth-1 cubes are probes: same flags, same implied sets, same failed-literal bitmap as ProbeAll."""
+    for name in ["regr_47", "fuzz_10", "fuzz_5"]:
+        g = lambda k: golden[f"{name}/{k}"]
+        t, _ = engine_for(g("words"))
+        n = 2 * t.max_var
+        idx = np.arange(n)
+        lits = np.where(idx & 1, -(idx // 2 + 1), idx // 2 + 1).astype(np.int32)
+        off = np.arange(n + 1, dtype=np.uint64)
+        res = t.PropagateBatch(lits, off)
+        gpu_util.assert_same_results(res, g("probe_flag"), g("probe_off"), g("probe_lits"), name)
+        fa, ua = t.Bitmaps()
+        t.ClearBitmaps()
+        assert not t.Bitmaps()[0].any()
+        t.ProbeAll(implied=False)
+        fb, ub = t.Bitmaps()
+        assert np.array_equal(fa, fb) and np.array_equal(ua, ub) and fa.any() == bool((g("probe_flag") == 1).any())
