@@ -224,7 +224,7 @@ def ours_arm(args, rank, local_rank, world):
         return ms
 
     clocks = ClockSampler(local_rank)
-    stats = {"kernel_ms": [], "tier1_ms": [], "kernel_bytes": 0, "launches": 0, "props_ref": 0, "props_all": 0}
+    stats = {"triage_ms": [], "deep_ms": [], "kernel_bytes": 0, "triage_bytes": 0, "launches": 0, "props_ref": 0, "props_all": 0}
     step_ms = []
     for it in range(args.warmup + args.steps):
         flush.fill_(it & 0xff)       # L2 flush between iterations
@@ -234,9 +234,9 @@ def ours_arm(args, rank, local_rank, world):
         ms = device_step()
         if it >= args.warmup:
             step_ms.append(ms)
-            stats["kernel_ms"].append(info.kernel_ms)
-            stats["tier1_ms"].append(info.tier1_ms)
-            stats["kernel_bytes"] = info.kernel_bytes
+            stats["triage_ms"].append(info.triage_ms)
+            stats["deep_ms"].append(info.deep_ms)
+            stats["kernel_bytes"], stats["triage_bytes"] = info.kernel_bytes, info.triage_bytes
             stats["launches"] += info.launches
             stats["props_ref"], stats["props_all"] = info.props_ref, info.props_all
     barrier()
@@ -296,8 +296,14 @@ def ours_arm(args, rank, local_rank, world):
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        t1 = sum(stats["tier1_ms"]) / len(stats["tier1_ms"]) / 1e3
-        achieved = stats["kernel_bytes"] / t1 / 1e9
+        tri = sum(stats["triage_ms"]) / len(stats["triage_ms"]) / 1e3
+        dee = sum(stats["deep_ms"]) / len(stats["deep_ms"]) / 1e3
+        # the dominant kernel of the step: the triage (k_triage) when nothing propagates, else the propagate kernel
+        if stats["kernel_bytes"] - stats["triage_bytes"] > stats["triage_bytes"]:
+            kname, kbytes, t1 = "k_deep (warp-per-probe propagate, shared-memory state)", stats["kernel_bytes"] - stats["triage_bytes"], dee
+        else:
+            kname, kbytes, t1 = "k_triage (one probe per thread, streaming)", stats["triage_bytes"], tri
+        achieved = kbytes / t1 / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_small_c2_dram_bytes_per_launch")
@@ -318,11 +324,11 @@ def ours_arm(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "probes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(e2e_total.item()) / args.steps},
             "gpu_launches": stats["launches"],
-            "roofline": {"bound": "hbm", "kernel": "k_small (triage + propagate, first tier)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
-                         "bytes_per_launch": stats["kernel_bytes"], "kernel_ms": 1e3 * t1, "traffic": traffic,
+                         "bytes_per_launch": kbytes, "kernel_ms": 1e3 * t1, "triage_ms": 1e3 * tri, "deep_ms": 1e3 * dee, "traffic": traffic,
                          "abytes_2wl_per_launch": abytes_2wl if world == 1 else None,
-                         "abytes_2wl_frac": (abytes_2wl / t1 / 1e9 / peak) if world == 1 else None},
+                         "abytes_2wl_frac_of_step": (abytes_2wl / (total_s / args.steps) / 1e9 / peak) if world == 1 else None},
             "cpu_baseline": cpu,
             "clocks": clk,
         }

@@ -66,11 +66,15 @@ typedef struct {
                                   m_Implications convention (TopiBcp.cc:193-198) */
     uint64_t slots;            /* 8-byte row slots examined */
     uint64_t clause_fetches;   /* long clauses fetched from the arena */
-    uint64_t kernel_bytes;     /* algorithmic bytes moved by the propagate kernels ("bytes model") */
-    float kernel_ms;           /* device time of the propagate kernels of this call (CUDA events) */
-    float total_ms;            /* device time of the whole call incl. result compaction */
+    uint64_t kernel_bytes;     /* algorithmic bytes moved by triage + propagation ("bytes model") */
+    uint64_t triage_bytes;     /* of those, the triage kernel's */
+    uint64_t n_deep;           /* items the triage queued for propagation */
+    float kernel_ms;           /* = total_ms (kept for callers of the first ABI revision) */
+    float total_ms;            /* device time of the whole call incl. result compaction (CUDA events) */
     uint32_t launches;         /* kernels of this engine launched by the call (library scan kernels not counted) */
-    float tier1_ms;            /* device time of the first-tier propagate kernel alone (last attempt) */
+    float tier1_ms;            /* triage_ms + deep_ms */
+    float triage_ms;           /* device time of k_triage (last attempt) */
+    float deep_ms;             /* device time of k_deep, the shared-memory propagate kernel (last attempt) */
 } bbcp_batch_info;
 
 typedef struct {

@@ -16,7 +16,9 @@ class BatchInfo(C.Structure):
     _fields_ = [("n", C.c_uint64), ("n_implied", C.c_uint64), ("n_ok", C.c_uint64), ("n_conflict", C.c_uint64),
                 ("n_skipped", C.c_uint64), ("n_large", C.c_uint64), ("props_all", C.c_uint64), ("props_ref", C.c_uint64),
                 ("slots", C.c_uint64), ("clause_fetches", C.c_uint64), ("kernel_bytes", C.c_uint64),
-                ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("tier1_ms", C.c_float)]
+                ("triage_bytes", C.c_uint64), ("n_deep", C.c_uint64),
+                ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("tier1_ms", C.c_float),
+                ("triage_ms", C.c_float), ("deep_ms", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

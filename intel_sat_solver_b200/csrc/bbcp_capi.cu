@@ -41,14 +41,12 @@ struct DevBuf {
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
-struct CastU64 {
-    __host__ __device__ uint64_t operator()(const uint32_t &x) const { return (uint64_t)x; }
-};
-
-// misc device words: [0..C_N) counters, then cursor, then (u32) ticket, overflow_count
+// misc device words (u64): [0..C_N) counters, cursor, {ticket, overflow_count} (u32 pair), {deep_count, -} (u32 pair),
+// total (a copy of off[n])
 constexpr int MISC_CURSOR = C_N;
-constexpr int MISC_U32 = C_N + 1;       // as u32 index: 2*MISC_U32 = ticket, +1 = overflow_count
-constexpr int MISC_WORDS64 = C_N + 2;
+constexpr int MISC_U32 = C_N + 1;       // as u32 index: 2*MISC_U32 = ticket, +1 = overflow_count, +2 = deep_count
+constexpr int MISC_TOTAL = C_N + 3;
+constexpr int MISC_WORDS64 = C_N + 4;
 
 }  // namespace
 
@@ -62,13 +60,13 @@ struct bbcp_handle {
     int sm_count = 148;
 
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
-    DevBuf d_hdr, d_slots, d_arena, d_varinfo, d_failed, d_unit;
+    DevBuf d_hdr, d_slots, d_arena, d_litinfo, d_failed, d_unit;
     uint64_t bitmap_words = 0;
     uint64_t device_db_bytes = 0;
 
-    DevBuf d_flag, d_raw_off, d_len, d_out, d_off, d_impl, d_cube_lits, d_cube_off, d_overflow, d_misc, d_lbits, d_ltrail, d_cubtmp;
+    DevBuf d_flag, d_raw_off, d_len, d_out, d_off, d_impl, d_cube_lits, d_cube_off, d_overflow, d_deep, d_misc, d_lbits, d_ltrail, d_cubtmp;
     unsigned long long *h_misc = nullptr;   // pinned
     uint32_t large_workers = 0;
 
@@ -125,16 +123,29 @@ bool upload(bbcp_handle *h, DevBuf &b, const void *src, size_t bytes)
 bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo)
 {
     HostDb &db = h->db;
+    // per-literal facts for the triage: level-0 value and mappedness of the variable, and what the row of
+    // the literal's NEGATION holds (that row is the one scanned when the literal is assigned)
+    std::vector<uint8_t> litinfo(db.hdr.size(), 0);
+    for (size_t l = 2; l < litinfo.size(); ++l) {
+        const uint8_t vi = varinfo[l >> 1];
+        uint8_t li = 0;
+        if (vi & 4) li |= LI_MAPPED;
+        if (vi & 3) li |= (((vi & 3) == 1) == ((l & 1) == 0)) ? LI_TRUE_L0 : LI_FALSE_L0;
+        const RowHdr &r = db.hdr[l ^ 1];
+        if (r.nbin) li |= LI_HAS_BIN;
+        if (r.nbin | r.ntern | r.nlong) li |= LI_NONEMPTY;
+        litinfo[l] = li;
+    }
     if (!upload(h, h->d_hdr, db.hdr.data(), db.hdr.size() * sizeof(RowHdr))) return false;
     if (!upload(h, h->d_slots, db.slots.data(), db.slots.size() * sizeof(Slot))) return false;
     if (!upload(h, h->d_arena, db.arena.data(), db.arena.size() * 4)) return false;
-    if (!upload(h, h->d_varinfo, varinfo.data(), varinfo.size())) return false;
+    if (!upload(h, h->d_litinfo, litinfo.data(), litinfo.size())) return false;
     h->bitmap_words = (2 * ((uint64_t)db.max_var + 1) + 31) / 32;
     if (!h->d_failed.reserve(h->bitmap_words * 4) || !h->d_unit.reserve(h->bitmap_words * 4)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (bitmaps)"); return false; }
     cudaMemsetAsync(h->d_failed.p, 0, h->bitmap_words * 4, h->stream);
     cudaMemsetAsync(h->d_unit.p, 0, h->bitmap_words * 4, h->stream);
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "upload sync")) return false;
-    h->device_db_bytes = db.hdr.size() * sizeof(RowHdr) + db.slots.size() * sizeof(Slot) + db.arena.size() * 4 + varinfo.size() + 2 * h->bitmap_words * 4;
+    h->device_db_bytes = db.hdr.size() * sizeof(RowHdr) + db.slots.size() * sizeof(Slot) + db.arena.size() * 4 + litinfo.size() + 2 * h->bitmap_words * 4;
     return true;
 }
 
@@ -144,7 +155,7 @@ DbView db_view(const bbcp_handle *h)
     v.hdr = h->d_hdr.as<uint4>();
     v.slots = h->d_slots.as<uint2>();
     v.arena = h->d_arena.as<uint4>();
-    v.varinfo = h->d_varinfo.as<uint8_t>();
+    v.litinfo = h->d_litinfo.as<uint8_t>();
     v.max_var = h->db.max_var;
     v.nvars_words16 = (uint32_t)(((uint64_t)h->db.max_var + 1 + 15) / 16);
     return v;
@@ -152,14 +163,32 @@ DbView db_view(const bbcp_handle *h)
 
 uint32_t pow2_at_least(uint32_t x) { uint32_t p = 32; while (p < x) p <<= 1; return p; }
 
+struct CastLen {
+    __host__ __device__ uint64_t operator()(const uint32_t &x) const { return (uint64_t)(x & 0x7fffffffu); }
+};
+
+// scan of the set sizes -> canonical CSR offsets (off[n] = total), gather out of allocation order
+bool compact(bbcp_handle *h, const BatchView &b, uint64_t n)
+{
+    cub::TransformInputIterator<uint64_t, CastLen, const uint32_t *> in(b.len, CastLen());
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, h->d_off.as<uint64_t>(), (int)(n + 1), h->stream);
+    if (!h->d_cubtmp.reserve(tmp + 16)) return false;
+    cub::DeviceScan::ExclusiveSum(h->d_cubtmp.p, tmp, in, h->d_off.as<uint64_t>(), (int)(n + 1), h->stream);
+    launch_gather(b, h->d_off.as<uint64_t>(), h->d_impl.as<int32_t>(), h->stream);
+    cudaMemcpyAsync(h->d_misc.as<unsigned long long>() + MISC_TOTAL, h->d_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToDevice, h->stream);
+    return true;
+}
+
 // The whole device-side batch. cube arrays already on the device (nullptr = probe universe from `first`).
+// Common path: memset, k_triage, k_deep, scan, k_gather, one read-back, ONE host synchronisation.
 int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint64_t first, uint64_t n,
               const bbcp_opts *uopts, bbcp_batch_info *info)
 {
     bbcp_opts opts;
     opts.flags = BBCP_OPT_IMPLIED; opts.small_trail = 0; opts.out_capacity = 0;
     if (uopts) opts = *uopts;
-    if (n > 0xfffffff0ull) return h->fail(BBCP_ERR_ARG, "batch too large (split it)");
+    if (n > 0x7ffffff0ull) return h->fail(BBCP_ERR_ARG, "batch too large (split it)");
     bbcp_batch_info bi;
     memset(&bi, 0, sizeof(bi));
     bi.n = n;
@@ -167,13 +196,13 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
 
     const size_t n1 = (size_t)n + 1;
     if (!h->d_flag.reserve(n1) || !h->d_raw_off.reserve(n1 * 8) || !h->d_len.reserve(n1 * 4) || !h->d_off.reserve(n1 * 8) ||
-        !h->d_overflow.reserve(n1 * 4) || !h->d_misc.reserve(MISC_WORDS64 * 8))
+        !h->d_overflow.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_misc.reserve(MISC_WORDS64 * 8))
         return h->fail(BBCP_ERR_ALLOC, "device allocation failed (batch buffers)");
 
     uint32_t cap = opts.small_trail ? pow2_at_least(opts.small_trail) : 512;
     if (cap > 8192) cap = 8192;
     const bool implied = (opts.flags & BBCP_OPT_IMPLIED) != 0;
-    uint64_t out_cap = implied ? (opts.out_capacity ? opts.out_capacity : std::max<uint64_t>(1u << 20, 8 * n)) : 0;
+    uint64_t out_cap = implied ? (opts.out_capacity ? opts.out_capacity : std::max<uint64_t>(1u << 20, 4 * n)) : 0;
 
     DbView dbv = db_view(h);
     BatchView b;
@@ -191,33 +220,45 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.out_cursor = h->d_misc.as<unsigned long long>() + MISC_CURSOR;
     b.ticket = h->d_misc.as<unsigned int>() + 2 * MISC_U32;
     b.overflow_count = h->d_misc.as<uint32_t>() + 2 * MISC_U32 + 1;
+    b.deep_count = h->d_misc.as<uint32_t>() + 2 * MISC_U32 + 2;
     b.overflow_list = h->d_overflow.as<uint32_t>();
+    b.deep_list = h->d_deep.as<uint32_t>();
     b.opts = opts.flags;
 
     const int bps = small_blocks_per_sm(cap);
     if (bps <= 0) return h->fail(BBCP_ERR_CUDA, "first-tier kernel does not fit (shared memory)");
-    const uint64_t chunks = (n + 31) / 32;
+    const uint32_t *h_u32 = reinterpret_cast<uint32_t *>(h->h_misc);
+    float triage_ms = 0, deep_ms = 0;
 
     cudaEventRecord(h->ev[0], h->stream);
     for (int attempt = 0; attempt < 8; ++attempt) {
-        if (!h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (implied literals)");
+        // room for every self-implying probe (n) plus out_cap stored literals
+        if (!h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4) || (implied && !h->d_impl.reserve((n + out_cap + 4) * 4)))
+            return h->fail(BBCP_ERR_ALLOC, "device allocation failed (implied literals)");
         b.out_lits = h->d_out.as<int32_t>();
         b.out_cap = out_cap;
         b.worklist = nullptr;
         b.nwork = 0;
         cudaMemsetAsync(h->d_misc.p, 0, MISC_WORDS64 * 8, h->stream);
+        cudaMemsetAsync(b.len + n, 0, 4, h->stream);
         bi.launches = 0;
         if (n) {
-            int blocks = (int)std::min<uint64_t>((uint64_t)bps * h->sm_count, (chunks + SMALL_WARPS - 1) / SMALL_WARPS);
             cudaEventRecord(h->ev[3], h->stream);
-            launch_small(dbv, b, cap, std::max(blocks, 1), h->stream);
+            launch_triage(b, dbv, (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)h->sm_count * 8), h->stream);
             cudaEventRecord(h->ev[4], h->stream);
-            ++bi.launches;
+            launch_small(dbv, b, cap, bps * h->sm_count, h->stream);
+            cudaEventRecord(h->ev[5], h->stream);
+            bi.launches += 2;
+            if (implied) {
+                if (!compact(h, b, n)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (compaction)");
+                ++bi.launches;
+            }
         }
         cudaMemcpyAsync(h->h_misc, h->d_misc.p, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
-        if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "first-tier kernel")) return BBCP_ERR_CUDA;
-        const uint32_t n_over = reinterpret_cast<uint32_t *>(h->h_misc)[2 * MISC_U32 + 1];
-        if (n_over) {
+        if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "propagate kernels")) return BBCP_ERR_CUDA;
+        if (n) { cudaEventElapsedTime(&triage_ms, h->ev[3], h->ev[4]); cudaEventElapsedTime(&deep_ms, h->ev[4], h->ev[5]); }
+        const uint32_t n_over = h_u32[2 * MISC_U32 + 1];
+        if (n_over && h->h_misc[MISC_CURSOR] <= out_cap) {
             // second tier: per-warp global slabs sized for the whole variable range
             const size_t per_worker = (size_t)dbv.nvars_words16 * 4 + ((size_t)dbv.max_var + 1) * 4;
             size_t free_b = 0, total_b = 0;
@@ -240,16 +281,22 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             cudaMemsetAsync(b.ticket, 0, 4, h->stream);
             launch_large(dbv, b, ls, (int)(std::min<uint64_t>(workers, h->large_workers) / LARGE_WARPS), h->stream);
             ++bi.launches;
+            if (implied) {
+                if (!compact(h, b, n)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (compaction)");
+                ++bi.launches;
+            }
             cudaMemcpyAsync(h->h_misc, h->d_misc.p, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
             if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "second-tier kernel")) return BBCP_ERR_CUDA;
         }
         const uint64_t cursor = h->h_misc[MISC_CURSOR];
-        if (cursor <= out_cap) { bi.n_implied = cursor; break; }
+        if (cursor <= out_cap) { bi.n_implied = implied ? h->h_misc[MISC_TOTAL] : 0; break; }
         // implied-literal buffer too small: redo the batch with room for everything that was asked for
         out_cap = std::max<uint64_t>(cursor + cursor / 8, out_cap * 2);
         if (attempt == 7) return h->fail(BBCP_ERR_ALLOC, "implied-literal buffer keeps overflowing");
     }
-    cudaEventRecord(h->ev[1], h->stream);
+    if (!implied) cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
+    cudaEventRecord(h->ev[2], h->stream);
+    if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "batch")) return BBCP_ERR_CUDA;
 
     bi.props_all = h->h_misc[C_PROPS_ALL];
     bi.props_ref = h->h_misc[C_PROPS_REF];
@@ -259,29 +306,17 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     bi.n_ok = h->h_misc[C_OK];
     bi.n_conflict = h->h_misc[C_CONFLICT];
     bi.n_skipped = h->h_misc[C_SKIPPED];
-    // bytes model: row headers + row slots + clause units + implied literals (kernel counters),
-    // plus the per-item result record (flag 1 + len 4 + raw_off 8) and the cube input
-    bi.kernel_bytes = h->h_misc[C_BYTES] + 13 * n;
-
-    if (implied && n) {
-        // canonical CSR: exclusive scan of the set sizes, then a gather out of allocation order
-        cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> in(b.len, CastU64());
-        size_t tmp = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, h->d_off.as<uint64_t>(), (int)n, h->stream);
-        if (!h->d_cubtmp.reserve(tmp + 16) || !h->d_impl.reserve(std::max<uint64_t>(bi.n_implied, 4) * 4))
-            return h->fail(BBCP_ERR_ALLOC, "device allocation failed (compaction)");
-        cub::DeviceScan::ExclusiveSum(h->d_cubtmp.p, tmp, in, h->d_off.as<uint64_t>(), (int)n, h->stream);
-        cudaMemcpyAsync(h->d_off.as<uint64_t>() + n, b.out_cursor, 8, cudaMemcpyDeviceToDevice, h->stream);
-        launch_gather(b, h->d_off.as<uint64_t>(), h->d_impl.as<int32_t>(), h->stream);
-        bi.launches += 1;  // (the scan is two library kernels, not counted)
-    } else {
-        cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
-    }
-    cudaEventRecord(h->ev[2], h->stream);
-    if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "batch")) return BBCP_ERR_CUDA;
-    cudaEventElapsedTime(&bi.kernel_ms, h->ev[0], h->ev[1]);
+    bi.n_deep = h_u32[2 * MISC_U32 + 2];
+    // bytes model: triage = 1 B of literal facts + 1 B flag + 4 B size per item (+ 16 B offsets and
+    // 4 B literal for explicit probe lists); propagation = row headers, row slots, clause units, stored
+    // implied literals (kernel counters) + the per-item record (flag, size, position) of the queued items
+    bi.triage_bytes = n * (6 + (d_off ? 20 : 0));
+    bi.kernel_bytes = bi.triage_bytes + h->h_misc[C_BYTES] + 17ull * bi.n_deep;
     cudaEventElapsedTime(&bi.total_ms, h->ev[0], h->ev[2]);
-    if (n) cudaEventElapsedTime(&bi.tier1_ms, h->ev[3], h->ev[4]);
+    bi.triage_ms = triage_ms;
+    bi.deep_ms = deep_ms;
+    bi.tier1_ms = triage_ms + deep_ms;
+    bi.kernel_ms = bi.total_ms;
     h->last_n = n;
     h->last_n_implied = bi.n_implied;
     h->have_batch = true;
@@ -316,8 +351,8 @@ void bbcp_release(bbcp_handle *h)
     if (h->device_ready) {
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
-        for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_varinfo, &h->d_failed, &h->d_unit, &h->d_flag, &h->d_raw_off, &h->d_len,
-                          &h->d_out, &h->d_off, &h->d_impl, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_misc, &h->d_lbits,
+        for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_failed, &h->d_unit, &h->d_flag, &h->d_raw_off, &h->d_len,
+                          &h->d_out, &h->d_off, &h->d_impl, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_deep, &h->d_misc, &h->d_lbits,
                           &h->d_ltrail, &h->d_cubtmp})
             b->release();
         if (h->h_misc) cudaFreeHost(h->h_misc);

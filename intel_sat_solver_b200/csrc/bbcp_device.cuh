@@ -8,7 +8,8 @@
 //               held inline: no arena fetch), then nlong long slots {blocker, clause16} -- one per OCCURRENCE
 //               of ilit in a clause of >= 4 literals, blocker = the next literal of that clause.
 //   arena[]     16-byte units; clause = [size, l0, l1, ...] padded with 0 to a multiple of 4 words.
-//   varinfo[v]  bits 0-1: level-0 value of var v (0 none, 1 true, 2 false); bit 2: mapped.
+//   litinfo[l]  per internal literal l, the facts a probe of l needs: true / false at level 0, variable
+//               mapped, row of the NEGATION of l has binary clauses / is non-empty (LI_* bits).
 // Internal literal = 2*var + neg with var = the external (DIMACS) variable.
 #pragma once
 #include <cstdint>
@@ -20,10 +21,13 @@ struct DbView {
     const uint4 *hdr;
     const uint2 *slots;
     const uint4 *arena;
-    const uint8_t *varinfo;
+    const uint8_t *litinfo;     // per internal literal l (as a probe): LI_* bits
     int32_t max_var;
     uint32_t nvars_words16;    // words of a 2-bit-per-var dense assignment: ceil((max_var+1)/16)
 };
+
+constexpr uint8_t LI_TRUE_L0 = 1, LI_FALSE_L0 = 2, LI_MAPPED = 4, LI_HAS_BIN = 8, LI_NONEMPTY = 16;
+constexpr uint32_t LEN_SELF = 0x80000000u;   // len[] flag: the implied set is the item's own literal (not stored)
 
 enum Counter { C_PROPS_ALL = 0, C_PROPS_REF, C_SLOTS, C_CLAUSE_FETCH, C_BYTES, C_LARGE, C_OK, C_CONFLICT, C_SKIPPED, C_N };
 
@@ -38,7 +42,7 @@ struct BatchView {
     // output
     uint8_t *flag;              // [n]
     uint64_t *raw_off;          // [n] position of the item's implied set in out_lits
-    uint32_t *len;              // [n] size of the implied set
+    uint32_t *len;              // [n] size of the implied set (| LEN_SELF)
     int32_t *out_lits;          // external literals, sorted by |var| inside each set
     uint64_t out_cap;
     unsigned long long *out_cursor;
@@ -46,7 +50,9 @@ struct BatchView {
     unsigned long long *counters;
     uint32_t *overflow_list;    // items that did not fit the shared-memory state
     uint32_t *overflow_count;
-    unsigned int *ticket;       // dynamic chunk scheduler
+    unsigned int *ticket;       // dynamic scheduler over the queued items
+    uint32_t *deep_list;        // items queued by the triage for propagation
+    uint32_t *deep_count;
     uint32_t opts;
 };
 
@@ -61,6 +67,7 @@ struct LargeState {
     uint32_t *trail;   // [workers][max_var + 1]
 };
 
+void launch_triage(const BatchView &b, const DbView &db, int blocks, cudaStream_t s);
 void launch_small(const DbView &db, const BatchView &b, uint32_t trail_cap, int blocks, cudaStream_t s);
 void launch_large(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s);
 void launch_gather(const BatchView &b, const uint64_t *off, int32_t *dst, cudaStream_t s);

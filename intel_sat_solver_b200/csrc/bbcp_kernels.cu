@@ -21,8 +21,9 @@
 //     the hash set (atomicCAS) is the linearisation point that detects x / not-x conflicts;
 //   * while exactly one literal is assigned, only binary clauses can become unit, so the first step of a
 //     depth-1 probe reads the binary part of its row only ("length pruning"); a probe whose literal has no
-//     binary clause ends right there. The triage of 32 consecutive probes is done one probe per lane, with
-//     coalesced header loads and one aggregated output allocation per warp.
+//     binary clause ends right there. That triage is its own streaming kernel (k_triage: one probe per
+//     thread, one byte of per-literal facts read, flag + set size written, no atomics on the common path);
+//     only the probes that can propagate are queued for the warp-per-probe kernel (k_deep).
 // A conflict ends the probe (NewContradiction's same-level branch, TopiBcp.cc:141-158); only the flag is
 // part of the contract for conflicting probes.
 #include "bbcp_device.cuh"
@@ -297,10 +298,11 @@ __device__ int load_cube(const DbView &db, S &st, const int32_t *lits, uint32_t 
             const int32_t l = lits[i];
             const uint32_t v = (uint32_t)(l < 0 ? -l : l);
             if (l != 0) {
-                const uint8_t vi = (int32_t)v <= db.max_var ? db.varinfo[v] : 0;
-                if (!(vi & 4)) unmapped = true;
-                else if ((vi & 3) == 0) cand = 2u * v + (l < 0);
-                else if (((vi & 3) == 1) == (l < 0)) false_l0 = true;  // var true & negative literal, or var false & positive
+                const uint32_t il = 2u * v + (l < 0);
+                const uint8_t li = (int32_t)v <= db.max_var ? db.litinfo[il] : 0;
+                if (!(li & LI_MAPPED)) unmapped = true;
+                else if (li & LI_FALSE_L0) false_l0 = true;
+                else if (!(li & LI_TRUE_L0)) cand = il;
             }
         }
         if (!overflow && !conflict) {
@@ -382,10 +384,11 @@ template <class S>
 __device__ int load_probe(const DbView &db, S &st, int32_t l, uint32_t &tail)
 {
     const uint32_t v = (uint32_t)(l < 0 ? -l : l);
-    const uint8_t vi = (int32_t)v <= db.max_var ? db.varinfo[v] : 0;
+    const uint8_t li = (int32_t)v <= db.max_var ? db.litinfo[2u * v + (l < 0)] : 0;
     tail = 0;
-    if (!(vi & 4)) return FLAG_UNMAPPED;
-    if ((vi & 3) != 0) return (((vi & 3) == 1) == (l < 0)) ? FLAG_FALSE_L0 : FLAG_TRIVIAL_L0;
+    if (!(li & LI_MAPPED)) return FLAG_UNMAPPED;
+    if (li & LI_FALSE_L0) return FLAG_FALSE_L0;
+    if (li & LI_TRUE_L0) return FLAG_TRIVIAL_L0;
     const int r = commit(st, lane_id() == 0 ? 2u * v + (l < 0) : 0u, tail);
     __syncwarp();
     return r == 2 ? FLAG_OVERFLOW : 0xff;
@@ -429,11 +432,88 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
     __syncwarp();
 }
 
+// Triage: one item per thread. Decides every depth-1 item that needs no propagation (unmapped / assigned at
+// level 0 / no binary clause on the negation => the implied set is the literal itself, marked LEN_SELF so
+// that nothing but the size is written here) and queues the rest for k_deep.
+__global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView b)
+{
+    __shared__ unsigned int s_cnt[4];  // ok, skipped, props_ref, deep
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
+    const bool probe_mode = b.cube_off == nullptr;
+    uint32_t n_ok = 0, n_skip = 0, n_ref = 0;
+    for (uint64_t base = (uint64_t)blockIdx.x * 256; base < b.n; base += (uint64_t)gridDim.x * 256) {
+        const uint64_t item = base + threadIdx.x;
+        const bool valid = item < b.n;
+        int32_t lit = 0;
+        if (valid) {
+            if (probe_mode) {
+                const uint64_t idx = b.first + item;
+                const int32_t pv = (int32_t)(idx / 2 + 1);
+                lit = (idx & 1) ? -pv : pv;
+            } else {
+                const uint64_t o = b.cube_off[item];
+                if (b.cube_off[item + 1] - o == 1) lit = b.cube_lits[o];
+            }
+        }
+        uint8_t flag = 0xff;
+        bool self = false;
+        if (lit != 0) {
+            const uint32_t v = (uint32_t)(lit < 0 ? -lit : lit);
+            const uint8_t li = (int32_t)v <= db.max_var ? db.litinfo[2u * v + (lit < 0)] : 0;
+            if (!(li & LI_MAPPED)) flag = FLAG_UNMAPPED;
+            else if (li & LI_FALSE_L0) flag = FLAG_FALSE_L0;
+            else if (li & LI_TRUE_L0) flag = FLAG_TRIVIAL_L0;
+            else if (prune && !(li & LI_HAS_BIN)) {
+                flag = FLAG_OK;   // no binary clause on the negation: the probe implies exactly itself
+                self = true;
+                n_ref += (li & LI_NONEMPTY) != 0;
+            }
+        }
+        if (flag != 0xff) {
+            b.flag[item] = flag;
+            b.len[item] = self && (b.opts & OPT_IMPLIED) ? (LEN_SELF | 1u) : 0u;
+            n_ok += self;
+            n_skip += !self;
+        }
+        const bool deep = valid && flag == 0xff;
+        const unsigned dm = __ballot_sync(FULL, deep);
+        if (dm) {
+            unsigned pos = 0;
+            if (lane_id() == 0) pos = atomicAdd(b.deep_count, (unsigned)__popc(dm));
+            pos = __shfl_sync(FULL, pos, 0);
+            if (deep) b.deep_list[pos + __popc(dm & lanemask_lt())] = (uint32_t)item;
+        }
+    }
+    // one set of counter atomics per block
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        n_ok += __shfl_xor_sync(FULL, n_ok, d);
+        n_skip += __shfl_xor_sync(FULL, n_skip, d);
+        n_ref += __shfl_xor_sync(FULL, n_ref, d);
+    }
+    if (lane_id() == 0) {
+        if (n_ok) atomicAdd(&s_cnt[0], n_ok);
+        if (n_skip) atomicAdd(&s_cnt[1], n_skip);
+        if (n_ref) atomicAdd(&s_cnt[2], n_ref);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) { atomicAdd(&b.counters[C_OK], (unsigned long long)s_cnt[0]); atomicAdd(&b.counters[C_PROPS_ALL], (unsigned long long)s_cnt[0]); }
+        if (s_cnt[1]) atomicAdd(&b.counters[C_SKIPPED], (unsigned long long)s_cnt[1]);
+        if (s_cnt[2]) atomicAdd(&b.counters[C_PROPS_REF], (unsigned long long)s_cnt[2]);
+    }
+}
+
+// Warp-per-probe propagation of the queued items, per-probe state in shared memory.
 __global__ void __launch_bounds__(SMALL_WARPS * 32)
-k_small(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t cap)
+k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t cap)
 {
     extern __shared__ uint32_t smem[];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t ndeep = *b.deep_count;
+    if ((uint64_t)blockIdx.x * SMALL_WARPS >= ndeep) return;
     const uint32_t hs = 1u << log_hs;
     const uint32_t per_warp = hs + cap + cap / 2;  // words: hash, trail, tslot (u16)
     SmemState st;
@@ -446,97 +526,28 @@ k_small(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_
     __syncwarp();
 
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
-    const bool probe_mode = b.cube_off == nullptr;
     WarpCounters wc;
     for (;;) {
-        unsigned chunk = 0;
-        if (lane == 0) chunk = atomicAdd(b.ticket, 1u);
-        chunk = __shfl_sync(FULL, chunk, 0);
-        const uint64_t base = (uint64_t)chunk * 32;
-        if (base >= b.n) break;
-        const uint64_t item = base + lane;
-        const bool valid = item < b.n;
-        unsigned deep = __ballot_sync(FULL, valid);
-        {
-            // triage, one depth-1 item per lane: consecutive probes read consecutive row headers
-            int32_t lit = 0;
-            if (valid) {
-                if (probe_mode) {
-                    const uint64_t idx = b.first + item;
-                    const int32_t pv = (int32_t)(idx / 2 + 1);
-                    lit = (idx & 1) ? -pv : pv;
-                } else {
-                    const uint64_t o = b.cube_off[item];
-                    if (b.cube_off[item + 1] - o == 1) lit = b.cube_lits[o];
-                }
-            }
-            const uint32_t v = (uint32_t)(lit < 0 ? -lit : lit), neg = lit < 0;
-            uint8_t flag = 0xff;
-            bool shallow = false, nonempty = false;
-            if (lit != 0) {
-                const uint8_t vi = (int32_t)v <= db.max_var ? db.varinfo[v] : 0;
-                if (!(vi & 4)) flag = FLAG_UNMAPPED;
-                else if ((vi & 3) != 0) flag = (((vi & 3) == 1) == (neg != 0)) ? FLAG_FALSE_L0 : FLAG_TRIVIAL_L0;
-                else if (prune) {
-                    const uint4 hd = __ldg(&db.hdr[(2u * v + neg) ^ 1u]);
-                    shallow = hd.y == 0;   // no binary clause on the negation: nothing can be implied
-                    nonempty = (hd.z | hd.w) != 0;
-                    if (shallow) flag = FLAG_OK;
-                }
-            }
-            const unsigned sm = __ballot_sync(FULL, shallow);
-            const unsigned decided = __ballot_sync(FULL, flag != 0xff);
-            wc.n_skip += __popc(__ballot_sync(FULL, flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED));
-            if (sm) {
-                // every shallow probe implies exactly itself
-                const uint32_t ns = __popc(sm);
-                wc.n_ok += ns;  // (an output-buffer overflow makes the host redo the batch)
-                wc.props_all += ns;
-                wc.props_ref += __popc(__ballot_sync(FULL, shallow && nonempty));
-                wc.bytes += 16ull * ns;
-                unsigned long long off = 0;
-                uint32_t len = 0;
-                if (b.opts & OPT_IMPLIED) {
-                    const unsigned long long o = out_alloc(b, ns);
-                    if (shallow) {
-                        if (o == ~0ull) flag = FLAG_OUT_OVERFLOW;
-                        else {
-                            off = o + __popc(sm & lanemask_lt());
-                            len = 1;
-                            b.out_lits[off] = neg ? -(int32_t)v : (int32_t)v;
-                        }
-                    }
-                    wc.bytes += 4ull * ns;
-                }
-                if (shallow) { b.len[item] = len; b.raw_off[item] = off; }
-            }
-            if (flag != 0xff) {
-                b.flag[item] = flag;
-                if (!shallow) { b.len[item] = 0; b.raw_off[item] = 0; }
-            }
-            deep &= ~decided;
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(b.ticket, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= ndeep) break;
+        const uint64_t it_idx = b.deep_list[t];
+        const Item it = get_item(b, it_idx);
+        uint32_t tail = 0;
+        int f = it.probe_lit ? load_probe(db, st, it.probe_lit, tail) : load_cube(db, st, it.lits, it.n, tail);
+        int res;
+        if (f == 0xff) res = propagate(db, st, tail, prune, wc);
+        else if (f == FLAG_OVERFLOW) res = 2;
+        else if (f == FLAG_CONFLICT) res = 1;
+        else {
+            st.cleanup(tail);
+            if (lane == 0) { b.flag[it_idx] = (uint8_t)f; b.len[it_idx] = 0; b.raw_off[it_idx] = 0; }
+            ++wc.n_skip;
+            __syncwarp();
+            continue;
         }
-        // warp-cooperative propagation of the remaining items of this chunk, one at a time
-        while (deep) {
-            const int j = __ffs(deep) - 1;
-            deep &= deep - 1;
-            const uint64_t it_idx = base + j;
-            const Item it = get_item(b, it_idx);
-            uint32_t tail = 0;
-            int f = it.probe_lit ? load_probe(db, st, it.probe_lit, tail) : load_cube(db, st, it.lits, it.n, tail);
-            int res;
-            if (f == 0xff) res = propagate(db, st, tail, prune, wc);
-            else if (f == FLAG_OVERFLOW) res = 2;
-            else if (f == FLAG_CONFLICT) res = 1;
-            else {
-                st.cleanup(tail);
-                if (lane == 0) { b.flag[it_idx] = (uint8_t)f; b.len[it_idx] = 0; b.raw_off[it_idx] = 0; }
-                ++wc.n_skip;
-                __syncwarp();
-                continue;
-            }
-            finish_small(b, st, it_idx, it, res, tail, wc);
-        }
+        finish_small(b, st, it_idx, it, res, tail, wc);
     }
     wc.flush(b.counters);
 }
@@ -639,12 +650,24 @@ __global__ void k_gather(const BatchView b, const uint64_t *__restrict__ off, in
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const int lane = lane_id();
-    // short segments: one item per lane; long ones: the warp copies together
+    // self-implying probes regenerate their literal; short sets: one item per lane; long ones: warp copy
     for (uint64_t base = warp * 32; base < b.n; base += nwarps * 32) {
         const uint64_t item = base + lane;
         uint32_t len = 0;
         uint64_t src = 0, d = 0;
-        if (item < b.n) { len = b.len[item]; src = b.raw_off[item]; d = off[item]; }
+        if (item < b.n) { len = b.len[item]; d = off[item]; }
+        if (len & LEN_SELF) {
+            int32_t lit;
+            if (b.cube_off) lit = b.cube_lits[b.cube_off[item]];
+            else {
+                const uint64_t idx = b.first + item;
+                const int32_t pv = (int32_t)(idx / 2 + 1);
+                lit = (idx & 1) ? -pv : pv;
+            }
+            dst[d] = lit;
+            len = 0;
+        }
+        if (len) src = b.raw_off[item];
         if (len && len <= 4) {
             for (uint32_t i = 0; i < len; ++i) dst[d + i] = b.out_lits[src + i];
         }
@@ -672,16 +695,21 @@ static uint32_t ilog2(uint32_t x) { uint32_t l = 0; while ((1u << l) < x) ++l; r
 int small_blocks_per_sm(uint32_t cap)
 {
     int nb = 0;
-    cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(cap));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_small, SMALL_WARPS * 32, small_smem_bytes(cap));
+    cudaFuncSetAttribute(k_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(cap));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_deep, SMALL_WARPS * 32, small_smem_bytes(cap));
     return nb;
+}
+
+void launch_triage(const BatchView &b, const DbView &db, int blocks, cudaStream_t s)
+{
+    k_triage<<<blocks, 256, 0, s>>>(db, b);
 }
 
 void launch_small(const DbView &db, const BatchView &b, uint32_t cap, int blocks, cudaStream_t s)
 {
     const size_t smem = small_smem_bytes(cap);
-    cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_small<<<blocks, SMALL_WARPS * 32, smem, s>>>(db, b, ilog2(2 * cap), cap);
+    cudaFuncSetAttribute(k_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_deep<<<blocks, SMALL_WARPS * 32, smem, s>>>(db, b, ilog2(2 * cap), cap);
 }
 
 void launch_large(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s)
