@@ -191,7 +191,7 @@ def ours_arm(args, rank, local_rank, world):
     n_local = last - first
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    opts = Opts(1, 0, 0)
+    opts = Opts(1, 0, 0, 0, 0)
     info = BatchInfo()
     if world > 1:
         slice_t = torch.zeros(wp, dtype=torch.int32, device=dev)

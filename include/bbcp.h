@@ -52,15 +52,17 @@ enum {
 
 typedef struct {
     uint32_t flags;            /* BBCP_OPT_* ; default BBCP_OPT_IMPLIED */
-    uint32_t small_trail;      /* per-probe shared-memory trail capacity of the first-tier kernel (0 = auto) */
+    uint32_t small_trail;      /* trail capacity of the warp-per-probe tier, shared memory (0 = 512) */
     uint64_t out_capacity;     /* device capacity for implied literals per launch, in literals (0 = auto) */
+    uint32_t mid_trail;        /* trail capacity of the CTA-per-probe shared-memory tier (0 = 4096) */
+    uint32_t reserved;
 } bbcp_opts;
 
 typedef struct {
     uint64_t n;                /* probes / cubes in the batch */
     uint64_t n_implied;        /* total implied literals (length of impl_lits) */
     uint64_t n_ok, n_conflict, n_skipped; /* flag 0 / flag 1 / flags 2,3,4 */
-    uint64_t n_large;          /* probes that overflowed shared memory and ran in the global-state kernel */
+    uint64_t n_large;          /* probes that ran in the third tier (CTA per probe, state in a global slab) */
     uint64_t props_all;        /* literals dequeued and propagated (every trail literal of every probe) */
     uint64_t props_ref;        /* of those, literals whose negation has a non-empty row: the reference's
                                   m_Implications convention (TopiBcp.cc:193-198) */
@@ -69,12 +71,15 @@ typedef struct {
     uint64_t kernel_bytes;     /* algorithmic bytes moved by triage + propagation ("bytes model") */
     uint64_t triage_bytes;     /* of those, the triage kernel's */
     uint64_t n_deep;           /* items the triage queued for propagation */
-    float kernel_ms;           /* = total_ms (kept for callers of the first ABI revision) */
+    float kernel_ms;           /* triage_ms + deep_ms + block_ms */
     float total_ms;            /* device time of the whole call incl. result compaction (CUDA events) */
     uint32_t launches;         /* kernels of this engine launched by the call (library scan kernels not counted) */
     float tier1_ms;            /* triage_ms + deep_ms */
     float triage_ms;           /* device time of k_triage (last attempt) */
-    float deep_ms;             /* device time of k_deep, the shared-memory propagate kernel (last attempt) */
+    float deep_ms;             /* device time of k_deep, the warp-per-probe propagate kernel (last attempt) */
+    float block_ms;            /* device time of the two CTA-per-probe tiers (last attempt) */
+    float mid_ms;              /* of which the shared-memory one */
+    uint64_t n_mid;            /* probes that ran in the second tier (CTA per probe, state in shared memory) */
 } bbcp_batch_info;
 
 typedef struct {

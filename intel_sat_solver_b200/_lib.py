@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libbbcp.so")
 
 
 class Opts(C.Structure):
-    _fields_ = [("flags", C.c_uint32), ("small_trail", C.c_uint32), ("out_capacity", C.c_uint64)]
+    _fields_ = [("flags", C.c_uint32), ("small_trail", C.c_uint32), ("out_capacity", C.c_uint64), ("mid_trail", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class BatchInfo(C.Structure):
@@ -18,7 +18,7 @@ class BatchInfo(C.Structure):
                 ("slots", C.c_uint64), ("clause_fetches", C.c_uint64), ("kernel_bytes", C.c_uint64),
                 ("triage_bytes", C.c_uint64), ("n_deep", C.c_uint64),
                 ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("tier1_ms", C.c_float),
-                ("triage_ms", C.c_float), ("deep_ms", C.c_float)]
+                ("triage_ms", C.c_float), ("deep_ms", C.c_float), ("block_ms", C.c_float), ("mid_ms", C.c_float), ("n_mid", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

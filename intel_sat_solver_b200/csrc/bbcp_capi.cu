@@ -41,12 +41,12 @@ struct DevBuf {
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
-// misc device words (u64): [0..C_N) counters, cursor, {ticket, overflow_count} (u32 pair), {deep_count, -} (u32 pair),
+// misc device words (u64): [0..C_N) counters, cursor, six u32 {ticket[3], mid_count, big_count, deep_count},
 // total (a copy of off[n])
 constexpr int MISC_CURSOR = C_N;
-constexpr int MISC_U32 = C_N + 1;       // as u32 index: 2*MISC_U32 = ticket, +1 = overflow_count, +2 = deep_count
-constexpr int MISC_TOTAL = C_N + 3;
-constexpr int MISC_WORDS64 = C_N + 4;
+constexpr int MISC_U32 = C_N + 1;       // as u32 index from 2*MISC_U32: +0..2 tickets, +3 mid_count, +4 big_count, +5 deep_count
+constexpr int MISC_TOTAL = C_N + 5;     // (u32 +6 = chunk_count of the long-set gather)
+constexpr int MISC_WORDS64 = C_N + 6;
 
 }  // namespace
 
@@ -60,15 +60,17 @@ struct bbcp_handle {
     int sm_count = 148;
 
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     DevBuf d_hdr, d_slots, d_arena, d_litinfo, d_failed, d_unit;
     uint64_t bitmap_words = 0;
     uint64_t device_db_bytes = 0;
 
-    DevBuf d_flag, d_raw_off, d_len, d_out, d_off, d_impl, d_cube_lits, d_cube_off, d_overflow, d_deep, d_misc, d_lbits, d_ltrail, d_cubtmp;
+    DevBuf d_flag, d_raw_off, d_len, d_out, d_off, d_impl, d_cube_lits, d_cube_off, d_overflow, d_big, d_deep, d_chunks, d_misc, d_lbits, d_ltrail, d_cubtmp;
     unsigned long long *h_misc = nullptr;   // pinned
-    uint32_t large_workers = 0;
+    uint64_t out_cap_hint = 0;   // stored literals the last batch needed (sizes the next batch's buffer)
+    uint32_t big_slabs = 0;
+    uint32_t slab_version = 0;   // db_version the slabs were sized for
 
     uint64_t last_n = 0, last_n_implied = 0;
     bool have_batch = false;
@@ -180,13 +182,34 @@ bool compact(bbcp_handle *h, const BatchView &b, uint64_t n)
     return true;
 }
 
+// third-tier slabs: one dense assignment + trail per resident CTA, sized for the whole variable range
+bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
+{
+    if (h->d_lbits.p && h->slab_version == h->db_version + 1) return true;
+    const size_t per_slab = (size_t)dbv.nvars_words16 * 4 + ((size_t)dbv.max_var + 1) * 4;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    free_b += h->d_lbits.bytes + h->d_ltrail.bytes;
+    h->d_lbits.release();
+    h->d_ltrail.release();
+    uint64_t slabs = std::min<uint64_t>((uint64_t)h->sm_count * 2, (free_b / 4) / std::max<size_t>(per_slab, 1));
+    slabs = std::max<uint64_t>(slabs, 1);
+    if (!h->d_lbits.reserve(slabs * dbv.nvars_words16 * 4, true) || !h->d_ltrail.reserve(slabs * ((size_t)dbv.max_var + 1) * 4)) return false;
+    h->big_slabs = (uint32_t)slabs;
+    h->slab_version = h->db_version + 1;
+    return true;
+}
+
 // The whole device-side batch. cube arrays already on the device (nullptr = probe universe from `first`).
-// Common path: memset, k_triage, k_deep, scan, k_gather, one read-back, ONE host synchronisation.
+// One stream, no host round trip inside: memset, k_triage, k_deep, k_block<mid>, k_block<big>, scan, k_gather,
+// one read-back, ONE host synchronisation. Each tier hands what it cannot hold to the next through a
+// device-side list; a tier with an empty list exits at once.
 int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint64_t first, uint64_t n,
               const bbcp_opts *uopts, bbcp_batch_info *info)
 {
     bbcp_opts opts;
-    opts.flags = BBCP_OPT_IMPLIED; opts.small_trail = 0; opts.out_capacity = 0;
+    memset(&opts, 0, sizeof(opts));
+    opts.flags = BBCP_OPT_IMPLIED;
     if (uopts) opts = *uopts;
     if (n > 0x7ffffff0ull) return h->fail(BBCP_ERR_ARG, "batch too large (split it)");
     bbcp_batch_info bi;
@@ -196,15 +219,22 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
 
     const size_t n1 = (size_t)n + 1;
     if (!h->d_flag.reserve(n1) || !h->d_raw_off.reserve(n1 * 8) || !h->d_len.reserve(n1 * 4) || !h->d_off.reserve(n1 * 8) ||
-        !h->d_overflow.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_misc.reserve(MISC_WORDS64 * 8))
+        !h->d_overflow.reserve(n1 * 4) || !h->d_big.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_misc.reserve(MISC_WORDS64 * 8))
         return h->fail(BBCP_ERR_ALLOC, "device allocation failed (batch buffers)");
 
     uint32_t cap = opts.small_trail ? pow2_at_least(opts.small_trail) : 512;
     if (cap > 8192) cap = 8192;
+    uint32_t cap_mid = opts.mid_trail ? pow2_at_least(opts.mid_trail) : 4096;
+    if (cap_mid > 16384) cap_mid = 16384;
     const bool implied = (opts.flags & BBCP_OPT_IMPLIED) != 0;
-    uint64_t out_cap = implied ? (opts.out_capacity ? opts.out_capacity : std::max<uint64_t>(1u << 20, 4 * n)) : 0;
+    uint64_t out_cap = implied ? (opts.out_capacity ? opts.out_capacity : std::max<uint64_t>({(uint64_t)1 << 20, 4 * n, h->out_cap_hint + h->out_cap_hint / 4})) : 0;
 
     DbView dbv = db_view(h);
+    if (!ensure_slabs(h, dbv)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (third-tier state)");
+    LargeState ls;
+    ls.bits = h->d_lbits.as<uint32_t>();
+    ls.trail = h->d_ltrail.as<uint32_t>();
+
     BatchView b;
     memset(&b, 0, sizeof(b));
     b.cube_lits = d_lits;
@@ -218,27 +248,32 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.unit = h->d_unit.as<uint32_t>();
     b.counters = h->d_misc.as<unsigned long long>();
     b.out_cursor = h->d_misc.as<unsigned long long>() + MISC_CURSOR;
-    b.ticket = h->d_misc.as<unsigned int>() + 2 * MISC_U32;
-    b.overflow_count = h->d_misc.as<uint32_t>() + 2 * MISC_U32 + 1;
-    b.deep_count = h->d_misc.as<uint32_t>() + 2 * MISC_U32 + 2;
-    b.overflow_list = h->d_overflow.as<uint32_t>();
+    uint32_t *u32 = h->d_misc.as<uint32_t>() + 2 * MISC_U32;
+    b.ticket = u32;
+    b.mid_count = u32 + 3;
+    b.big_count = u32 + 4;
+    b.deep_count = u32 + 5;
+    b.chunk_count = u32 + 6;
+    b.mid_list = h->d_overflow.as<uint32_t>();
+    b.big_list = h->d_big.as<uint32_t>();
     b.deep_list = h->d_deep.as<uint32_t>();
     b.opts = opts.flags;
 
     const int bps = small_blocks_per_sm(cap);
-    if (bps <= 0) return h->fail(BBCP_ERR_CUDA, "first-tier kernel does not fit (shared memory)");
-    const uint32_t *h_u32 = reinterpret_cast<uint32_t *>(h->h_misc);
-    float triage_ms = 0, deep_ms = 0;
+    const int bps_mid = mid_blocks_per_sm(cap_mid);
+    if (bps <= 0 || bps_mid <= 0) return h->fail(BBCP_ERR_CUDA, "propagate kernel does not fit (shared memory)");
+    const uint32_t *h_u32 = reinterpret_cast<uint32_t *>(h->h_misc) + 2 * MISC_U32;
+    float triage_ms = 0, deep_ms = 0, block_ms = 0, mid_ms = 0;
 
     cudaEventRecord(h->ev[0], h->stream);
     for (int attempt = 0; attempt < 8; ++attempt) {
         // room for every self-implying probe (n) plus out_cap stored literals
-        if (!h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4) || (implied && !h->d_impl.reserve((n + out_cap + 4) * 4)))
+        if (!h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4) || (implied && !h->d_impl.reserve((n + out_cap + 4) * 4)) ||
+            !h->d_chunks.reserve((out_cap / 1024 + 64) * 8))
             return h->fail(BBCP_ERR_ALLOC, "device allocation failed (implied literals)");
         b.out_lits = h->d_out.as<int32_t>();
+        b.chunk_list = h->d_chunks.as<uint2>();
         b.out_cap = out_cap;
-        b.worklist = nullptr;
-        b.nwork = 0;
         cudaMemsetAsync(h->d_misc.p, 0, MISC_WORDS64 * 8, h->stream);
         cudaMemsetAsync(b.len + n, 0, 4, h->stream);
         bi.launches = 0;
@@ -248,65 +283,46 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             cudaEventRecord(h->ev[4], h->stream);
             launch_small(dbv, b, cap, bps * h->sm_count, h->stream);
             cudaEventRecord(h->ev[5], h->stream);
-            bi.launches += 2;
+            launch_mid(dbv, b, cap_mid, bps_mid * h->sm_count, h->stream);
+            cudaEventRecord(h->ev[7], h->stream);
+            launch_big(dbv, b, ls, (int)h->big_slabs, h->stream);
+            cudaEventRecord(h->ev[6], h->stream);
+            bi.launches += 4;
             if (implied) {
                 if (!compact(h, b, n)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (compaction)");
-                ++bi.launches;
+                bi.launches += 2;
             }
         }
         cudaMemcpyAsync(h->h_misc, h->d_misc.p, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
+        cudaEventRecord(h->ev[2], h->stream);
         if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "propagate kernels")) return BBCP_ERR_CUDA;
-        if (n) { cudaEventElapsedTime(&triage_ms, h->ev[3], h->ev[4]); cudaEventElapsedTime(&deep_ms, h->ev[4], h->ev[5]); }
-        const uint32_t n_over = h_u32[2 * MISC_U32 + 1];
-        if (n_over && h->h_misc[MISC_CURSOR] <= out_cap) {
-            // second tier: per-warp global slabs sized for the whole variable range
-            const size_t per_worker = (size_t)dbv.nvars_words16 * 4 + ((size_t)dbv.max_var + 1) * 4;
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
-            uint64_t workers = std::min<uint64_t>({(uint64_t)h->sm_count * 8 * LARGE_WARPS, (uint64_t)((n_over + LARGE_WARPS - 1) / LARGE_WARPS) * LARGE_WARPS,
-                                                   std::max<uint64_t>(LARGE_WARPS, (free_b / 2 + h->d_lbits.bytes + h->d_ltrail.bytes) / std::max<size_t>(per_worker, 1))});
-            workers = std::max<uint64_t>(LARGE_WARPS, workers / LARGE_WARPS * LARGE_WARPS);
-            if (workers > h->large_workers || !h->d_lbits.p) {
-                h->d_lbits.release();
-                h->d_ltrail.release();
-                if (!h->d_lbits.reserve(workers * dbv.nvars_words16 * 4, true) || !h->d_ltrail.reserve(workers * ((size_t)dbv.max_var + 1) * 4))
-                    return h->fail(BBCP_ERR_ALLOC, "device allocation failed (second-tier state)");
-                h->large_workers = (uint32_t)workers;
-            }
-            LargeState ls;
-            ls.bits = h->d_lbits.as<uint32_t>();
-            ls.trail = h->d_ltrail.as<uint32_t>();
-            b.worklist = b.overflow_list;
-            b.nwork = n_over;
-            cudaMemsetAsync(b.ticket, 0, 4, h->stream);
-            launch_large(dbv, b, ls, (int)(std::min<uint64_t>(workers, h->large_workers) / LARGE_WARPS), h->stream);
-            ++bi.launches;
-            if (implied) {
-                if (!compact(h, b, n)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (compaction)");
-                ++bi.launches;
-            }
-            cudaMemcpyAsync(h->h_misc, h->d_misc.p, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
-            if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "second-tier kernel")) return BBCP_ERR_CUDA;
+        if (n) {
+            cudaEventElapsedTime(&triage_ms, h->ev[3], h->ev[4]);
+            cudaEventElapsedTime(&deep_ms, h->ev[4], h->ev[5]);
+            cudaEventElapsedTime(&block_ms, h->ev[5], h->ev[6]);
+            cudaEventElapsedTime(&mid_ms, h->ev[5], h->ev[7]);
         }
         const uint64_t cursor = h->h_misc[MISC_CURSOR];
-        if (cursor <= out_cap) { bi.n_implied = implied ? h->h_misc[MISC_TOTAL] : 0; break; }
+        if (cursor <= out_cap) { bi.n_implied = implied ? h->h_misc[MISC_TOTAL] : 0; if (!opts.out_capacity) h->out_cap_hint = cursor; break; }
         // implied-literal buffer too small: redo the batch with room for everything that was asked for
         out_cap = std::max<uint64_t>(cursor + cursor / 8, out_cap * 2);
         if (attempt == 7) return h->fail(BBCP_ERR_ALLOC, "implied-literal buffer keeps overflowing");
     }
-    if (!implied) cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
-    cudaEventRecord(h->ev[2], h->stream);
-    if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "batch")) return BBCP_ERR_CUDA;
+    if (!implied) {
+        cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
+        if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "batch")) return BBCP_ERR_CUDA;
+    }
 
     bi.props_all = h->h_misc[C_PROPS_ALL];
     bi.props_ref = h->h_misc[C_PROPS_REF];
     bi.slots = h->h_misc[C_SLOTS];
     bi.clause_fetches = h->h_misc[C_CLAUSE_FETCH];
     bi.n_large = h->h_misc[C_LARGE];
+    bi.n_mid = h->h_misc[C_MID];
     bi.n_ok = h->h_misc[C_OK];
     bi.n_conflict = h->h_misc[C_CONFLICT];
     bi.n_skipped = h->h_misc[C_SKIPPED];
-    bi.n_deep = h_u32[2 * MISC_U32 + 2];
+    bi.n_deep = h_u32[5];
     // bytes model: triage = 1 B of literal facts + 1 B flag + 4 B size per item (+ 16 B offsets and
     // 4 B literal for explicit probe lists); propagation = row headers, row slots, clause units, stored
     // implied literals (kernel counters) + the per-item record (flag, size, position) of the queued items
@@ -315,8 +331,10 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     cudaEventElapsedTime(&bi.total_ms, h->ev[0], h->ev[2]);
     bi.triage_ms = triage_ms;
     bi.deep_ms = deep_ms;
+    bi.block_ms = block_ms;
+    bi.mid_ms = mid_ms;
     bi.tier1_ms = triage_ms + deep_ms;
-    bi.kernel_ms = bi.total_ms;
+    bi.kernel_ms = triage_ms + deep_ms + block_ms;
     h->last_n = n;
     h->last_n_implied = bi.n_implied;
     h->have_batch = true;
@@ -352,7 +370,7 @@ void bbcp_release(bbcp_handle *h)
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
         for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_failed, &h->d_unit, &h->d_flag, &h->d_raw_off, &h->d_len,
-                          &h->d_out, &h->d_off, &h->d_impl, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_deep, &h->d_misc, &h->d_lbits,
+                          &h->d_out, &h->d_off, &h->d_impl, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_big, &h->d_deep, &h->d_chunks, &h->d_misc, &h->d_lbits,
                           &h->d_ltrail, &h->d_cubtmp})
             b->release();
         if (h->h_misc) cudaFreeHost(h->h_misc);

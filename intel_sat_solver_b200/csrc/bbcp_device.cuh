@@ -29,7 +29,7 @@ struct DbView {
 constexpr uint8_t LI_TRUE_L0 = 1, LI_FALSE_L0 = 2, LI_MAPPED = 4, LI_HAS_BIN = 8, LI_NONEMPTY = 16;
 constexpr uint32_t LEN_SELF = 0x80000000u;   // len[] flag: the implied set is the item's own literal (not stored)
 
-enum Counter { C_PROPS_ALL = 0, C_PROPS_REF, C_SLOTS, C_CLAUSE_FETCH, C_BYTES, C_LARGE, C_OK, C_CONFLICT, C_SKIPPED, C_N };
+enum Counter { C_PROPS_ALL = 0, C_PROPS_REF, C_SLOTS, C_CLAUSE_FETCH, C_BYTES, C_LARGE, C_MID, C_OK, C_CONFLICT, C_SKIPPED, C_N };
 
 struct BatchView {
     // input: cubes (external literals) or, when cube_off == nullptr, the probe universe
@@ -37,8 +37,6 @@ struct BatchView {
     const uint64_t *cube_off;
     uint64_t first;             // universe index of item 0 (probe mode)
     uint64_t n;                 // items in the batch
-    const uint32_t *worklist;   // large tier: the item indices to run (nullptr = all items)
-    uint32_t nwork;
     // output
     uint8_t *flag;              // [n]
     uint64_t *raw_off;          // [n] position of the item's implied set in out_lits
@@ -48,11 +46,15 @@ struct BatchView {
     unsigned long long *out_cursor;
     uint32_t *failed, *unit;    // bitmaps over internal literals (probe mode only)
     unsigned long long *counters;
-    uint32_t *overflow_list;    // items that did not fit the shared-memory state
-    uint32_t *overflow_count;
-    unsigned int *ticket;       // dynamic scheduler over the queued items
+    uint32_t *mid_list;         // items that did not fit the warp-private shared-memory state
+    uint32_t *mid_count;
+    uint32_t *big_list;         // items that did not fit the CTA-wide shared-memory state either
+    uint32_t *big_count;
+    unsigned int *ticket;       // [3] dynamic schedulers of k_deep / k_block<mid> / k_block<big>
     uint32_t *deep_list;        // items queued by the triage for propagation
     uint32_t *deep_count;
+    uint2 *chunk_list;          // (item, chunk) pairs of long implied sets, filled by k_gather for k_gather_long
+    uint32_t *chunk_count;
     uint32_t opts;
 };
 
@@ -63,17 +65,21 @@ constexpr uint8_t FLAG_OVERFLOW = 250;      // internal: re-run in the global-st
 constexpr uint8_t FLAG_OUT_OVERFLOW = 251;  // internal: implied-literal buffer full, re-run in a later launch
 
 struct LargeState {
-    uint32_t *bits;    // [workers][nvars_words16] 2 bits per var, all zero between probes
-    uint32_t *trail;   // [workers][max_var + 1]
+    uint32_t *bits;    // [slabs][nvars_words16] 2 bits per var, all zero between probes
+    uint32_t *trail;   // [slabs][max_var + 1]
 };
 
 void launch_triage(const BatchView &b, const DbView &db, int blocks, cudaStream_t s);
 void launch_small(const DbView &db, const BatchView &b, uint32_t trail_cap, int blocks, cudaStream_t s);
-void launch_large(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s);
+void launch_mid(const DbView &db, const BatchView &b, uint32_t cap, int blocks, cudaStream_t s);
+void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s);
+size_t mid_smem_bytes(uint32_t trail_cap);
+int mid_blocks_per_sm(uint32_t trail_cap);
 void launch_gather(const BatchView &b, const uint64_t *off, int32_t *dst, cudaStream_t s);
 size_t small_smem_bytes(uint32_t trail_cap);
 int small_blocks_per_sm(uint32_t trail_cap);
 constexpr int SMALL_WARPS = 4;   // warps (= concurrent probes) per CTA, first tier
-constexpr int LARGE_WARPS = 4;
+constexpr int MID_THREADS = 128;   // second tier: 4 warps share one probe, state in shared memory
+constexpr int BIG_THREADS = 512;   // third tier: 16 warps share one probe, state in a global slab
 
 }  // namespace bbcp

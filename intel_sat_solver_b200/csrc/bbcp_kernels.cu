@@ -137,25 +137,63 @@ struct WarpCounters {
     }
 };
 
-// Commit one round of candidate implications (one candidate literal per lane, 0 = none). Warp-converged.
-// Returns 0 ok, 1 conflict, 2 state overflow.
-template <class S>
-__device__ __forceinline__ int commit(S &st, uint32_t cand, uint32_t &tail)
-{
-    const bool has = cand != 0;
-    // same literal implied by several clauses in this step: keep the lowest lane (deterministic trail order)
-    const unsigned same = __match_any_sync(FULL, has ? cand : (0x80000000u | (uint32_t)lane_id()));
-    const bool leader = has && (lane_id() == __ffs(same) - 1);
-    uint32_t slot = 0;
-    const int r = leader ? st.insert(cand, slot) : 1;
-    const bool any_conf = __any_sync(FULL, r == 2);
-    const unsigned newm = __ballot_sync(FULL, leader && r == 0);
-    const uint32_t nnew = __popc(newm);
-    if (tail + nnew > st.cap) return 2;  // caller wipes the whole table: the new entries are not on the trail
-    if (leader && r == 0) st.tset(tail + __popc(newm & lanemask_lt()), cand, slot);
-    tail += nnew;
-    return any_conf ? 1 : 0;
-}
+// ---------------------------------------------------------------- where newly implied literals go
+// WarpTail: one warp owns the probe, the trail tail is a register. BlockTail: the warps of a CTA share one
+// probe, the tail and the conflict / overflow latches live in shared memory.
+struct WarpTail {
+    uint32_t tail;
+    __device__ __forceinline__ uint32_t get() const { return tail; }
+    __device__ __forceinline__ bool aborted() const { return false; }
+    __device__ __forceinline__ void latch_conflict() {}
+    // Commit one round of candidate implications (one candidate per lane, 0 = none). Warp-converged.
+    // Returns 0 ok, 1 conflict, 2 state overflow.
+    template <class S>
+    __device__ __forceinline__ int commit(S &st, uint32_t cand)
+    {
+        const bool has = cand != 0;
+        // same literal implied by several clauses in this step: keep the lowest lane (deterministic trail order)
+        const unsigned same = __match_any_sync(FULL, has ? cand : (0x80000000u | (uint32_t)lane_id()));
+        const bool leader = has && (lane_id() == __ffs(same) - 1);
+        uint32_t slot = 0;
+        const int r = leader ? st.insert(cand, slot) : 1;
+        const bool any_conf = __any_sync(FULL, r == 2);
+        const unsigned newm = __ballot_sync(FULL, leader && r == 0);
+        const uint32_t nnew = __popc(newm);
+        if (tail + nnew > st.cap) return 2;  // caller wipes the whole table: the new entries are not on the trail
+        if (leader && r == 0) st.tset(tail + __popc(newm & lanemask_lt()), cand, slot);
+        tail += nnew;
+        return any_conf ? 1 : 0;
+    }
+};
+
+struct BlockTail {
+    uint32_t *ctl;  // shared: [0] tail, [1] conflict latch, [2] overflow latch
+    __device__ __forceinline__ uint32_t get() const { return *(volatile uint32_t *)&ctl[0]; }
+    __device__ __forceinline__ bool aborted() const { return (*(volatile uint32_t *)&ctl[1] | *(volatile uint32_t *)&ctl[2]) != 0; }
+    __device__ __forceinline__ void latch_conflict() { if (lane_id() == 0) ctl[1] = 1; }
+    template <class S>
+    __device__ __forceinline__ int commit(S &st, uint32_t cand)
+    {
+        const bool has = cand != 0;
+        const unsigned same = __match_any_sync(FULL, has ? cand : (0x80000000u | (uint32_t)lane_id()));
+        const bool leader = has && (lane_id() == __ffs(same) - 1);
+        uint32_t slot = 0;
+        const int r = leader ? st.insert(cand, slot) : 1;   // duplicates across warps: only one insert returns 0
+        const bool any_conf = __any_sync(FULL, r == 2);
+        const unsigned newm = __ballot_sync(FULL, leader && r == 0);
+        const uint32_t nnew = __popc(newm);
+        int ret = 0;
+        if (nnew) {
+            uint32_t pos = 0;
+            if (lane_id() == 0) pos = atomicAdd(&ctl[0], nnew);
+            pos = __shfl_sync(FULL, pos, 0);
+            if (pos + nnew > st.cap) { if (lane_id() == 0) ctl[2] = 1; ret = 2; }
+            else if (leader && r == 0) st.tset(pos + __popc(newm & lanemask_lt()), cand, slot);
+        }
+        if (any_conf) { if (lane_id() == 0) ctl[1] = 1; if (!ret) ret = 1; }
+        return ret;
+    }
+};
 
 // Judge a long clause (>= 4 literals) from scratch: TopiBcp.cc:262-367 without the watch bookkeeping.
 // Returns the literal to imply (0 = none); sets confl when every literal is false.
@@ -187,97 +225,109 @@ __device__ __forceinline__ uint32_t visit_long(const DbView &db, const S &st, ui
     return cand;
 }
 
-// Breadth-first unit propagation of trail[0..tail) to fixpoint. Returns 0 fixpoint, 1 conflict, 2 overflow.
+// One warp scans the rows of up to 32 newly true literals (lane i holds literal p for i < B): one header
+// gather, then the union of the rows is flattened and walked 32 eight-byte slots at a time.
+// Returns 0 ok, 1 conflict, 2 overflow.
+template <class S, class T>
+__device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t p, uint32_t B, bool bins_only, WarpCounters &wc)
+{
+    const int lane = lane_id();
+    uint4 hd = make_uint4(0, 0, 0, 0);
+    if (lane < (int)B) hd = __ldg(&db.hdr[p ^ 1u]);
+    const uint32_t nb2 = (hd.y + 1u) >> 1;
+    const uint32_t cnt = bins_only ? nb2 : nb2 + hd.z + hd.w;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t excl = incl - cnt;
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    wc.props_all += B;
+    wc.props_ref += __popc(__ballot_sync(FULL, (hd.y | hd.z | hd.w) != 0));
+    wc.slots += total;
+    wc.bytes += 16ull * B + 8ull * total;
+
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t g = base + lane;
+        const bool active = g < total;
+        // owner row of slot g: the largest lane i with excl_i <= g
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+            const int mid = lo + step;
+            const uint32_t e = __shfl_sync(FULL, excl, mid & 31);
+            if (mid < 32 && e <= g) lo = mid;
+        }
+        const uint32_t r_start = __shfl_sync(FULL, hd.x, lo);
+        const uint32_t r_nb2 = (__shfl_sync(FULL, hd.y, lo) + 1u) >> 1;
+        const uint32_t r_nt = __shfl_sync(FULL, hd.z, lo);
+        const uint32_t k = g - __shfl_sync(FULL, excl, lo);
+        uint32_t c0 = 0, c1 = 0;
+        bool confl = false;
+        uint32_t fetched16 = 0;
+        if (active) {
+            const uint2 s = __ldg(&db.slots[r_start + k]);
+            if (k < r_nb2) {
+                // binary clauses (TopiBcp.cc:207-246)
+                int v = st.lookup(s.x);
+                if (v == 0) c0 = s.x; else if (v == 2) confl = true;
+                if (s.y) {
+                    v = st.lookup(s.y);
+                    if (v == 0) c1 = s.y; else if (v == 2) confl = true;
+                }
+            } else if (k < r_nb2 + r_nt) {
+                // inline ternary clause (falsified literal, s.x, s.y)
+                const int va = st.lookup(s.x);
+                if (va != 1) {
+                    const int vb = st.lookup(s.y);
+                    if (vb != 1) {
+                        if (va == 2 && vb == 2) confl = true;
+                        else if (va == 2) c0 = s.y;
+                        else if (vb == 2) c0 = s.x;
+                    }
+                }
+            } else {
+                // long clause: cached literal first (TopiBcp.cc:255-259), then the clause itself
+                if (st.lookup(s.x) != 1) c0 = visit_long(db, st, s.y, confl, fetched16);
+            }
+        }
+        const unsigned fm = __ballot_sync(FULL, fetched16 != 0);
+        if (fm) {
+            uint32_t f = fetched16;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) f += __shfl_xor_sync(FULL, f, d);
+            wc.fetches += __popc(fm);
+            wc.bytes += 16ull * f;
+        }
+        if (__any_sync(FULL, confl)) { tl.latch_conflict(); return 1; }
+        if (__any_sync(FULL, c0 != 0)) {
+            const int r = tl.commit(st, c0);
+            if (r) return r;
+        }
+        if (__any_sync(FULL, c1 != 0)) {
+            const int r = tl.commit(st, c1);
+            if (r) return r;
+        }
+        __syncwarp();
+        if (tl.aborted()) return 1;  // another warp of the CTA hit a conflict / overflow
+    }
+    return 0;
+}
+
+// Breadth-first unit propagation of trail[0..tail) to fixpoint by ONE warp. Returns 0 fixpoint, 1 conflict, 2 overflow.
 template <class S>
-__device__ int propagate(const DbView &db, S &st, uint32_t &tail, bool prune, WarpCounters &wc)
+__device__ int propagate(const DbView &db, S &st, WarpTail &tl, bool prune, WarpCounters &wc)
 {
     const int lane = lane_id();
     uint32_t head = 0;
-    while (head < tail) {
-        const uint32_t B = min(32u, tail - head);
+    while (head < tl.tail) {
+        const uint32_t B = min(32u, tl.tail - head);
         const uint32_t p = lane < (int)B ? st.tget(head + lane) : 0u;
-        uint4 hd = make_uint4(0, 0, 0, 0);
-        if (lane < (int)B) hd = __ldg(&db.hdr[p ^ 1u]);
         // while a single literal is assigned only binary clauses can become unit
-        const bool bins_only = prune && tail == 1;
-        const uint32_t nb2 = (hd.y + 1u) >> 1;
-        const uint32_t cnt = bins_only ? nb2 : nb2 + hd.z + hd.w;
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const uint32_t excl = incl - cnt;
-        const uint32_t total = __shfl_sync(FULL, incl, 31);
-        wc.props_all += B;
-        wc.props_ref += __popc(__ballot_sync(FULL, (hd.y | hd.z | hd.w) != 0));
-        wc.slots += total;
-        wc.bytes += 16ull * B + 8ull * total;
-
-        for (uint32_t base = 0; base < total; base += 32) {
-            const uint32_t g = base + lane;
-            const bool active = g < total;
-            // owner row of slot g: the largest lane i with excl_i <= g
-            int lo = 0;
-#pragma unroll
-            for (int step = 16; step; step >>= 1) {
-                const int mid = lo + step;
-                const uint32_t e = __shfl_sync(FULL, excl, mid & 31);
-                if (mid < 32 && e <= g) lo = mid;
-            }
-            const uint32_t r_start = __shfl_sync(FULL, hd.x, lo);
-            const uint32_t r_nb2 = (__shfl_sync(FULL, hd.y, lo) + 1u) >> 1;
-            const uint32_t r_nt = __shfl_sync(FULL, hd.z, lo);
-            const uint32_t k = g - __shfl_sync(FULL, excl, lo);
-            uint32_t c0 = 0, c1 = 0;
-            bool confl = false;
-            uint32_t fetched16 = 0;
-            if (active) {
-                const uint2 s = __ldg(&db.slots[r_start + k]);
-                if (k < r_nb2) {
-                    // binary clauses (TopiBcp.cc:207-246)
-                    int v = st.lookup(s.x);
-                    if (v == 0) c0 = s.x; else if (v == 2) confl = true;
-                    if (s.y) {
-                        v = st.lookup(s.y);
-                        if (v == 0) c1 = s.y; else if (v == 2) confl = true;
-                    }
-                } else if (k < r_nb2 + r_nt) {
-                    // inline ternary clause (falsified literal, s.x, s.y)
-                    const int va = st.lookup(s.x);
-                    if (va != 1) {
-                        const int vb = st.lookup(s.y);
-                        if (vb != 1) {
-                            if (va == 2 && vb == 2) confl = true;
-                            else if (va == 2) c0 = s.y;
-                            else if (vb == 2) c0 = s.x;
-                        }
-                    }
-                } else {
-                    // long clause: cached literal first (TopiBcp.cc:255-259), then the clause itself
-                    if (st.lookup(s.x) != 1) c0 = visit_long(db, st, s.y, confl, fetched16);
-                }
-            }
-            const unsigned fm = __ballot_sync(FULL, fetched16 != 0);
-            if (fm) {
-                uint32_t f = fetched16;
-#pragma unroll
-                for (int d = 16; d; d >>= 1) f += __shfl_xor_sync(FULL, f, d);
-                wc.fetches += __popc(fm);
-                wc.bytes += 16ull * f;
-            }
-            if (__any_sync(FULL, confl)) return 1;
-            if (__any_sync(FULL, c0 != 0)) {
-                const int r = commit(st, c0, tail);
-                if (r) return r;
-            }
-            if (__any_sync(FULL, c1 != 0)) {
-                const int r = commit(st, c1, tail);
-                if (r) return r;
-            }
-            __syncwarp();
-        }
+        const int r = process_batch(db, st, tl, p, B, prune && tl.tail == 1, wc);
+        if (r) return r;
         head += B;
     }
     return 0;
@@ -285,12 +335,11 @@ __device__ int propagate(const DbView &db, S &st, uint32_t &tail, bool prune, Wa
 
 // Load a cube into the (empty) state with the semantics of HandleAssumptions (Topi.cc:797-938).
 // Returns the flag to report if the cube is decided here (2,3,4 or 1), FLAG_OVERFLOW, or 0xff = propagate.
-template <class S>
-__device__ int load_cube(const DbView &db, S &st, const int32_t *lits, uint32_t n, uint32_t &tail)
+template <class S, class T>
+__device__ int load_cube(const DbView &db, S &st, const int32_t *lits, uint32_t n, T &tl)
 {
     const int lane = lane_id();
     bool unmapped = false, false_l0 = false, conflict = false, overflow = false;
-    tail = 0;
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t i = base + lane;
         uint32_t cand = 0;
@@ -306,18 +355,17 @@ __device__ int load_cube(const DbView &db, S &st, const int32_t *lits, uint32_t 
             }
         }
         if (!overflow && !conflict) {
-            const int r = commit(st, cand, tail);
+            const int r = tl.commit(st, cand);
             if (r == 1) conflict = true;
             if (r == 2) overflow = true;
         }
         __syncwarp();
     }
-    if (overflow) { st.wipe(); tail = 0; }
     if (__any_sync(FULL, unmapped)) return FLAG_UNMAPPED;
     if (__any_sync(FULL, false_l0)) return FLAG_FALSE_L0;
     if (overflow) return FLAG_OVERFLOW;
     if (conflict) return FLAG_CONFLICT;
-    if (tail == 0) return FLAG_TRIVIAL_L0;
+    if (tl.get() == 0) return FLAG_TRIVIAL_L0;
     return 0xff;
 }
 
@@ -380,16 +428,15 @@ __device__ __forceinline__ Item get_item(const BatchView &b, uint64_t item)
 }
 
 // load_cube for probe mode (a single literal, no memory to read)
-template <class S>
-__device__ int load_probe(const DbView &db, S &st, int32_t l, uint32_t &tail)
+template <class S, class T>
+__device__ int load_probe(const DbView &db, S &st, int32_t l, T &tl)
 {
     const uint32_t v = (uint32_t)(l < 0 ? -l : l);
     const uint8_t li = (int32_t)v <= db.max_var ? db.litinfo[2u * v + (l < 0)] : 0;
-    tail = 0;
     if (!(li & LI_MAPPED)) return FLAG_UNMAPPED;
     if (li & LI_FALSE_L0) return FLAG_FALSE_L0;
     if (li & LI_TRUE_L0) return FLAG_TRIVIAL_L0;
-    const int r = commit(st, lane_id() == 0 ? 2u * v + (l < 0) : 0u, tail);
+    const int r = tl.commit(st, lane_id() == 0 ? 2u * v + (l < 0) : 0u);
     __syncwarp();
     return r == 2 ? FLAG_OVERFLOW : 0xff;
 }
@@ -405,7 +452,7 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
     unsigned long long off = 0;
     if (res == 2) {
         flag = FLAG_OVERFLOW;
-        if (lane == 0) b.overflow_list[atomicAdd(b.overflow_count, 1u)] = (uint32_t)item;
+        if (lane == 0) b.mid_list[atomicAdd(b.mid_count, 1u)] = (uint32_t)item;
     } else if (res == 1) {
         flag = FLAG_CONFLICT;
         if (it.probe_lit && lane == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
@@ -534,67 +581,193 @@ k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t
         if (t >= ndeep) break;
         const uint64_t it_idx = b.deep_list[t];
         const Item it = get_item(b, it_idx);
-        uint32_t tail = 0;
-        int f = it.probe_lit ? load_probe(db, st, it.probe_lit, tail) : load_cube(db, st, it.lits, it.n, tail);
+        WarpTail tl{0};
+        int f = it.probe_lit ? load_probe(db, st, it.probe_lit, tl) : load_cube(db, st, it.lits, it.n, tl);
         int res;
-        if (f == 0xff) res = propagate(db, st, tail, prune, wc);
+        if (f == 0xff) res = propagate(db, st, tl, prune, wc);
         else if (f == FLAG_OVERFLOW) res = 2;
         else if (f == FLAG_CONFLICT) res = 1;
         else {
-            st.cleanup(tail);
+            st.cleanup(tl.tail);
             if (lane == 0) { b.flag[it_idx] = (uint8_t)f; b.len[it_idx] = 0; b.raw_off[it_idx] = 0; }
             ++wc.n_skip;
             __syncwarp();
             continue;
         }
-        finish_small(b, st, it_idx, it, res, tail, wc);
+        finish_small(b, st, it_idx, it, res, tl.tail, wc);
     }
     wc.flush(b.counters);
 }
 
-// ---------------------------------------------------------------- second tier: global-slab state, any size
-__global__ void __launch_bounds__(LARGE_WARPS * 32)
-k_large(const DbView db, const BatchView b, const LargeState ls)
+// ---------------------------------------------------------------- block-cooperative tiers
+// One CTA per probe: the warps share the per-probe state and walk each breadth-first level of the trail
+// together (level-synchronous, two barriers per level). Second tier: state in shared memory (hash + trail
+// of cap_mid literals); third tier: dense 2-bit assignment + trail in a per-CTA global slab, any size.
+struct SmemBlockState {
+    uint32_t *hash;
+    uint32_t *trail;
+    uint32_t log_hs, cap;
+    __device__ __forceinline__ uint32_t h(uint32_t var) const { return (var * 0x9E3779B1u) >> (32 - log_hs); }
+    __device__ __forceinline__ int lookup(uint32_t lit) const
+    {
+        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
+        uint32_t s = h(var);
+        for (;;) {
+            const uint32_t k = *(volatile uint32_t *)&hash[s];
+            if (k == 0) return 0;
+            if ((k >> 1) == var) return k == lit ? 1 : 2;
+            s = (s + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ int insert(uint32_t lit, uint32_t &slot)
+    {
+        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
+        uint32_t s = h(var);
+        slot = 0;
+        for (;;) {
+            const uint32_t old = atomicCAS(&hash[s], 0u, lit);
+            if (old == 0) return 0;
+            if ((old >> 1) == var) return old == lit ? 1 : 2;
+            s = (s + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ uint32_t tget(uint32_t i) const { return trail[i]; }
+    __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t) { trail[i] = lit; }
+};
+
+// block bitonic sort of a[0..n2) ascending, n2 a power of two, in shared memory
+__device__ void block_bitonic_sort(uint32_t *a, uint32_t n2)
 {
-    const int lane = lane_id();
-    const uint32_t gw = blockIdx.x * LARGE_WARPS + (threadIdx.x >> 5);
-    GmemState st;
-    st.bits = ls.bits + (size_t)gw * db.nvars_words16;
-    st.trail = ls.trail + (size_t)gw * ((size_t)db.max_var + 1);
-    st.cap = (uint32_t)db.max_var + 1;
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < n2 / 2; t += blockDim.x) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t ixj = i | j;
+                const bool up = (i & k) == 0;
+                const uint32_t x = a[i], y = a[ixj];
+                if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// level-synchronous propagation by all warps of the CTA. ctl[0] tail, ctl[1] conflict, ctl[2] overflow.
+template <class S>
+__device__ void block_propagate(const DbView &db, S &st, uint32_t *ctl, bool prune, WarpCounters &wc)
+{
+    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    BlockTail tl{ctl};
+    uint32_t head = 0;
+    for (;;) {
+        __syncthreads();
+        const uint32_t level_end = ctl[0];
+        const bool stop = (ctl[1] | ctl[2]) != 0 || head >= level_end;
+        __syncthreads();   // everybody has its snapshot before anyone appends
+        if (stop) break;
+        const bool bins_only = prune && level_end == 1;
+        for (uint32_t bse = head + warp * 32; bse < level_end; bse += nwarps * 32) {
+            const uint32_t B = min(32u, level_end - bse);
+            const uint32_t p = lane < (int)B ? st.tget(bse + lane) : 0u;
+            if (process_batch(db, st, tl, p, B, bins_only, wc)) break;
+        }
+        head = level_end;
+    }
+}
+
+template <bool GMEM>
+__global__ void __launch_bounds__(512) k_block(const DbView db, const BatchView b, const LargeState ls, const uint32_t log_hs, const uint32_t cap)
+{
+    extern __shared__ uint32_t smem[];
+    __shared__ uint32_t ctl[8];      // 0 tail, 1 conflict, 2 overflow, 3 load result, 4 ticket, 5 vmin, 6 vmax
+    __shared__ unsigned long long s_off;
+    __shared__ uint32_t s_warp[17];
+    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t *list = GMEM ? b.big_list : b.mid_list;
+    const uint32_t count = GMEM ? *b.big_count : *b.mid_count;
+    if (blockIdx.x >= count) return;
+    unsigned int *ticket = b.ticket + (GMEM ? 2 : 1);
+
+    SmemBlockState ss;
+    GmemState gs;
+    if (GMEM) {
+        gs.bits = ls.bits + (size_t)blockIdx.x * db.nvars_words16;
+        gs.trail = ls.trail + (size_t)blockIdx.x * ((size_t)db.max_var + 1);
+        gs.cap = (uint32_t)db.max_var + 1;
+    } else {
+        ss.hash = smem;
+        ss.trail = smem + (1u << log_hs);
+        ss.log_hs = log_hs;
+        ss.cap = cap;
+        for (uint32_t i = threadIdx.x; i < (1u << log_hs); i += blockDim.x) ss.hash[i] = 0;
+    }
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
-    const bool probe_mode = b.cube_off == nullptr;
     WarpCounters wc;
     for (;;) {
-        unsigned t = 0;
-        if (lane == 0) t = atomicAdd(b.ticket, 1u);
-        t = __shfl_sync(FULL, t, 0);
-        if (t >= b.nwork) break;
-        const uint64_t item = b.worklist ? b.worklist[t] : t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ctl[4] = atomicAdd(ticket, 1u);
+            ctl[0] = ctl[1] = ctl[2] = 0;
+            ctl[3] = 0xff;
+            ctl[5] = 0xffffffffu;
+            ctl[6] = 0;
+        }
+        __syncthreads();
+        const uint32_t t = ctl[4];
+        if (t >= count) break;
+        const uint64_t item = list[t];
         const Item it = get_item(b, item);
-        uint32_t tail = 0;
-        int f = it.probe_lit ? load_probe(db, st, it.probe_lit, tail) : load_cube(db, st, it.lits, it.n, tail);
-        int res = 0;
-        if (f == 0xff) res = propagate(db, st, tail, prune, wc);
-        else if (f == FLAG_CONFLICT) res = 1;
+        if (warp == 0) {
+            BlockTail tl{ctl};
+            int f;
+            if (GMEM) f = it.probe_lit ? load_probe(db, gs, it.probe_lit, tl) : load_cube(db, gs, it.lits, it.n, tl);
+            else f = it.probe_lit ? load_probe(db, ss, it.probe_lit, tl) : load_cube(db, ss, it.lits, it.n, tl);
+            if (lane == 0) ctl[3] = (uint32_t)f;
+        }
+        __syncthreads();
+        const uint32_t f = ctl[3];
+        if (f == 0xff) {
+            if (GMEM) block_propagate(db, gs, ctl, prune, wc); else block_propagate(db, ss, ctl, prune, wc);
+        }
+        __syncthreads();
+        const uint32_t tail = min(ctl[0], GMEM ? gs.cap : ss.cap);
+        const bool overflow = ctl[2] != 0 || f == FLAG_OVERFLOW;
+        const bool conflict = ctl[1] != 0 || f == FLAG_CONFLICT;
         uint8_t flag = (uint8_t)f;
         uint32_t len = 0;
         unsigned long long off = 0;
-        if (f == 0xff || f == FLAG_CONFLICT) {
-            if (res == 1) {
+        if (f == 0xff || f == FLAG_CONFLICT || f == FLAG_OVERFLOW) {
+            if (overflow && !GMEM) {
+                flag = FLAG_OVERFLOW;
+                if (threadIdx.x == 0) b.big_list[atomicAdd(b.big_count, 1u)] = (uint32_t)item;
+            } else if (conflict) {
                 flag = FLAG_CONFLICT;
-                if (it.probe_lit && lane == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
+                if (it.probe_lit && threadIdx.x == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
             } else {
                 flag = FLAG_OK;
                 if (b.opts & OPT_IMPLIED) {
-                    off = out_alloc(b, tail);
+                    if (threadIdx.x == 0) {
+                        const unsigned long long o = atomicAdd(b.out_cursor, (unsigned long long)tail);
+                        s_off = o + tail <= b.out_cap ? o : ~0ull;
+                    }
+                    __syncthreads();
+                    off = s_off;
                     if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
-                    else {
+                    else if (!GMEM) {
+                        len = tail;
+                        uint32_t n2 = 1;
+                        while (n2 < tail) n2 <<= 1;
+                        for (uint32_t i = tail + threadIdx.x; i < n2; i += blockDim.x) ss.trail[i] = 0xffffffffu;
+                        __syncthreads();
+                        if (tail > 1) block_bitonic_sort(ss.trail, n2);
+                        for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) b.out_lits[off + i] = to_ext(ss.trail[i]);
+                        wc.bytes += warp == 0 ? 4ull * tail : 0ull;
+                    } else {
                         // ordered emission: sweep the dense assignment between the smallest and largest assigned var
                         len = tail;
                         uint32_t vmin = 0xffffffffu, vmax = 0;
-                        for (uint32_t i = lane; i < tail; i += 32) {
-                            const uint32_t var = st.tget(i) >> 1;
+                        for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
+                            const uint32_t var = gs.tget(i) >> 1;
                             vmin = min(vmin, var);
                             vmax = max(vmax, var);
                         }
@@ -603,10 +776,13 @@ k_large(const DbView db, const BatchView b, const LargeState ls)
                             vmin = min(vmin, __shfl_xor_sync(FULL, vmin, d));
                             vmax = max(vmax, __shfl_xor_sync(FULL, vmax, d));
                         }
+                        if (lane == 0) { atomicMin(&ctl[5], vmin); atomicMax(&ctl[6], vmax); }
+                        __syncthreads();
+                        const uint32_t w0 = ctl[5] >> 4, w1 = ctl[6] >> 4;
                         unsigned long long w = off;
-                        for (uint32_t wbase = vmin >> 4; wbase <= (vmax >> 4); wbase += 32) {
-                            const uint32_t wi = wbase + lane;
-                            const uint32_t word = wi <= (vmax >> 4) ? __ldcg(&st.bits[wi]) : 0u;
+                        for (uint32_t wbase = w0; wbase <= w1; wbase += blockDim.x) {
+                            const uint32_t wi = wbase + threadIdx.x;
+                            const uint32_t word = wi <= w1 ? __ldcg(&gs.bits[wi]) : 0u;
                             const uint32_t nz = (word | (word >> 1)) & 0x55555555u;  // one bit per assigned var
                             const uint32_t c = __popc(nz);
                             uint32_t incl = c;
@@ -615,7 +791,11 @@ k_large(const DbView db, const BatchView b, const LargeState ls)
                                 const uint32_t x = __shfl_up_sync(FULL, incl, d);
                                 if (lane >= d) incl += x;
                             }
-                            unsigned long long o = w + (incl - c);
+                            if (lane == 31) s_warp[warp] = incl;
+                            __syncthreads();
+                            uint32_t before = 0, total = 0;
+                            for (int k = 0; k < nwarps; ++k) { const uint32_t x = s_warp[k]; total += x; if (k < warp) before += x; }
+                            unsigned long long o = w + before + (incl - c);
                             uint32_t m = nz;
                             while (m) {
                                 const int bpos = __ffs(m) - 1;
@@ -624,33 +804,46 @@ k_large(const DbView db, const BatchView b, const LargeState ls)
                                 const bool isneg = ((word >> bpos) & 3u) == 2u;
                                 b.out_lits[o++] = isneg ? -(int32_t)var : (int32_t)var;
                             }
-                            w += __shfl_sync(FULL, incl, 31);
+                            w += total;
+                            __syncthreads();
                         }
-                        wc.bytes += 4ull * tail + 4ull * ((vmax >> 4) - (vmin >> 4) + 1);
+                        wc.bytes += warp == 0 ? 4ull * tail + 4ull * (w1 - w0 + 1) : 0ull;
                     }
                 }
             }
         }
-        st.cleanup(tail);
-        if (lane == 0) {
-            b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
-            atomicAdd(&b.counters[C_LARGE], 1ull);
+        __syncthreads();
+        // leave the state empty for the next probe
+        if (GMEM) {
+            for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
+                const uint32_t var = gs.tget(i) >> 1;
+                atomicAnd(&gs.bits[var >> 4], ~(3u << ((var & 15u) * 2u)));
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < (1u << log_hs); i += blockDim.x) ss.hash[i] = 0;
         }
-        wc.n_ok += flag == FLAG_OK;
-        wc.n_conf += flag == FLAG_CONFLICT;
-        wc.n_skip += flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED;
-        __syncwarp();
+        if (threadIdx.x == 0) {
+            b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
+            if (flag != FLAG_OVERFLOW) atomicAdd(&b.counters[GMEM ? C_LARGE : C_MID], 1ull);
+            wc.n_ok += flag == FLAG_OK;
+            wc.n_conf += flag == FLAG_CONFLICT;
+            wc.n_skip += flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED;
+        }
     }
     wc.flush(b.counters);
 }
 
 // ---------------------------------------------------------------- result compaction into canonical CSR order
+constexpr uint32_t GATHER_LONG = 1024;   // sets longer than this are copied chunk-wise by k_gather_long
+constexpr uint32_t GATHER_CHUNK = 2048;
+
 __global__ void k_gather(const BatchView b, const uint64_t *__restrict__ off, int32_t *__restrict__ dst)
 {
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const int lane = lane_id();
-    // self-implying probes regenerate their literal; short sets: one item per lane; long ones: warp copy
+    // self-implying probes regenerate their literal; short sets: one item per lane; medium: warp copy;
+    // long sets are cut into chunks for k_gather_long so that no warp is stuck with a giant
     for (uint64_t base = warp * 32; base < b.n; base += nwarps * 32) {
         const uint64_t item = base + lane;
         uint32_t len = 0;
@@ -671,13 +864,40 @@ __global__ void k_gather(const BatchView b, const uint64_t *__restrict__ off, in
         if (len && len <= 4) {
             for (uint32_t i = 0; i < len; ++i) dst[d + i] = b.out_lits[src + i];
         }
-        unsigned big = __ballot_sync(FULL, len > 4);
+        unsigned big = __ballot_sync(FULL, len > 4 && len <= GATHER_LONG);
         while (big) {
             const int j = __ffs(big) - 1;
             big &= big - 1;
             const uint32_t l = __shfl_sync(FULL, len, j);
             const uint64_t s = __shfl_sync(FULL, src, j), dd = __shfl_sync(FULL, d, j);
             for (uint32_t i = lane; i < l; i += 32) dst[dd + i] = b.out_lits[s + i];
+        }
+        unsigned lng = __ballot_sync(FULL, len > GATHER_LONG);
+        while (lng) {
+            const int j = __ffs(lng) - 1;
+            lng &= lng - 1;
+            const uint32_t l = __shfl_sync(FULL, len, j);
+            const uint32_t nch = (l + GATHER_CHUNK - 1) / GATHER_CHUNK;
+            uint32_t pos = 0;
+            if (lane == 0) pos = atomicAdd(b.chunk_count, nch);
+            pos = __shfl_sync(FULL, pos, 0);
+            for (uint32_t c = lane; c < nch; c += 32) b.chunk_list[pos + c] = make_uint2((uint32_t)(base + j), c);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather_long(const BatchView b, const uint64_t *__restrict__ off, int32_t *__restrict__ dst)
+{
+    const uint32_t nchunks = *b.chunk_count;
+    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const uint2 e = b.chunk_list[c];
+        const uint32_t len = b.len[e.x];
+        const uint64_t src = b.raw_off[e.x] + (uint64_t)e.y * GATHER_CHUNK, d = off[e.x] + (uint64_t)e.y * GATHER_CHUNK;
+        const uint32_t m = min(GATHER_CHUNK, len - e.y * GATHER_CHUNK);
+#pragma unroll
+        for (uint32_t k = 0; k < GATHER_CHUNK / 256; ++k) {
+            const uint32_t i = k * 256 + threadIdx.x;
+            if (i < m) dst[d + i] = b.out_lits[src + i];
         }
     }
 }
@@ -712,9 +932,26 @@ void launch_small(const DbView &db, const BatchView &b, uint32_t cap, int blocks
     k_deep<<<blocks, SMALL_WARPS * 32, smem, s>>>(db, b, ilog2(2 * cap), cap);
 }
 
-void launch_large(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s)
+size_t mid_smem_bytes(uint32_t cap) { return (size_t)(2 * cap + cap) * 4; }
+
+int mid_blocks_per_sm(uint32_t cap)
 {
-    k_large<<<blocks, LARGE_WARPS * 32, 0, s>>>(db, b, ls);
+    int nb = 0;
+    cudaFuncSetAttribute(k_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem_bytes(cap));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_block<false>, MID_THREADS, mid_smem_bytes(cap));
+    return nb;
+}
+
+void launch_mid(const DbView &db, const BatchView &b, uint32_t cap, int blocks, cudaStream_t s)
+{
+    const size_t smem = mid_smem_bytes(cap);
+    cudaFuncSetAttribute(k_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_block<false><<<blocks, MID_THREADS, smem, s>>>(db, b, LargeState{nullptr, nullptr}, ilog2(2 * cap), cap);
+}
+
+void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s)
+{
+    k_block<true><<<blocks, BIG_THREADS, 0, s>>>(db, b, ls, 0, 0);
 }
 
 void launch_gather(const BatchView &b, const uint64_t *off, int32_t *dst, cudaStream_t s)
@@ -724,6 +961,7 @@ void launch_gather(const BatchView &b, const uint64_t *off, int32_t *dst, cudaSt
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_gather<<<blocks, 256, 0, s>>>(b, off, dst);
+    k_gather_long<<<148 * 8, 256, 0, s>>>(b, off, dst);
 }
 
 }  // namespace bbcp

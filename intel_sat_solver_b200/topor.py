@@ -123,8 +123,8 @@ class BatchedTopor:
         return rc
 
     @staticmethod
-    def _opts(implied=True, small_trail=0, out_capacity=0, no_len_prune=False) -> Opts:
-        return Opts((OPT_IMPLIED if implied else 0) | (OPT_NO_LEN_PRUNE if no_len_prune else 0), small_trail, out_capacity)
+    def _opts(implied=True, small_trail=0, out_capacity=0, no_len_prune=False, mid_trail=0) -> Opts:
+        return Opts((OPT_IMPLIED if implied else 0) | (OPT_NO_LEN_PRUNE if no_len_prune else 0), small_trail, out_capacity, mid_trail, 0)
 
     def _fetch(self, info: BatchInfo, implied: bool, fetch: bool) -> BatchResult:
         res = BatchResult(info.as_dict())

@@ -67,10 +67,12 @@ def test_regression_corpus_totals(golden, golden_names):
     assert (valid, failed) == (4694, 77)
 
 
-@pytest.mark.parametrize("kw", [dict(small_trail=32), dict(no_len_prune=True), dict(out_capacity=64), dict(small_trail=32, out_capacity=16)])
+@pytest.mark.parametrize("kw", [dict(small_trail=32), dict(small_trail=32, mid_trail=32), dict(no_len_prune=True), dict(out_capacity=64),
+                                dict(small_trail=32, mid_trail=64, out_capacity=16)])
 def test_option_variants_keep_results(golden, kw):
-    """Tiny shared-memory state (forces the global-state tier), no length pruning, and an implied-literal
-    buffer that overflows and regrows must all give the same bits."""
+    """Tiny warp-private state (forces the CTA-per-probe shared-memory tier), tiny CTA state too (forces the
+    global-slab tier), no length pruning, and an implied-literal buffer that overflows and regrows must all
+    give the same bits."""
     for name in ["regr_47", "regr_72", "fuzz_5", "fuzz_10", "hand_long", "hand_alias"]:
         g = lambda k: golden[f"{name}/{k}"]
         t, rc = engine_for(g("words"))
@@ -114,10 +116,14 @@ def test_synthetic_shapes_against_checker(kind, kw, cubekw):
             cref, _ = gpu_util.run_checker(inst, gkw["cubes"])
             res = t.PropagateBatch(lits, off)
             gpu_util.assert_same_results(res, cref.flag, cref.off, cref.lits, kind + " cubes")
-        # the same instance through the tiny-state path (every deep probe takes the global-state tier)
+        # the same instance with tiny state budgets: deep probes cascade to the CTA-per-probe tiers
         res2 = t.ProbeAll(small_trail=32)
         gpu_util.assert_same_results(res2, ref.flag, ref.off, ref.lits, kind + " tier2")
-        assert res2.info["n_large"] >= res.info["n_large"]
+        res3 = t.ProbeAll(small_trail=32, mid_trail=32)
+        gpu_util.assert_same_results(res3, ref.flag, ref.off, ref.lits, kind + " tier3")
+        assert res2.info["n_mid"] >= res.info["n_mid"] and res3.info["n_large"] >= res2.info["n_large"]
+        if kind in ("aig", "plaw"):
+            assert res2.info["n_mid"] > 0 and res3.info["n_large"] > 0
 
 
 def test_probe_range_shards_compose(golden):
