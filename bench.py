@@ -182,21 +182,19 @@ def ours_arm(args, rank, local_rank, world):
     L, h = eng.lib, eng.handle
     dbi = eng.DbInfo()
 
-    # shard = a contiguous slice of failed-literal-bitmap words (internal literal = universe index + 2)
+    # shard = a contiguous slice of failed-literal-bitmap words (intel_sat_solver_b200/sharding.py)
+    from intel_sat_solver_b200 import sharding
     universe = 2 * nvars
+    shard = sharding.shard_for(rank, world, nvars)
     words_total = L.bbcp_bitmap_words(h)
-    wp = (words_total + world - 1) // world
-    lo_lit, hi_lit = 32 * rank * wp, min(32 * (rank + 1) * wp, universe + 2)
-    first, last = max(lo_lit - 2, 0), max(hi_lit - 2, 0)
+    assert words_total == sharding.bitmap_words(nvars)
+    first, last = shard.first, shard.last
     n_local = last - first
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     opts = Opts(1, 0, 0, 0, 0)
     info = BatchInfo()
     if world > 1:
-        slice_t = torch.zeros(wp, dtype=torch.int32, device=dev)
-        gathered_f = torch.zeros(wp * world, dtype=torch.int32, device=dev)
-        gathered_u = torch.zeros(wp * world, dtype=torch.int32, device=dev)
         failed_t = torch.as_tensor(DevArr(L.bbcp_device_failed_bitmap(h), words_total), device=dev)
         unit_t = torch.as_tensor(DevArr(L.bbcp_device_unit_bitmap(h), words_total), device=dev)
 
@@ -204,6 +202,8 @@ def ours_arm(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    merged = {}
 
     def device_step():
         """all inputs resident: kernels + compaction (+ on-stream all-gather of the bitmap slices)"""
@@ -213,11 +213,8 @@ def ours_arm(args, rank, local_rank, world):
         if world > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for src, dst in ((failed_t, gathered_f), (unit_t, gathered_u)):
-                slice_t.zero_()
-                seg = src[rank * wp: min((rank + 1) * wp, words_total)]
-                slice_t[: seg.numel()].copy_(seg)
-                dist.all_gather_into_tensor(dst, slice_t)
+            merged["failed"] = sharding.allgather_bitmap(failed_t, shard)
+            merged["unit"] = sharding.allgather_bitmap(unit_t, shard)
             e1.record()
             e1.synchronize()
             ms += e0.elapsed_time(e1)

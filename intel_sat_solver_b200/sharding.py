@@ -1,0 +1,57 @@
+"""Probe sharding across ranks and the merge of the failed-literal / unit bitmaps.
+
+The probe universe (+1,-1,+2,-2,...) is cut into one CONTIGUOUS range per rank. Ranges are
+aligned to 32-bit words of the failed-literal bitmap (bit index = internal literal = universe index + 2), so
+that each rank owns a whole slice of bitmap words and ONE all-gather of the slices (NCCL over NVLink on the
+GPU box, gloo in the CPU tests) merges them -- no reduction, no second pass. The clause database is
+replicated; nothing else is exchanged on the data path.
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import torch
+import torch.distributed as dist
+
+
+@dataclasses.dataclass(frozen=True)
+class Shard:
+    rank: int
+    world: int
+    words_per_rank: int    # bitmap words owned by each rank (the last one may own fewer real words)
+    word_lo: int           # this rank's words are [word_lo, word_hi)
+    word_hi: int
+    first: int             # probe-universe indices [first, last) belong to this rank
+    last: int
+
+
+def bitmap_words(max_var: int) -> int:
+    return (2 * (max_var + 1) + 31) // 32
+
+
+def shard_for(rank: int, world: int, max_var: int) -> Shard:
+    universe = 2 * max_var
+    words = bitmap_words(max_var)
+    wp = (words + world - 1) // world
+    word_lo, word_hi = min(rank * wp, words), min((rank + 1) * wp, words)
+    first = min(max(32 * word_lo - 2, 0), universe)
+    last = min(max(32 * word_hi - 2, 0), universe)
+    return Shard(rank, world, wp, word_lo, word_hi, first, last)
+
+
+def all_shards(world: int, max_var: int) -> list[Shard]:
+    return [shard_for(r, world, max_var) for r in range(world)]
+
+
+def allgather_bitmap(local: torch.Tensor, shard: Shard, group=None) -> torch.Tensor:
+    """local: int32[bitmap_words] holding (at least) this rank's slice. Returns the merged int32[bitmap_words]."""
+    words = local.numel()
+    if shard.world == 1:
+        return local.clone()
+    send = torch.zeros(shard.words_per_rank, dtype=local.dtype, device=local.device)
+    n = shard.word_hi - shard.word_lo
+    if n > 0:
+        send[:n].copy_(local[shard.word_lo:shard.word_hi])
+    out = torch.empty(shard.words_per_rank * shard.world, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, send, group=group)
+    return out[:words]
