@@ -251,19 +251,19 @@ def ours_arm(args, rank, local_rank, world):
     # ---- e2e: the call a user makes, host buffers in and out, every step
     idx = np.arange(first, last, dtype=np.int64)
     h_lits = torch.from_numpy(np.where(idx & 1, -(idx // 2 + 1), idx // 2 + 1).astype(np.int32)).pin_memory()
-    h_off = torch.arange(n_local + 1, dtype=torch.int64).pin_memory()
     o_flag = torch.empty(n_local + 8, dtype=torch.uint8).pin_memory()
-    o_off = torch.empty(n_local + 1, dtype=torch.int64).pin_memory()
+    o_off = torch.empty(n_local + 1, dtype=torch.int32).pin_memory()   # u32 CSR offsets (BBCP_OPT_OFF32)
+    opts_e2e = Opts(1 | 4, 0, 0, 0, 0)
     o_lits = torch.empty(max(int(n_implied) * 2, 1024), dtype=torch.int32).pin_memory()
     e2e_s = []
     for it in range(args.warmup + args.steps):
         flush.fill_(it & 0xff)
         barrier()
         t0 = time.perf_counter()
-        rc = L.bbcp_propagate_batch(h, h_lits.data_ptr(), h_off.data_ptr(), n_local, C.byref(opts), C.byref(info))
+        rc = L.bbcp_probe_lits(h, h_lits.data_ptr(), n_local, C.byref(opts_e2e), C.byref(info))
         assert rc == 0 and info.n_implied <= o_lits.numel()
         L.bbcp_fetch_flags(h, o_flag.data_ptr())
-        L.bbcp_fetch_implied(h, o_off.data_ptr(), o_lits.data_ptr())
+        L.bbcp_fetch_implied32(h, o_off.data_ptr(), o_lits.data_ptr())
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if it >= args.warmup:
@@ -273,10 +273,10 @@ def ours_arm(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
     e2e_value = float(probes.item()) * args.steps / float(e2e_total.item())
-    h2d = h_lits.numel() * 4 + h_off.numel() * 8
-    d2h = n_local + (n_local + 1) * 8 + int(info.n_implied) * 4
+    h2d = h_lits.numel() * 4
+    d2h = n_local + (n_local + 1) * 4 + int(info.n_implied) * 4
     # sanity on the last e2e step: every probe of this workload implies exactly itself
-    assert int(o_off[n_local]) == info.n_implied
+    assert int(o_off[n_local]) == info.n_implied and int((o_flag[:n_local] == 0).sum()) == info.n_ok
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -47,7 +47,9 @@ enum {
 /* option bits */
 enum {
     BBCP_OPT_IMPLIED = 1u,     /* produce the per-probe implied-literal sets (else flags + bitmaps only) */
-    BBCP_OPT_NO_LEN_PRUNE = 2u /* diagnostic: scan ternary/long rows even while only one literal is assigned */
+    BBCP_OPT_NO_LEN_PRUNE = 2u,/* diagnostic: scan ternary/long rows even while only one literal is assigned */
+    BBCP_OPT_OFF32 = 4u        /* produce impl_off as uint32 (fetch with bbcp_fetch_implied32): halves the offset
+                                  read-back; the batch fails with BBCP_ERR_ARG if it implies >= 2^32 literals */
 };
 
 typedef struct {
@@ -131,13 +133,19 @@ int bbcp_propagate_batch(bbcp_handle *h, const int32_t *lits, const uint64_t *of
 /* probe universe indices [first, last): index i is literal (i/2+1) * (i odd ? -1 : +1) */
 int bbcp_probe_range(bbcp_handle *h, uint64_t first, uint64_t last, const bbcp_opts *opts, bbcp_batch_info *info);
 int bbcp_probe_all(bbcp_handle *h, const bbcp_opts *opts, bbcp_batch_info *info);
-/* same as bbcp_propagate_batch with the cube arrays already resident in device memory */
+/* explicit list of depth-1 probes: item i is the single literal lits[i] (4 bytes per probe instead of a CSR
+ * cube; a 0 entry is reported BBCP_FLAG_UNMAPPED). Same results as one-literal cubes. */
+int bbcp_probe_lits(bbcp_handle *h, const int32_t *lits, uint64_t n, const bbcp_opts *opts, bbcp_batch_info *info);
+/* same as bbcp_propagate_batch with the cube arrays already resident in device memory (d_off == NULL: d_lits is
+ * a probe list of ncubes literals) */
 int bbcp_propagate_batch_device(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint64_t ncubes,
                                 uint64_t nlits, const bbcp_opts *opts, bbcp_batch_info *info);
 
 /* ---- results of the last batch, device -> caller buffers */
 int bbcp_fetch_flags(bbcp_handle *h, uint8_t *flag /* n */);
 int bbcp_fetch_implied(bbcp_handle *h, uint64_t *impl_off /* n+1 */, int32_t *impl_lits /* n_implied */);
+/* the same after a batch run with BBCP_OPT_OFF32 */
+int bbcp_fetch_implied32(bbcp_handle *h, uint32_t *impl_off /* n+1 */, int32_t *impl_lits /* n_implied */);
 /* failed-literal bitmap (bit 2*var+neg set <=> that literal is a failed literal found by a depth-1 probe so
  * far) and unit bitmap (the negations). nwords32 = bbcp_bitmap_words(). Bitmaps accumulate over calls until
  * bbcp_clear_bitmaps. */

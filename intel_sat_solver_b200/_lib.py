@@ -48,11 +48,13 @@ _SIGS = {
     "bbcp_status": (C.c_int, [C.c_void_p]),
     "bbcp_error_string": (C.c_char_p, [C.c_void_p]),
     "bbcp_propagate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Opts), C.POINTER(BatchInfo)]),
+    "bbcp_probe_lits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Opts), C.POINTER(BatchInfo)]),
     "bbcp_probe_range": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(Opts), C.POINTER(BatchInfo)]),
     "bbcp_probe_all": (C.c_int, [C.c_void_p, C.POINTER(Opts), C.POINTER(BatchInfo)]),
     "bbcp_propagate_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(Opts), C.POINTER(BatchInfo)]),
     "bbcp_fetch_flags": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bbcp_fetch_implied": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bbcp_fetch_implied32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bbcp_bitmap_words": (C.c_uint64, [C.c_void_p]),
     "bbcp_fetch_bitmaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bbcp_clear_bitmaps": (C.c_int, [C.c_void_p]),

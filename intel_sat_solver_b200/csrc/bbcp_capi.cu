@@ -4,9 +4,6 @@
 #include "bbcp_db.h"
 #include "bbcp_device.cuh"
 
-#include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
-
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -45,8 +42,9 @@ struct DevBuf {
 // total (a copy of off[n])
 constexpr int MISC_CURSOR = C_N;
 constexpr int MISC_U32 = C_N + 1;       // as u32 index from 2*MISC_U32: +0..2 tickets, +3 mid_count, +4 big_count, +5 deep_count
-constexpr int MISC_TOTAL = C_N + 5;     // (u32 +6 = chunk_count of the long-set gather)
+constexpr int MISC_TOTAL = C_N + 5;     // (u32 +6 = chunk_count of the giant-set gather, +7 = tile ticket of the scan)
 constexpr int MISC_WORDS64 = C_N + 6;
+// two counter blocks used alternately: the triage kernel of one launch sequence zeroes the block of the next one
 
 }  // namespace
 
@@ -58,6 +56,7 @@ struct bbcp_handle {
     bool prepared = false, finalized = false, device_ready = false;
     uint32_t db_version = 0;
     int sm_count = 148;
+    int sg_blocks = 148;   // co-resident CTAs of the cooperative compaction kernel
 
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -66,7 +65,9 @@ struct bbcp_handle {
     uint64_t bitmap_words = 0;
     uint64_t device_db_bytes = 0;
 
-    DevBuf d_flag, d_raw_off, d_len, d_out, d_off, d_impl, d_cube_lits, d_cube_off, d_overflow, d_big, d_deep, d_chunks, d_misc, d_lbits, d_ltrail, d_cubtmp;
+    DevBuf d_flag, d_raw_off, d_len, d_out, d_off, d_impl, d_cube_lits, d_cube_off, d_overflow, d_big, d_deep, d_chunks, d_misc, d_lbits, d_ltrail, d_tiles;
+    uint32_t misc_parity = 0;
+    bool last_off32 = false;
     unsigned long long *h_misc = nullptr;   // pinned
     uint64_t out_cap_hint = 0;   // stored literals the last batch needed (sizes the next batch's buffer)
     uint32_t big_slabs = 0;
@@ -82,7 +83,9 @@ struct bbcp_handle {
 
     int fail(int code, const std::string &msg)
     {
-        if (code < 0 || code == BBCP_CONTRADICTORY) status = code;
+        // resource / device failures are permanent (the reference's STATUS_FIRST_PERMANENT_ERROR class,
+        // ToporExternalTypes.hpp:32-48); caller mistakes (ERR_STATE, ERR_ARG) only fail the call
+        if (code == BBCP_ERR_ALLOC || code == BBCP_ERR_CUDA || code == BBCP_ERR_INDEX_TOO_NARROW || code == BBCP_CONTRADICTORY) status = code;
         err = msg;
         return code;
     }
@@ -108,9 +111,12 @@ bool ensure_device(bbcp_handle *h)
     cudaDeviceProp prop;
     if (!h->cuda_ok(cudaGetDeviceProperties(&prop, h->device), "cudaGetDeviceProperties")) return false;
     h->sm_count = prop.multiProcessorCount;
+    h->sg_blocks = scan_gather_max_blocks(h->sm_count);
     if (!h->cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
     for (auto &e : h->ev) if (!h->cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return false;
     if (!h->cuda_ok(cudaMallocHost(&h->h_misc, MISC_WORDS64 * 8), "cudaMallocHost")) return false;
+    if (!h->d_misc.reserve(2 * MISC_WORDS64 * 8, true)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (counters)"); return false; }
+    if (!h->cuda_ok(cudaDeviceSynchronize(), "counter init")) return false;
     h->device_ready = true;
     return true;
 }
@@ -165,23 +171,6 @@ DbView db_view(const bbcp_handle *h)
 
 uint32_t pow2_at_least(uint32_t x) { uint32_t p = 32; while (p < x) p <<= 1; return p; }
 
-struct CastLen {
-    __host__ __device__ uint64_t operator()(const uint32_t &x) const { return (uint64_t)(x & 0x7fffffffu); }
-};
-
-// scan of the set sizes -> canonical CSR offsets (off[n] = total), gather out of allocation order
-bool compact(bbcp_handle *h, const BatchView &b, uint64_t n)
-{
-    cub::TransformInputIterator<uint64_t, CastLen, const uint32_t *> in(b.len, CastLen());
-    size_t tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, h->d_off.as<uint64_t>(), (int)(n + 1), h->stream);
-    if (!h->d_cubtmp.reserve(tmp + 16)) return false;
-    cub::DeviceScan::ExclusiveSum(h->d_cubtmp.p, tmp, in, h->d_off.as<uint64_t>(), (int)(n + 1), h->stream);
-    launch_gather(b, h->d_off.as<uint64_t>(), h->d_impl.as<int32_t>(), h->stream);
-    cudaMemcpyAsync(h->d_misc.as<unsigned long long>() + MISC_TOTAL, h->d_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToDevice, h->stream);
-    return true;
-}
-
 // third-tier slabs: one dense assignment + trail per resident CTA, sized for the whole variable range
 bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
 {
@@ -200,10 +189,14 @@ bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
     return true;
 }
 
-// The whole device-side batch. cube arrays already on the device (nullptr = probe universe from `first`).
-// One stream, no host round trip inside: memset, k_triage, k_deep, k_block<mid>, k_block<big>, scan, k_gather,
-// one read-back, ONE host synchronisation. Each tier hands what it cannot hold to the next through a
-// device-side list; a tier with an empty list exits at once.
+// The whole device-side batch. Input arrays already on the device: (d_lits, d_off) cubes in CSR form,
+// (d_lits, nullptr) a list of probe literals, (nullptr, nullptr) the probe universe from `first`.
+// One stream, no memset nodes, one host synchronisation in the common case:
+//     k_triage -> k_deep -> k_scan_gather -> 200-byte counter read-back -> sync
+// Only if some probe outgrew the warp-private shared-memory state (the read-back says so; k_scan_gather saw it
+// too and returned at once) a second sequence runs: k_block<smem> -> k_block<gmem> -> k_scan_gather
+// (-> k_gather_long) -> read-back -> sync. Each tier hands what it cannot hold to the next through a
+// device-side list.
 int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint64_t first, uint64_t n,
               const bbcp_opts *uopts, bbcp_batch_info *info)
 {
@@ -218,8 +211,8 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     h->have_batch = false;
 
     const size_t n1 = (size_t)n + 1;
-    if (!h->d_flag.reserve(n1) || !h->d_raw_off.reserve(n1 * 8) || !h->d_len.reserve(n1 * 4) || !h->d_off.reserve(n1 * 8) ||
-        !h->d_overflow.reserve(n1 * 4) || !h->d_big.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_misc.reserve(MISC_WORDS64 * 8))
+    if (!h->d_flag.reserve(n1) || !h->d_raw_off.reserve(n1 * 8) || !h->d_len.reserve(n1 * 4 + 64) || !h->d_off.reserve(n1 * 8) ||
+        !h->d_overflow.reserve(n1 * 4) || !h->d_big.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_tiles.reserve(((size_t)h->sg_blocks + 4) * 8))
         return h->fail(BBCP_ERR_ALLOC, "device allocation failed (batch buffers)");
 
     uint32_t cap = opts.small_trail ? pow2_at_least(opts.small_trail) : 512;
@@ -227,13 +220,11 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     uint32_t cap_mid = opts.mid_trail ? pow2_at_least(opts.mid_trail) : 4096;
     if (cap_mid > 16384) cap_mid = 16384;
     const bool implied = (opts.flags & BBCP_OPT_IMPLIED) != 0;
+    const bool off32 = (opts.flags & BBCP_OPT_OFF32) != 0;
     uint64_t out_cap = implied ? (opts.out_capacity ? opts.out_capacity : std::max<uint64_t>({(uint64_t)1 << 20, 4 * n, h->out_cap_hint + h->out_cap_hint / 4})) : 0;
 
     DbView dbv = db_view(h);
-    if (!ensure_slabs(h, dbv)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (third-tier state)");
-    LargeState ls;
-    ls.bits = h->d_lbits.as<uint32_t>();
-    ls.trail = h->d_ltrail.as<uint32_t>();
+    LargeState ls{nullptr, nullptr};
 
     BatchView b;
     memset(&b, 0, sizeof(b));
@@ -246,65 +237,97 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.len = h->d_len.as<uint32_t>();
     b.failed = h->d_failed.as<uint32_t>();
     b.unit = h->d_unit.as<uint32_t>();
-    b.counters = h->d_misc.as<unsigned long long>();
-    b.out_cursor = h->d_misc.as<unsigned long long>() + MISC_CURSOR;
-    uint32_t *u32 = h->d_misc.as<uint32_t>() + 2 * MISC_U32;
-    b.ticket = u32;
-    b.mid_count = u32 + 3;
-    b.big_count = u32 + 4;
-    b.deep_count = u32 + 5;
-    b.chunk_count = u32 + 6;
     b.mid_list = h->d_overflow.as<uint32_t>();
     b.big_list = h->d_big.as<uint32_t>();
     b.deep_list = h->d_deep.as<uint32_t>();
+    b.off = h->d_off.p;
+    b.tile_state = h->d_tiles.as<unsigned long long>();
+    b.zero_words = MISC_WORDS64;
     b.opts = opts.flags;
 
     const int bps = small_blocks_per_sm(cap);
-    const int bps_mid = mid_blocks_per_sm(cap_mid);
-    if (bps <= 0 || bps_mid <= 0) return h->fail(BBCP_ERR_CUDA, "propagate kernel does not fit (shared memory)");
+    if (bps <= 0) return h->fail(BBCP_ERR_CUDA, "propagate kernel does not fit (shared memory)");
     const uint32_t *h_u32 = reinterpret_cast<uint32_t *>(h->h_misc) + 2 * MISC_U32;
     float triage_ms = 0, deep_ms = 0, block_ms = 0, mid_ms = 0;
 
     cudaEventRecord(h->ev[0], h->stream);
-    for (int attempt = 0; attempt < 8; ++attempt) {
+    for (int attempt = 0;; ++attempt) {
         // room for every self-implying probe (n) plus out_cap stored literals
         if (!h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4) || (implied && !h->d_impl.reserve((n + out_cap + 4) * 4)) ||
-            !h->d_chunks.reserve((out_cap / 1024 + 64) * 8))
+            !h->d_chunks.reserve((out_cap / 2048 + 64) * 8))
             return h->fail(BBCP_ERR_ALLOC, "device allocation failed (implied literals)");
         b.out_lits = h->d_out.as<int32_t>();
+        b.impl = h->d_impl.as<int32_t>();
         b.chunk_list = h->d_chunks.as<uint2>();
         b.out_cap = out_cap;
-        cudaMemsetAsync(h->d_misc.p, 0, MISC_WORDS64 * 8, h->stream);
-        cudaMemsetAsync(b.len + n, 0, 4, h->stream);
+        // counter block of this launch sequence (zeroed by the previous sequence's triage, or at creation)
+        unsigned long long *misc = h->d_misc.as<unsigned long long>() + (size_t)h->misc_parity * MISC_WORDS64;
+        b.zero_next = h->d_misc.as<unsigned long long>() + (size_t)(h->misc_parity ^ 1u) * MISC_WORDS64;
+        h->misc_parity ^= 1u;
+        b.counters = misc;
+        b.out_cursor = misc + MISC_CURSOR;
+        b.total = misc + MISC_TOTAL;
+        uint32_t *u32 = reinterpret_cast<uint32_t *>(misc) + 2 * MISC_U32;
+        b.ticket = u32;
+        b.mid_count = u32 + 3;
+        b.big_count = u32 + 4;
+        b.deep_count = u32 + 5;
+        b.chunk_count = u32 + 6;
+        b.tile_ticket = u32 + 7;
         bi.launches = 0;
+        bool second = false;
         if (n) {
             cudaEventRecord(h->ev[3], h->stream);
-            launch_triage(b, dbv, (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)h->sm_count * 8), h->stream);
+            launch_triage(b, dbv, (int)std::min<uint64_t>((n + 1023) / 1024, (uint64_t)h->sm_count * 8), h->stream);
             cudaEventRecord(h->ev[4], h->stream);
             launch_small(dbv, b, cap, bps * h->sm_count, h->stream);
             cudaEventRecord(h->ev[5], h->stream);
+            bi.launches += 2;
+            if (implied) {
+                if (!launch_scan_gather(b, 0, h->sg_blocks, false, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
+                ++bi.launches;
+            }
+        } else {
+            // empty batch: nothing ran, but the next sequence still needs a zeroed counter block
+            cudaMemsetAsync(b.zero_next, 0, MISC_WORDS64 * 8, h->stream);
+            cudaMemsetAsync(h->d_off.p, 0, 8, h->stream);
+        }
+        cudaMemcpyAsync(h->h_misc, misc, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
+        cudaEventRecord(h->ev[2], h->stream);
+        if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "propagate kernels")) return BBCP_ERR_CUDA;
+        if (n && h_u32[3] != 0) {
+            // some probes outgrew the first tier: CTA-per-probe tiers, then the compaction for real
+            second = true;
+            const int bps_mid = mid_blocks_per_sm(cap_mid);
+            if (bps_mid <= 0) return h->fail(BBCP_ERR_CUDA, "propagate kernel does not fit (shared memory)");
+            if (!ensure_slabs(h, dbv)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (third-tier state)");
+            ls.bits = h->d_lbits.as<uint32_t>();
+            ls.trail = h->d_ltrail.as<uint32_t>();
+            cudaEventRecord(h->ev[1], h->stream);
             launch_mid(dbv, b, cap_mid, bps_mid * h->sm_count, h->stream);
             cudaEventRecord(h->ev[7], h->stream);
             launch_big(dbv, b, ls, (int)h->big_slabs, h->stream);
             cudaEventRecord(h->ev[6], h->stream);
-            bi.launches += 4;
+            bi.launches += 2;
             if (implied) {
-                if (!compact(h, b, n)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (compaction)");
+                if (!launch_scan_gather(b, 1, h->sg_blocks, true, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
                 bi.launches += 2;
             }
+            cudaMemcpyAsync(h->h_misc, misc, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
+            cudaEventRecord(h->ev[2], h->stream);
+            if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "propagate kernels (CTA-per-probe tiers)")) return BBCP_ERR_CUDA;
         }
-        cudaMemcpyAsync(h->h_misc, h->d_misc.p, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
-        cudaEventRecord(h->ev[2], h->stream);
-        if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "propagate kernels")) return BBCP_ERR_CUDA;
         if (n) {
             cudaEventElapsedTime(&triage_ms, h->ev[3], h->ev[4]);
             cudaEventElapsedTime(&deep_ms, h->ev[4], h->ev[5]);
-            cudaEventElapsedTime(&block_ms, h->ev[5], h->ev[6]);
-            cudaEventElapsedTime(&mid_ms, h->ev[5], h->ev[7]);
+            if (second) {
+                cudaEventElapsedTime(&block_ms, h->ev[1], h->ev[6]);
+                cudaEventElapsedTime(&mid_ms, h->ev[1], h->ev[7]);
+            }
         }
         const uint64_t cursor = h->h_misc[MISC_CURSOR];
         if (cursor <= out_cap) { bi.n_implied = implied ? h->h_misc[MISC_TOTAL] : 0; if (!opts.out_capacity) h->out_cap_hint = cursor; break; }
-        // implied-literal buffer too small: redo the batch with room for everything that was asked for
+        // implied-literal pool too small: redo the batch with room for everything that was asked for
         out_cap = std::max<uint64_t>(cursor + cursor / 8, out_cap * 2);
         if (attempt == 7) return h->fail(BBCP_ERR_ALLOC, "implied-literal buffer keeps overflowing");
     }
@@ -312,6 +335,8 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
         if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "batch")) return BBCP_ERR_CUDA;
     }
+    if (off32 && bi.n_implied > 0xffffffffull) return h->fail(BBCP_ERR_ARG, "BBCP_OPT_OFF32: more than 2^32-1 implied literals in one batch (split it)");
+    h->last_off32 = off32 && implied;
 
     bi.props_all = h->h_misc[C_PROPS_ALL];
     bi.props_ref = h->h_misc[C_PROPS_REF];
@@ -323,10 +348,12 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     bi.n_conflict = h->h_misc[C_CONFLICT];
     bi.n_skipped = h->h_misc[C_SKIPPED];
     bi.n_deep = h_u32[5];
-    // bytes model: triage = 1 B of literal facts + 1 B flag + 4 B size per item (+ 16 B offsets and
-    // 4 B literal for explicit probe lists); propagation = row headers, row slots, clause units, stored
-    // implied literals (kernel counters) + the per-item record (flag, size, position) of the queued items
-    bi.triage_bytes = n * (6 + (d_off ? 20 : 0));
+    // bytes model: triage = 1 B of literal facts + 1 B flag + 4 B size per item (+ 4 B literal for
+    // probe lists, + 16 B offsets more for cubes); propagation = row headers, row slots, clause units, stored
+    // implied literals (kernel counters) + the per-item record (flag, size, position) of the queued items;
+    // compaction = 4 B size read + offset written per item + 8 B per implied literal (read + write; 4 B for the
+    // regenerated self literals)
+    bi.triage_bytes = n * (6 + (d_off ? 20 : d_lits ? 4 : 0));
     bi.kernel_bytes = bi.triage_bytes + h->h_misc[C_BYTES] + 17ull * bi.n_deep;
     cudaEventElapsedTime(&bi.total_ms, h->ev[0], h->ev[2]);
     bi.triage_ms = triage_ms;
@@ -371,7 +398,7 @@ void bbcp_release(bbcp_handle *h)
         cudaStreamSynchronize(h->stream);
         for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_failed, &h->d_unit, &h->d_flag, &h->d_raw_off, &h->d_len,
                           &h->d_out, &h->d_off, &h->d_impl, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_big, &h->d_deep, &h->d_chunks, &h->d_misc, &h->d_lbits,
-                          &h->d_ltrail, &h->d_cubtmp})
+                          &h->d_ltrail, &h->d_tiles})
             b->release();
         if (h->h_misc) cudaFreeHost(h->h_misc);
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -578,6 +605,17 @@ int bbcp_propagate_batch(bbcp_handle *h, const int32_t *lits, const uint64_t *of
     return run_batch(h, h->d_cube_lits.as<int32_t>(), h->d_cube_off.as<uint64_t>(), 0, ncubes, opts, info);
 }
 
+int bbcp_probe_lits(bbcp_handle *h, const int32_t *lits, uint64_t n, const bbcp_opts *opts, bbcp_batch_info *info)
+{
+    int rc = need_final(h);
+    if (rc) return rc;
+    if (!lits && n) return h->fail(BBCP_ERR_ARG, "probe list missing");
+    cudaSetDevice(h->device);
+    if (!h->d_cube_lits.reserve(std::max<uint64_t>(n, 4) * 4)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (probe list)");
+    if (n) cudaMemcpyAsync(h->d_cube_lits.p, lits, n * 4, cudaMemcpyHostToDevice, h->stream);
+    return run_batch(h, h->d_cube_lits.as<int32_t>(), nullptr, 0, n, opts, info);
+}
+
 int bbcp_probe_range(bbcp_handle *h, uint64_t first, uint64_t last, const bbcp_opts *opts, bbcp_batch_info *info)
 {
     int rc = need_final(h);
@@ -602,9 +640,20 @@ int bbcp_fetch_flags(bbcp_handle *h, uint8_t *flag)
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "fetch flags") ? BBCP_OK : BBCP_ERR_CUDA;
 }
 
+int bbcp_fetch_implied32(bbcp_handle *h, uint32_t *impl_off, int32_t *impl_lits)
+{
+    if (!h || !h->have_batch) return h ? h->fail(BBCP_ERR_STATE, "no batch results") : BBCP_ERR_ARG;
+    if (!h->last_off32) return h->fail(BBCP_ERR_STATE, "the last batch was not run with BBCP_OPT_OFF32");
+    cudaSetDevice(h->device);
+    if (!h->cuda_ok(cudaMemcpyAsync(impl_off, h->d_off.p, (h->last_n + 1) * 4, cudaMemcpyDeviceToHost, h->stream), "fetch offsets")) return BBCP_ERR_CUDA;
+    if (h->last_n_implied && !h->cuda_ok(cudaMemcpyAsync(impl_lits, h->d_impl.p, h->last_n_implied * 4, cudaMemcpyDeviceToHost, h->stream), "fetch implied")) return BBCP_ERR_CUDA;
+    return h->cuda_ok(cudaStreamSynchronize(h->stream), "fetch implied") ? BBCP_OK : BBCP_ERR_CUDA;
+}
+
 int bbcp_fetch_implied(bbcp_handle *h, uint64_t *impl_off, int32_t *impl_lits)
 {
     if (!h || !h->have_batch) return h ? h->fail(BBCP_ERR_STATE, "no batch results") : BBCP_ERR_ARG;
+    if (h->last_off32) return h->fail(BBCP_ERR_STATE, "the last batch was run with BBCP_OPT_OFF32: use bbcp_fetch_implied32");
     cudaSetDevice(h->device);
     if (!h->cuda_ok(cudaMemcpyAsync(impl_off, h->d_off.p, (h->last_n + 1) * 8, cudaMemcpyDeviceToHost, h->stream), "fetch offsets")) return BBCP_ERR_CUDA;
     if (h->last_n_implied && !h->cuda_ok(cudaMemcpyAsync(impl_lits, h->d_impl.p, h->last_n_implied * 4, cudaMemcpyDeviceToHost, h->stream), "fetch implied")) return BBCP_ERR_CUDA;

@@ -32,7 +32,8 @@ constexpr uint32_t LEN_SELF = 0x80000000u;   // len[] flag: the implied set is t
 enum Counter { C_PROPS_ALL = 0, C_PROPS_REF, C_SLOTS, C_CLAUSE_FETCH, C_BYTES, C_LARGE, C_MID, C_OK, C_CONFLICT, C_SKIPPED, C_N };
 
 struct BatchView {
-    // input: cubes (external literals) or, when cube_off == nullptr, the probe universe
+    // input: cubes (external literals, CSR); or, when cube_off == nullptr, a list of probe literals
+    // (cube_lits[i] is item i); or, when both are nullptr, the probe universe starting at `first`
     const int32_t *cube_lits;
     const uint64_t *cube_off;
     uint64_t first;             // universe index of item 0 (probe mode)
@@ -53,13 +54,22 @@ struct BatchView {
     unsigned int *ticket;       // [3] dynamic schedulers of k_deep / k_block<mid> / k_block<big>
     uint32_t *deep_list;        // items queued by the triage for propagation
     uint32_t *deep_count;
-    uint2 *chunk_list;          // (item, chunk) pairs of long implied sets, filled by k_gather for k_gather_long
+    uint2 *chunk_list;          // (item, chunk) pairs of giant implied sets, filled by k_scan_gather for k_gather_long
     uint32_t *chunk_count;
+    // result compaction (k_scan_gather): canonical CSR offsets + literals
+    void *off;                  // [n+1] u64, or u32 with OPT_OFF32
+    int32_t *impl;              // implied literals in item order
+    unsigned long long *tile_state;   // per-CTA segment sums of k_scan_gather
+    uint32_t *tile_ticket;            // its grid barrier word (zero before the launch)
+    unsigned long long *total;  // off[n]
+    unsigned long long *zero_next;    // the counter block of the NEXT launch sequence, zeroed by k_triage
+    uint32_t zero_words;
     uint32_t opts;
 };
 
 constexpr uint32_t OPT_IMPLIED = 1u;
 constexpr uint32_t OPT_NO_LEN_PRUNE = 2u;
+constexpr uint32_t OPT_OFF32 = 4u;
 constexpr uint8_t FLAG_OK = 0, FLAG_CONFLICT = 1, FLAG_TRIVIAL_L0 = 2, FLAG_FALSE_L0 = 3, FLAG_UNMAPPED = 4;
 constexpr uint8_t FLAG_OVERFLOW = 250;      // internal: re-run in the global-state tier
 constexpr uint8_t FLAG_OUT_OVERFLOW = 251;  // internal: implied-literal buffer full, re-run in a later launch
@@ -75,7 +85,9 @@ void launch_mid(const DbView &db, const BatchView &b, uint32_t cap, int blocks, 
 void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s);
 size_t mid_smem_bytes(uint32_t trail_cap);
 int mid_blocks_per_sm(uint32_t trail_cap);
-void launch_gather(const BatchView &b, const uint64_t *off, int32_t *dst, cudaStream_t s);
+bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, cudaStream_t s);
+int scan_gather_max_blocks(int sm_count);
+constexpr uint32_t SG_TILE = 2048;   // items per scan tile
 size_t small_smem_bytes(uint32_t trail_cap);
 int small_blocks_per_sm(uint32_t trail_cap);
 constexpr int SMALL_WARPS = 4;   // warps (= concurrent probes) per CTA, first tier

@@ -28,6 +28,8 @@
 // part of the contract for conflicting probes.
 #include "bbcp_device.cuh"
 
+#include <algorithm>
+
 namespace bbcp {
 
 namespace {
@@ -417,6 +419,10 @@ __device__ __forceinline__ Item get_item(const BatchView &b, uint64_t item)
         it.lits = b.cube_lits + o;
         it.n = (uint32_t)(b.cube_off[item + 1] - o);
         it.probe_lit = it.n == 1 ? it.lits[0] : 0;  // a depth-1 cube is a probe
+    } else if (b.cube_lits) {
+        it.probe_lit = b.cube_lits[item];   // probe-list mode; 0 is reported as unmapped by the triage
+        it.lits = b.cube_lits + item;
+        it.n = 1;
     } else {
         const uint64_t idx = b.first + item;
         const int32_t v = (int32_t)(idx / 2 + 1);
@@ -479,58 +485,98 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
     __syncwarp();
 }
 
-// Triage: one item per thread. Decides every depth-1 item that needs no propagation (unmapped / assigned at
+// Triage: four consecutive items per thread (four independent litinfo loads in flight, flag / size written as
+// one 4-byte / 16-byte store). Decides every depth-1 item that needs no propagation (unmapped / assigned at
 // level 0 / no binary clause on the negation => the implied set is the literal itself, marked LEN_SELF so
 // that nothing but the size is written here) and queues the rest for k_deep.
+constexpr int TRIAGE_ITEMS = 4;
 __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView b)
 {
-    __shared__ unsigned int s_cnt[4];  // ok, skipped, props_ref, deep
+    __shared__ unsigned int s_cnt[4];  // ok, skipped, props_ref
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
-    const bool probe_mode = b.cube_off == nullptr;
+    const bool want_len = (b.opts & OPT_IMPLIED) != 0;
+    // housekeeping: the counter block of the NEXT launch sequence starts from zero (no memset nodes on the stream)
+    if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < b.zero_words; i += 256) b.zero_next[i] = 0ull;
     uint32_t n_ok = 0, n_skip = 0, n_ref = 0;
-    for (uint64_t base = (uint64_t)blockIdx.x * 256; base < b.n; base += (uint64_t)gridDim.x * 256) {
-        const uint64_t item = base + threadIdx.x;
-        const bool valid = item < b.n;
-        int32_t lit = 0;
-        if (valid) {
-            if (probe_mode) {
-                const uint64_t idx = b.first + item;
-                const int32_t pv = (int32_t)(idx / 2 + 1);
-                lit = (idx & 1) ? -pv : pv;
-            } else {
-                const uint64_t o = b.cube_off[item];
-                if (b.cube_off[item + 1] - o == 1) lit = b.cube_lits[o];
+    const uint64_t stride = (uint64_t)gridDim.x * 256 * TRIAGE_ITEMS;
+    for (uint64_t wb = (uint64_t)blockIdx.x * 256 * TRIAGE_ITEMS; wb < b.n; wb += stride) {
+        const uint64_t base = wb + (uint64_t)threadIdx.x * TRIAGE_ITEMS;
+        int32_t lit[TRIAGE_ITEMS];
+        bool single[TRIAGE_ITEMS];
+#pragma unroll
+        for (int k = 0; k < TRIAGE_ITEMS; ++k) {
+            const uint64_t item = base + k;
+            lit[k] = 0;
+            single[k] = false;
+            if (item < b.n) {
+                if (b.cube_off) {
+                    const uint64_t o = b.cube_off[item];
+                    if (b.cube_off[item + 1] - o == 1) { lit[k] = b.cube_lits[o]; single[k] = true; }
+                } else if (b.cube_lits) {
+                    lit[k] = b.cube_lits[item];
+                    single[k] = true;
+                } else {
+                    const uint64_t idx = b.first + item;
+                    const int32_t pv = (int32_t)(idx / 2 + 1);
+                    lit[k] = (idx & 1) ? -pv : pv;
+                    single[k] = true;
+                }
             }
         }
-        uint8_t flag = 0xff;
-        bool self = false;
-        if (lit != 0) {
-            const uint32_t v = (uint32_t)(lit < 0 ? -lit : lit);
-            const uint8_t li = (int32_t)v <= db.max_var ? db.litinfo[2u * v + (lit < 0)] : 0;
-            if (!(li & LI_MAPPED)) flag = FLAG_UNMAPPED;
-            else if (li & LI_FALSE_L0) flag = FLAG_FALSE_L0;
-            else if (li & LI_TRUE_L0) flag = FLAG_TRIVIAL_L0;
-            else if (prune && !(li & LI_HAS_BIN)) {
-                flag = FLAG_OK;   // no binary clause on the negation: the probe implies exactly itself
-                self = true;
-                n_ref += (li & LI_NONEMPTY) != 0;
+        uint8_t li[TRIAGE_ITEMS];
+#pragma unroll
+        for (int k = 0; k < TRIAGE_ITEMS; ++k) {
+            const uint32_t v = (uint32_t)(lit[k] < 0 ? -lit[k] : lit[k]);
+            li[k] = (lit[k] != 0 && v <= (uint32_t)db.max_var) ? db.litinfo[2u * v + (lit[k] < 0)] : (uint8_t)0;
+        }
+        uint8_t flag[TRIAGE_ITEMS];
+        uint32_t len[TRIAGE_ITEMS];
+        bool deep[TRIAGE_ITEMS];
+#pragma unroll
+        for (int k = 0; k < TRIAGE_ITEMS; ++k) {
+            uint8_t f = 0xff;
+            bool self = false;
+            if (single[k] && lit[k] == 0 && !b.cube_off) f = FLAG_UNMAPPED;   // a 0 in a probe list names no variable
+            if (lit[k] != 0) {
+                if (!(li[k] & LI_MAPPED)) f = FLAG_UNMAPPED;
+                else if (li[k] & LI_FALSE_L0) f = FLAG_FALSE_L0;
+                else if (li[k] & LI_TRUE_L0) f = FLAG_TRIVIAL_L0;
+                else if (prune && !(li[k] & LI_HAS_BIN)) {
+                    f = FLAG_OK;   // no binary clause on the negation: the probe implies exactly itself
+                    self = true;
+                    n_ref += (li[k] & LI_NONEMPTY) != 0;
+                }
             }
+            const bool valid = base + k < b.n;
+            deep[k] = valid && f == 0xff;
+            flag[k] = f;
+            len[k] = self && want_len ? (LEN_SELF | 1u) : 0u;
+            if (valid && f != 0xff) { n_ok += self; n_skip += !self; }
         }
-        if (flag != 0xff) {
-            b.flag[item] = flag;
-            b.len[item] = self && (b.opts & OPT_IMPLIED) ? (LEN_SELF | 1u) : 0u;
-            n_ok += self;
-            n_skip += !self;
+        if (base + TRIAGE_ITEMS <= b.n) {
+            // deep items get their flag / size from the propagate kernels; writing a placeholder first is harmless
+            *reinterpret_cast<uchar4 *>(b.flag + base) = make_uchar4(flag[0], flag[1], flag[2], flag[3]);
+            *reinterpret_cast<uint4 *>(b.len + base) = make_uint4(len[0], len[1], len[2], len[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < TRIAGE_ITEMS; ++k)
+                if (base + k < b.n) { b.flag[base + k] = flag[k]; b.len[base + k] = len[k]; }
         }
-        const bool deep = valid && flag == 0xff;
-        const unsigned dm = __ballot_sync(FULL, deep);
-        if (dm) {
+        unsigned dm[TRIAGE_ITEMS];
+        uint32_t total = 0;
+#pragma unroll
+        for (int k = 0; k < TRIAGE_ITEMS; ++k) { dm[k] = __ballot_sync(FULL, deep[k]); total += __popc(dm[k]); }
+        if (total) {
             unsigned pos = 0;
-            if (lane_id() == 0) pos = atomicAdd(b.deep_count, (unsigned)__popc(dm));
+            if (lane_id() == 0) pos = atomicAdd(b.deep_count, total);
             pos = __shfl_sync(FULL, pos, 0);
-            if (deep) b.deep_list[pos + __popc(dm & lanemask_lt())] = (uint32_t)item;
+#pragma unroll
+            for (int k = 0; k < TRIAGE_ITEMS; ++k) {
+                if (deep[k]) b.deep_list[pos + __popc(dm[k] & lanemask_lt())] = (uint32_t)(base + k);
+                pos += __popc(dm[k]);
+            }
         }
     }
     // one set of counter atomics per block
@@ -834,70 +880,182 @@ __global__ void __launch_bounds__(512) k_block(const DbView db, const BatchView 
 }
 
 // ---------------------------------------------------------------- result compaction into canonical CSR order
-constexpr uint32_t GATHER_LONG = 1024;   // sets longer than this are copied chunk-wise by k_gather_long
+// One pass: sizes -> exclusive prefix sum (single-pass scan with decoupled look-back over 2048-item tiles)
+// -> CSR offsets written, every implied set copied from its allocation-order position in the pool to its
+// canonical position, self-implied literals regenerated from the item index. Sets above GATHER_GIANT are cut
+// into chunks for k_gather_long so that no CTA is stuck with one of them.
+constexpr int SG_THREADS = 256;
+constexpr int SG_ITEMS = 8;
+static_assert(SG_THREADS * SG_ITEMS == SG_TILE, "tile shape");
+constexpr uint32_t GATHER_WARP = 8;       // sets up to this size are copied by the owning thread
+constexpr uint32_t GATHER_BLOCK = 1024;   // up to this by a warp, above by the whole CTA
+constexpr uint32_t GATHER_GIANT = 16384;  // above: chunked through k_gather_long
 constexpr uint32_t GATHER_CHUNK = 2048;
 
-__global__ void k_gather(const BatchView b, const uint64_t *__restrict__ off, int32_t *__restrict__ dst)
+__device__ __forceinline__ int32_t item_self_lit(const BatchView &b, uint64_t item)
 {
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const int lane = lane_id();
-    // self-implying probes regenerate their literal; short sets: one item per lane; medium: warp copy;
-    // long sets are cut into chunks for k_gather_long so that no warp is stuck with a giant
-    for (uint64_t base = warp * 32; base < b.n; base += nwarps * 32) {
-        const uint64_t item = base + lane;
-        uint32_t len = 0;
-        uint64_t src = 0, d = 0;
-        if (item < b.n) { len = b.len[item]; d = off[item]; }
-        if (len & LEN_SELF) {
-            int32_t lit;
-            if (b.cube_off) lit = b.cube_lits[b.cube_off[item]];
-            else {
-                const uint64_t idx = b.first + item;
-                const int32_t pv = (int32_t)(idx / 2 + 1);
-                lit = (idx & 1) ? -pv : pv;
+    if (b.cube_off) return b.cube_lits[b.cube_off[item]];
+    if (b.cube_lits) return b.cube_lits[item];
+    const uint64_t idx = b.first + item;
+    const int32_t pv = (int32_t)(idx / 2 + 1);
+    return (idx & 1) ? -pv : pv;
+}
+
+// Cooperative launch (all CTAs co-resident). The items are cut into one contiguous segment per CTA.
+// Phase 1: every CTA sums the set sizes of its segment and publishes the sum; grid barrier. Phase 2: every CTA
+// adds up the sums of the segments before its own (<= a few hundred values), then walks its segment again
+// (from L2 now), 2048 items per step in a warp-striped arrangement -- lane l of warp w owns items
+// w*256 + j*32 + l, j = 0..7, so every load and store of a warp is one contiguous 128/256-byte run -- turns
+// sizes into offsets with warp shuffles, writes the offsets and moves the literals.
+__global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, const int pass, const uint64_t seg)
+{
+    // first pass of a batch: if some probes still wait for the CTA-per-probe tiers the sizes are not final
+    // (uniform over the grid, so nobody is left waiting at the barrier)
+    if (pass == 0 && *(volatile uint32_t *)b.mid_count != 0) return;
+    __shared__ unsigned long long s_warp[SG_THREADS / 32], s_red[SG_THREADS / 32];
+    __shared__ uint32_t s_nbig, s_pos;
+    __shared__ uint16_t s_big[SG_TILE];
+    __shared__ unsigned long long s_bigdst[SG_TILE];
+    const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const uint64_t n = b.n;
+    const bool off32 = (b.opts & OPT_OFF32) != 0;
+    int32_t *__restrict__ dst = b.impl;
+    const uint64_t lo = min((unsigned long long)blockIdx.x * seg, (unsigned long long)n), hi = min((unsigned long long)(lo + seg), (unsigned long long)n);
+
+    // ---- phase 1: segment sum
+    unsigned long long sum = 0;
+    for (uint64_t i = lo + tid; i < hi; i += SG_THREADS) sum += b.len[i] & 0x7fffffffu;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(FULL, sum, d);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    volatile unsigned long long *part = b.tile_state;   // [gridDim.x] segment sums, then the barrier word
+    if (tid == 0) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int k = 0; k < SG_THREADS / 32; ++k) t += s_red[k];
+        part[blockIdx.x] = t;
+        __threadfence();
+        atomicAdd(b.tile_ticket, 1u);
+        while (*(volatile uint32_t *)b.tile_ticket < gridDim.x) {}
+        __threadfence();
+    }
+    __syncthreads();
+
+    // ---- phase 2: my prefix = sum of the segments before mine
+    unsigned long long pre = 0;
+    for (uint32_t k = tid; k < blockIdx.x; k += SG_THREADS) pre += part[k];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) pre += __shfl_xor_sync(FULL, pre, d);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = pre;
+    __syncthreads();
+    unsigned long long run = 0;   // offset of the first item of the current step
+#pragma unroll
+    for (int k = 0; k < SG_THREADS / 32; ++k) run += s_red[k];
+    if (blockIdx.x == gridDim.x - 1 && lo >= hi && tid == 0) {
+        // degenerate tail (n == 0, or n a multiple of seg with spare CTAs): the last CTA still owes off[n]
+        if (off32) ((uint32_t *)b.off)[n] = (uint32_t)run; else ((uint64_t *)b.off)[n] = run;
+        *b.total = run;
+    }
+
+    for (uint64_t cbase = lo; cbase < hi; cbase += SG_TILE) {
+        if (tid == 0) s_nbig = 0;
+        const uint64_t wbase = cbase + (uint64_t)warp * (32 * SG_ITEMS);
+        uint32_t len[SG_ITEMS];
+        unsigned long long o[SG_ITEMS];
+        unsigned long long rowbase = 0;
+#pragma unroll
+        for (int j = 0; j < SG_ITEMS; ++j) {
+            const uint64_t item = wbase + j * 32 + lane;
+            len[j] = item < hi ? b.len[item] : 0u;
+            const unsigned long long v = len[j] & 0x7fffffffu;
+            unsigned long long incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
             }
-            dst[d] = lit;
-            len = 0;
+            o[j] = rowbase + incl - v;
+            rowbase += __shfl_sync(FULL, incl, 31);
         }
-        if (len) src = b.raw_off[item];
-        if (len && len <= 4) {
-            for (uint32_t i = 0; i < len; ++i) dst[d + i] = b.out_lits[src + i];
+        if (lane == 0) s_warp[warp] = rowbase;
+        __syncthreads();
+        unsigned long long before = 0, agg = 0;
+#pragma unroll
+        for (int k = 0; k < SG_THREADS / 32; ++k) { const unsigned long long x = s_warp[k]; agg += x; if (k < warp) before += x; }
+        const unsigned long long wrun = run + before;
+#pragma unroll
+        for (int j = 0; j < SG_ITEMS; ++j) {
+            const uint64_t item = wbase + j * 32 + lane;
+            o[j] += wrun;
+            if (item < hi) { if (off32) ((uint32_t *)b.off)[item] = (uint32_t)o[j]; else ((uint64_t *)b.off)[item] = o[j]; }
         }
-        unsigned big = __ballot_sync(FULL, len > 4 && len <= GATHER_LONG);
-        while (big) {
-            const int j = __ffs(big) - 1;
-            big &= big - 1;
-            const uint32_t l = __shfl_sync(FULL, len, j);
-            const uint64_t s = __shfl_sync(FULL, src, j), dd = __shfl_sync(FULL, d, j);
-            for (uint32_t i = lane; i < l; i += 32) dst[dd + i] = b.out_lits[s + i];
+        run += agg;
+        if (cbase + SG_TILE >= hi && hi == n && tid == 0) {   // the step that holds the last item: off[n], total
+            if (off32) ((uint32_t *)b.off)[n] = (uint32_t)run; else ((uint64_t *)b.off)[n] = run;
+            *b.total = run;
         }
-        unsigned lng = __ballot_sync(FULL, len > GATHER_LONG);
-        while (lng) {
-            const int j = __ffs(lng) - 1;
-            lng &= lng - 1;
-            const uint32_t l = __shfl_sync(FULL, len, j);
-            const uint32_t nch = (l + GATHER_CHUNK - 1) / GATHER_CHUNK;
-            uint32_t pos = 0;
-            if (lane == 0) pos = atomicAdd(b.chunk_count, nch);
-            pos = __shfl_sync(FULL, pos, 0);
-            for (uint32_t c = lane; c < nch; c += 32) b.chunk_list[pos + c] = make_uint2((uint32_t)(base + j), c);
+        // literals
+#pragma unroll
+        for (int j = 0; j < SG_ITEMS; ++j) {
+            const uint64_t item = wbase + j * 32 + lane;
+            uint32_t l = len[j];
+            uint64_t src = 0;
+            if (l & LEN_SELF) { dst[o[j]] = item_self_lit(b, item); l = 0; }
+            if (l) src = b.raw_off[item];
+            if (l && l <= GATHER_WARP) {
+                for (uint32_t i = 0; i < l; ++i) dst[o[j] + i] = b.out_lits[src + i];
+            }
+            unsigned med = __ballot_sync(FULL, l > GATHER_WARP && l <= GATHER_BLOCK);
+            while (med) {
+                const int k = __ffs(med) - 1;
+                med &= med - 1;
+                const uint32_t ll = __shfl_sync(FULL, l, k);
+                const uint64_t ss = __shfl_sync(FULL, src, k), dd = __shfl_sync(FULL, o[j], k);
+                for (uint32_t i = lane; i < ll; i += 32) dst[dd + i] = b.out_lits[ss + i];
+            }
+            if (l > GATHER_BLOCK) {
+                const uint32_t e = atomicAdd(&s_nbig, 1u);
+                s_big[e] = (uint16_t)(warp * (32 * SG_ITEMS) + j * 32 + lane);
+                s_bigdst[e] = o[j];
+            }
         }
+        __syncthreads();
+        const uint32_t nbig = s_nbig;
+        for (uint32_t e = 0; e < nbig; ++e) {
+            const uint64_t item = cbase + s_big[e];
+            const uint32_t l = b.len[item] & 0x7fffffffu;
+            if (l > GATHER_GIANT) {
+                const uint32_t nch = (l + GATHER_CHUNK - 1) / GATHER_CHUNK;
+                if (tid == 0) s_pos = atomicAdd(b.chunk_count, nch);
+                __syncthreads();
+                const uint32_t pos = s_pos;
+                for (uint32_t c = tid; c < nch; c += SG_THREADS) b.chunk_list[pos + c] = make_uint2((uint32_t)item, c);
+                __syncthreads();
+                continue;
+            }
+            const uint64_t ss = b.raw_off[item], dd = s_bigdst[e];
+            for (uint32_t i = tid; i < l; i += SG_THREADS) dst[dd + i] = b.out_lits[ss + i];
+        }
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(256) k_gather_long(const BatchView b, const uint64_t *__restrict__ off, int32_t *__restrict__ dst)
+__global__ void __launch_bounds__(256) k_gather_long(const BatchView b)
 {
     const uint32_t nchunks = *b.chunk_count;
+    const bool off32 = (b.opts & OPT_OFF32) != 0;
     for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const uint2 e = b.chunk_list[c];
-        const uint32_t len = b.len[e.x];
-        const uint64_t src = b.raw_off[e.x] + (uint64_t)e.y * GATHER_CHUNK, d = off[e.x] + (uint64_t)e.y * GATHER_CHUNK;
+        const uint32_t len = b.len[e.x] & 0x7fffffffu;
+        const uint64_t o = off32 ? (uint64_t)((const uint32_t *)b.off)[e.x] : ((const uint64_t *)b.off)[e.x];
+        const uint64_t src = b.raw_off[e.x] + (uint64_t)e.y * GATHER_CHUNK, d = o + (uint64_t)e.y * GATHER_CHUNK;
         const uint32_t m = min(GATHER_CHUNK, len - e.y * GATHER_CHUNK);
 #pragma unroll
         for (uint32_t k = 0; k < GATHER_CHUNK / 256; ++k) {
             const uint32_t i = k * 256 + threadIdx.x;
-            if (i < m) dst[d + i] = b.out_lits[src + i];
+            if (i < m) b.impl[d + i] = b.out_lits[src + i];
         }
     }
 }
@@ -954,14 +1112,26 @@ void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int 
     k_block<true><<<blocks, BIG_THREADS, 0, s>>>(db, b, ls, 0, 0);
 }
 
-void launch_gather(const BatchView &b, const uint64_t *off, int32_t *dst, cudaStream_t s)
+int scan_gather_max_blocks(int sm_count)
 {
-    const uint64_t warps = (b.n + 31) / 32;
-    int blocks = (int)((warps + 7) / 8);
-    if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_gather<<<blocks, 256, 0, s>>>(b, off, dst);
-    k_gather_long<<<148 * 8, 256, 0, s>>>(b, off, dst);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_gather, SG_THREADS, 0);
+    return std::max(1, std::min(nb, 4)) * sm_count;
+}
+
+bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, cudaStream_t s)
+{
+    // one contiguous segment of whole 2048-item steps per CTA
+    uint64_t blocks = std::min<uint64_t>(std::max<uint64_t>((b.n + SG_TILE - 1) / SG_TILE, 1), (uint64_t)max_blocks);
+    uint64_t seg = ((b.n + blocks - 1) / blocks + SG_TILE - 1) / SG_TILE * SG_TILE;
+    if (seg == 0) seg = SG_TILE;
+    blocks = std::max<uint64_t>((b.n + seg - 1) / seg, 1);
+    BatchView bv = b;
+    int p = pass;
+    void *args[] = {&bv, &p, &seg};
+    if (cudaLaunchCooperativeKernel((const void *)k_scan_gather, dim3((unsigned)blocks), dim3(SG_THREADS), args, 0, s) != cudaSuccess) return false;
+    if (giant_sets_possible) k_gather_long<<<max_blocks, 256, 0, s>>>(b);
+    return true;
 }
 
 }  // namespace bbcp

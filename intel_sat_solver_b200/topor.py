@@ -20,14 +20,17 @@ from ._lib import BatchInfo, DbInfo, Opts
 
 OPT_IMPLIED = 1
 OPT_NO_LEN_PRUNE = 2
+OPT_OFF32 = 4
 
 
 class TToporReturnVal(enum.IntEnum):
     """ToporExternalTypes.hpp:52-78 (the values this path can produce)."""
     RET_SAT = 0
     RET_UNSAT = 1
+    RET_MEM_OUT = 4
     RET_USER_INTERRUPT = 5   # fixpoint reached, search not run (what SetCbStopNow->VAL_STOP yields in the reference)
-    RET_EXOTIC_ERROR = 10
+    RET_INDEX_TOO_NARROW = 6
+    RET_EXOTIC_ERROR = 11
 
 
 class TToporLitVal(enum.IntEnum):
@@ -123,18 +126,20 @@ class BatchedTopor:
         return rc
 
     @staticmethod
-    def _opts(implied=True, small_trail=0, out_capacity=0, no_len_prune=False, mid_trail=0) -> Opts:
-        return Opts((OPT_IMPLIED if implied else 0) | (OPT_NO_LEN_PRUNE if no_len_prune else 0), small_trail, out_capacity, mid_trail, 0)
+    def _opts(implied=True, small_trail=0, out_capacity=0, no_len_prune=False, mid_trail=0, off32=False) -> Opts:
+        return Opts((OPT_IMPLIED if implied else 0) | (OPT_NO_LEN_PRUNE if no_len_prune else 0) | (OPT_OFF32 if off32 else 0),
+                    small_trail, out_capacity, mid_trail, 0)
 
-    def _fetch(self, info: BatchInfo, implied: bool, fetch: bool) -> BatchResult:
+    def _fetch(self, info: BatchInfo, implied: bool, fetch: bool, off32: bool = False) -> BatchResult:
         res = BatchResult(info.as_dict())
         if fetch:
             res.flag = np.empty(info.n, dtype=np.uint8)
             self._check(self._L.bbcp_fetch_flags(self._h, res.flag.ctypes.data))
             if implied:
-                res.impl_off = np.empty(info.n + 1, dtype=np.uint64)
+                res.impl_off = np.empty(info.n + 1, dtype=np.uint32 if off32 else np.uint64)
                 res.impl_lits = np.empty(max(info.n_implied, 1), dtype=np.int32)
-                self._check(self._L.bbcp_fetch_implied(self._h, res.impl_off.ctypes.data, res.impl_lits.ctypes.data))
+                f = self._L.bbcp_fetch_implied32 if off32 else self._L.bbcp_fetch_implied
+                self._check(f(self._h, res.impl_off.ctypes.data, res.impl_lits.ctypes.data))
                 res.impl_lits = res.impl_lits[: info.n_implied]
         return res
 
@@ -142,7 +147,15 @@ class BatchedTopor:
         info = BatchInfo()
         o = self._opts(implied=implied, **kw)
         self._check(self._L.bbcp_probe_range(self._h, first, last, C.byref(o), C.byref(info)))
-        return self._fetch(info, implied, fetch)
+        return self._fetch(info, implied, fetch, kw.get("off32", False))
+
+    def ProbeLits(self, lits, implied=True, fetch=True, **kw) -> BatchResult:
+        """Explicit list of depth-1 probes (4 bytes per probe on the way in)."""
+        a = np.ascontiguousarray(lits, dtype=np.int32)
+        info = BatchInfo()
+        o = self._opts(implied=implied, **kw)
+        self._check(self._L.bbcp_probe_lits(self._h, a.ctypes.data if a.size else None, a.size, C.byref(o), C.byref(info)))
+        return self._fetch(info, implied, fetch, kw.get("off32", False))
 
     def ProbeAll(self, implied=True, fetch=True, **kw) -> BatchResult:
         return self.ProbeRange(0, 2 * self.max_var, implied=implied, fetch=fetch, **kw)
@@ -155,7 +168,7 @@ class BatchedTopor:
         info = BatchInfo()
         o = self._opts(implied=implied, **kw)
         self._check(self._L.bbcp_propagate_batch(self._h, lits.ctypes.data, off.ctypes.data, off.size - 1, C.byref(o), C.byref(info)))
-        return self._fetch(info, implied, fetch)
+        return self._fetch(info, implied, fetch, kw.get("off32", False))
 
     def Bitmaps(self) -> tuple[np.ndarray, np.ndarray]:
         n = self._L.bbcp_bitmap_words(self._h)

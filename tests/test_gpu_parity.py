@@ -200,3 +200,73 @@ def test_explicit_probe_list_equals_probe_universe(golden):
         t.ProbeAll(implied=False)
         fb, ub = t.Bitmaps()
         assert np.array_equal(fa, fb) and np.array_equal(ua, ub) and fa.any() == bool((g("probe_flag") == 1).any())
+
+
+def test_probe_list_and_u32_offsets(golden):
+    """bbcp_probe_lits (4-byte probe list) and BBCP_OPT_OFF32 (u32 CSR offsets) give the bits of the universe pass;
+    a 0 in the list and out-of-range variables are reported unmapped."""
+    for name in ["regr_47", "fuzz_10", "hand_long"]:
+        g = lambda k: golden[f"{name}/{k}"]
+        t, _ = engine_for(g("words"))
+        n = 2 * t.max_var
+        idx = np.arange(n)
+        lits = np.where(idx & 1, -(idx // 2 + 1), idx // 2 + 1).astype(np.int32)
+        res = t.ProbeLits(lits)
+        gpu_util.assert_same_results(res, g("probe_flag"), g("probe_off"), g("probe_lits"), name)
+        res32 = t.ProbeLits(lits, off32=True)
+        assert res32.impl_off.dtype == np.uint32
+        gpu_util.assert_same_results(res32, g("probe_flag"), g("probe_off").astype(np.uint32), g("probe_lits"), name + " off32")
+        res32 = t.ProbeAll(off32=True)
+        gpu_util.assert_same_results(res32, g("probe_flag"), g("probe_off").astype(np.uint32), g("probe_lits"), name + " universe off32")
+        # fetching with the wrong width is refused, not silently mis-read
+        assert t.lib.bbcp_fetch_implied(t.handle, None, None) == -4
+        # permuted list with junk entries
+        rng = np.random.default_rng(7)
+        perm = rng.permutation(n)
+        junk = np.concatenate([lits[perm], np.array([0, t.max_var + 5, -(t.max_var + 9)], dtype=np.int32)])
+        r = t.ProbeLits(junk)
+        assert np.array_equal(r.flag[:n], g("probe_flag")[perm]) and (r.flag[n:] == 4).all()
+        sizes = np.diff(g("probe_off"))
+        assert np.array_equal(np.diff(r.impl_off)[:n], sizes[perm])
+        for k in range(0, n, max(1, n // 50)):
+            p = perm[k]
+            assert np.array_equal(r.implied(k), g("probe_lits")[int(g("probe_off")[p]):int(g("probe_off")[p + 1])])
+        empty = t.ProbeLits(np.zeros(0, dtype=np.int32))
+        assert empty.info["n"] == 0 and empty.impl_off.tolist() == [0]
+
+
+def test_large_batch_scan_and_giant_sets():
+    """Many tiles of the single-pass scan (decoupled look-back across > 100 tiles), sets copied by thread / warp /
+    CTA / chunked, against the checker on a chain instance whose probes imply thousands of literals."""
+    with tempfile.TemporaryDirectory() as d:
+        # x1 -> x2 -> ... -> xN chain: probing x_i implies N-i+1 literals; plus noise ternaries
+        N = 40000
+        words = []
+        for i in range(1, N):
+            words += [-i, i + 1, 0]
+        rng = np.random.default_rng(3)
+        for _ in range(20000):
+            a, b, c = rng.choice(np.arange(N + 1, N + 20001), 3, replace=False)
+            words += [int(a), -int(b), int(c), 0]
+        words = np.asarray(words, dtype=np.int32)
+        used = set(np.abs(words).tolist())
+        t, rc = engine_for(words)
+        assert rc == 0
+        lits = np.concatenate([np.arange(1, N + 1, 97), -np.arange(1, N + 1, 89), np.arange(N + 1, N + 20001)]).astype(np.int32)
+        res = t.ProbeLits(lits)
+        sizes = np.diff(res.impl_off).astype(np.int64)
+        for k, l in enumerate(lits.tolist()):
+            if 0 < l <= N:
+                assert res.flag[k] == 0 and sizes[k] == N - l + 1
+                if k % 40 == 0:
+                    assert np.array_equal(res.implied(k), np.arange(l, N + 1, dtype=np.int32))
+            elif l < 0:
+                assert res.flag[k] == 0 and sizes[k] == -l
+                if k % 40 == 0:
+                    assert np.array_equal(res.implied(k), -np.arange(1, -l + 1, dtype=np.int32))
+            elif l in used:
+                assert res.flag[k] == 0 and sizes[k] == 1 and res.implied(k)[0] == l
+            else:
+                assert res.flag[k] == 4 and sizes[k] == 0
+        assert res.info["n_large"] > 0 and res.info["n_mid"] > 0
+        assert int(res.impl_off[-1]) == res.info["n_implied"] == int(sizes.sum())
