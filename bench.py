@@ -193,6 +193,7 @@ def ours_arm(args, rank, local_rank, world):
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     opts = Opts(1, 0, 0, 0, 0)
+    opts_timed = Opts(1 | 8, 0, 0, 0, 0)   # + BBCP_OPT_KERNEL_TIMES: per-kernel CUDA events (separate pass)
     info = BatchInfo()
     if world > 1:
         failed_t = torch.as_tensor(DevArr(L.bbcp_device_failed_bitmap(h), words_total), device=dev)
@@ -221,7 +222,7 @@ def ours_arm(args, rank, local_rank, world):
         return ms
 
     clocks = ClockSampler(local_rank)
-    stats = {"triage_ms": [], "deep_ms": [], "kernel_bytes": 0, "triage_bytes": 0, "launches": 0, "props_ref": 0, "props_all": 0}
+    stats = {"triage_ms": [], "deep_ms": [], "compact_ms": [], "block_ms": [], "kernel_bytes": 0, "triage_bytes": 0, "launches": 0, "props_ref": 0, "props_all": 0}
     step_ms = []
     for it in range(args.warmup + args.steps):
         flush.fill_(it & 0xff)       # L2 flush between iterations
@@ -231,11 +232,19 @@ def ours_arm(args, rank, local_rank, world):
         ms = device_step()
         if it >= args.warmup:
             step_ms.append(ms)
-            stats["triage_ms"].append(info.triage_ms)
-            stats["deep_ms"].append(info.deep_ms)
             stats["kernel_bytes"], stats["triage_bytes"] = info.kernel_bytes, info.triage_bytes
             stats["launches"] += info.launches
             stats["props_ref"], stats["props_all"] = info.props_ref, info.props_all
+    n_conflict, n_implied = info.n_conflict, info.n_implied
+    # per-kernel durations for the roofline: the same steps again with CUDA events between the kernels
+    # (BBCP_OPT_KERNEL_TIMES; kept out of the loop above because the extra events cost stream time)
+    for it in range(args.steps):
+        flush.fill_(it & 0xff)
+        barrier()
+        rc = L.bbcp_probe_range(h, first, last, C.byref(opts_timed), C.byref(info))
+        assert rc == 0, eng.GetStatusExplanation()
+        for k in ("triage_ms", "deep_ms", "compact_ms", "block_ms"):
+            stats[k].append(getattr(info, k))
     barrier()
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     probes = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
@@ -246,7 +255,6 @@ def ours_arm(args, rank, local_rank, world):
         dist.all_reduce(props)
     total_s = float(total_ms.item()) / 1e3
     value = float(probes.item()) * args.steps / total_s
-    n_conflict, n_implied = info.n_conflict, info.n_implied
 
     # ---- e2e: the call a user makes, host buffers in and out, every step
     idx = np.arange(first, last, dtype=np.int64)
@@ -293,17 +301,22 @@ def ours_arm(args, rank, local_rank, world):
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        tri = sum(stats["triage_ms"]) / len(stats["triage_ms"]) / 1e3
-        dee = sum(stats["deep_ms"]) / len(stats["deep_ms"]) / 1e3
-        # the dominant kernel of the step: the triage (k_triage) when nothing propagates, else the propagate kernel
-        if stats["kernel_bytes"] - stats["triage_bytes"] > stats["triage_bytes"]:
-            kname, kbytes, t1 = "k_deep (warp-per-probe propagate, shared-memory state)", stats["kernel_bytes"] - stats["triage_bytes"], dee
-        else:
-            kname, kbytes, t1 = "k_triage (one probe per thread, streaming)", stats["triage_bytes"], tri
+        avg = lambda k: sum(stats[k]) / max(len(stats[k]), 1) / 1e3
+        tri, dee, com, blk = avg("triage_ms"), avg("deep_ms"), avg("compact_ms"), avg("block_ms")
+        # bytes model of DESIGN.md section 4, per launch: triage; propagation (engine counters); compaction =
+        # 4 B size read twice (segment sums, then offsets) + 8 B offset + 4 B literal written per item here
+        # (every implied set of this workload is the probe's own literal, regenerated, so nothing is read back)
+        prop_bytes = stats["kernel_bytes"] - stats["triage_bytes"]
+        compact_bytes = n_local * (4 + 4 + 8) + int(n_implied) * 4
+        cands = [("k_triage (8 probes per thread, streaming)", stats["triage_bytes"], tri),
+                 ("k_deep (warp-per-probe propagate, shared-memory state)", prop_bytes, dee + blk),
+                 ("k_scan_gather (cooperative single-pass scan + gather)", compact_bytes, com)]
+        # the dominant kernel of the step = the one with the longest device time
+        kname, kbytes, t1 = max(cands, key=lambda c: c[2])
         achieved = kbytes / t1 / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_small_c2_dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname.split(" ")[0])
         except (OSError, ValueError):
             pass
         # SURVEY.md 8d ABYTES for this instance family in closed form: T={p}, no binaries, every long
@@ -323,7 +336,10 @@ def ours_arm(args, rank, local_rank, world):
             "gpu_launches": stats["launches"],
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
-                         "bytes_per_launch": kbytes, "kernel_ms": 1e3 * t1, "triage_ms": 1e3 * tri, "deep_ms": 1e3 * dee, "traffic": traffic,
+                         "bytes_per_launch": kbytes, "kernel_ms": 1e3 * t1, "triage_ms": 1e3 * tri, "deep_ms": 1e3 * dee, "compact_ms": 1e3 * com,
+                         "all_kernels": {"bytes": stats["triage_bytes"] + prop_bytes + compact_bytes, "ms": 1e3 * (tri + dee + blk + com),
+                                         "frac": (stats["triage_bytes"] + prop_bytes + compact_bytes) / max(tri + dee + blk + com, 1e-12) / 1e9 / peak},
+                         "traffic": traffic,
                          "abytes_2wl_per_launch": abytes_2wl if world == 1 else None,
                          "abytes_2wl_frac_of_step": (abytes_2wl / (total_s / args.steps) / 1e9 / peak) if world == 1 else None},
             "cpu_baseline": cpu,

@@ -48,6 +48,8 @@ enum {
 enum {
     BBCP_OPT_IMPLIED = 1u,     /* produce the per-probe implied-literal sets (else flags + bitmaps only) */
     BBCP_OPT_NO_LEN_PRUNE = 2u,/* diagnostic: scan ternary/long rows even while only one literal is assigned */
+    BBCP_OPT_KERNEL_TIMES = 8u,/* record CUDA events between the kernels and fill triage_ms / deep_ms / block_ms (a few
+                                  microseconds of stream time per batch; total_ms is always measured) */
     BBCP_OPT_OFF32 = 4u        /* produce impl_off as uint32 (fetch with bbcp_fetch_implied32): halves the offset
                                   read-back; the batch fails with BBCP_ERR_ARG if it implies >= 2^32 literals */
 };
@@ -73,7 +75,7 @@ typedef struct {
     uint64_t kernel_bytes;     /* algorithmic bytes moved by triage + propagation ("bytes model") */
     uint64_t triage_bytes;     /* of those, the triage kernel's */
     uint64_t n_deep;           /* items the triage queued for propagation */
-    float kernel_ms;           /* triage_ms + deep_ms + block_ms */
+    float kernel_ms;           /* triage_ms + deep_ms + block_ms (per-kernel times need BBCP_OPT_KERNEL_TIMES) */
     float total_ms;            /* device time of the whole call incl. result compaction (CUDA events) */
     uint32_t launches;         /* kernels of this engine launched by the call (library scan kernels not counted) */
     float tier1_ms;            /* triage_ms + deep_ms */
@@ -82,6 +84,8 @@ typedef struct {
     float block_ms;            /* device time of the two CTA-per-probe tiers (last attempt) */
     float mid_ms;              /* of which the shared-memory one */
     uint64_t n_mid;            /* probes that ran in the second tier (CTA per probe, state in shared memory) */
+    float compact_ms;          /* device time of k_scan_gather (+ k_gather_long), last sequence */
+    float reserved_f;
 } bbcp_batch_info;
 
 typedef struct {

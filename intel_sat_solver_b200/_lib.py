@@ -18,7 +18,8 @@ class BatchInfo(C.Structure):
                 ("slots", C.c_uint64), ("clause_fetches", C.c_uint64), ("kernel_bytes", C.c_uint64),
                 ("triage_bytes", C.c_uint64), ("n_deep", C.c_uint64),
                 ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("tier1_ms", C.c_float),
-                ("triage_ms", C.c_float), ("deep_ms", C.c_float), ("block_ms", C.c_float), ("mid_ms", C.c_float), ("n_mid", C.c_uint64)]
+                ("triage_ms", C.c_float), ("deep_ms", C.c_float), ("block_ms", C.c_float), ("mid_ms", C.c_float), ("n_mid", C.c_uint64),
+                ("compact_ms", C.c_float), ("reserved_f", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,8 +43,9 @@ struct DevBuf {
 // total (a copy of off[n])
 constexpr int MISC_CURSOR = C_N;
 constexpr int MISC_U32 = C_N + 1;       // as u32 index from 2*MISC_U32: +0..2 tickets, +3 mid_count, +4 big_count, +5 deep_count
-constexpr int MISC_TOTAL = C_N + 5;     // (u32 +6 = chunk_count of the giant-set gather, +7 = tile ticket of the scan)
-constexpr int MISC_WORDS64 = C_N + 6;
+                                        // +6 chunk_count of the giant-set gather, +7 grid barrier of the scan, +8 its finished-CTA count
+constexpr int MISC_TOTAL = C_N + 6;
+constexpr int MISC_WORDS64 = C_N + 7;
 // two counter blocks used alternately: the triage kernel of one launch sequence zeroes the block of the next one
 
 }  // namespace
@@ -68,7 +70,9 @@ struct bbcp_handle {
     DevBuf d_flag, d_raw_off, d_len, d_out, d_off, d_impl, d_cube_lits, d_cube_off, d_overflow, d_big, d_deep, d_chunks, d_misc, d_lbits, d_ltrail, d_tiles;
     uint32_t misc_parity = 0;
     bool last_off32 = false;
-    unsigned long long *h_misc = nullptr;   // pinned
+    unsigned long long *h_misc = nullptr;   // pinned, mapped
+    void *d_hmisc = nullptr;                // its device address
+    int lean = 3;                           // bit 0: counters reach the host through mapped memory; bit 1: no per-kernel events
     uint64_t out_cap_hint = 0;   // stored literals the last batch needed (sizes the next batch's buffer)
     uint32_t big_slabs = 0;
     uint32_t slab_version = 0;   // db_version the slabs were sized for
@@ -114,7 +118,9 @@ bool ensure_device(bbcp_handle *h)
     h->sg_blocks = scan_gather_max_blocks(h->sm_count);
     if (!h->cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
     for (auto &e : h->ev) if (!h->cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return false;
-    if (!h->cuda_ok(cudaMallocHost(&h->h_misc, MISC_WORDS64 * 8), "cudaMallocHost")) return false;
+    if (!h->cuda_ok(cudaHostAlloc(&h->h_misc, MISC_WORDS64 * 8, cudaHostAllocMapped), "cudaHostAlloc")) return false;
+    if (!h->cuda_ok(cudaHostGetDevicePointer(&h->d_hmisc, h->h_misc, 0), "cudaHostGetDevicePointer")) return false;
+    h->lean = getenv("BBCP_LEAN") ? atoi(getenv("BBCP_LEAN")) : 3;
     if (!h->d_misc.reserve(2 * MISC_WORDS64 * 8, true)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (counters)"); return false; }
     if (!h->cuda_ok(cudaDeviceSynchronize(), "counter init")) return false;
     h->device_ready = true;
@@ -133,8 +139,8 @@ bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo)
     HostDb &db = h->db;
     // per-literal facts for the triage: level-0 value and mappedness of the variable, and what the row of
     // the literal's NEGATION holds (that row is the one scanned when the literal is assigned)
-    std::vector<uint8_t> litinfo(db.hdr.size(), 0);
-    for (size_t l = 2; l < litinfo.size(); ++l) {
+    std::vector<uint8_t> litinfo(db.hdr.size() + 16, 0);   // padded: the triage reads it in aligned 32-bit words
+    for (size_t l = 2; l < db.hdr.size(); ++l) {
         const uint8_t vi = varinfo[l >> 1];
         uint8_t li = 0;
         if (vi & 4) li |= LI_MAPPED;
@@ -221,6 +227,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     if (cap_mid > 16384) cap_mid = 16384;
     const bool implied = (opts.flags & BBCP_OPT_IMPLIED) != 0;
     const bool off32 = (opts.flags & BBCP_OPT_OFF32) != 0;
+    const bool want_kernel_times = (opts.flags & BBCP_OPT_KERNEL_TIMES) != 0 || !(h->lean & 2);
     uint64_t out_cap = implied ? (opts.out_capacity ? opts.out_capacity : std::max<uint64_t>({(uint64_t)1 << 20, 4 * n, h->out_cap_hint + h->out_cap_hint / 4})) : 0;
 
     DbView dbv = db_view(h);
@@ -248,7 +255,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     const int bps = small_blocks_per_sm(cap);
     if (bps <= 0) return h->fail(BBCP_ERR_CUDA, "propagate kernel does not fit (shared memory)");
     const uint32_t *h_u32 = reinterpret_cast<uint32_t *>(h->h_misc) + 2 * MISC_U32;
-    float triage_ms = 0, deep_ms = 0, block_ms = 0, mid_ms = 0;
+    float triage_ms = 0, deep_ms = 0, block_ms = 0, mid_ms = 0, compact_ms = 0;
 
     cudaEventRecord(h->ev[0], h->stream);
     for (int attempt = 0;; ++attempt) {
@@ -274,14 +281,18 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         b.deep_count = u32 + 5;
         b.chunk_count = u32 + 6;
         b.tile_ticket = u32 + 7;
+        const bool zero_copy = implied && n && (h->lean & 1);
+        const bool kevents = want_kernel_times;
+        b.host_report = zero_copy ? static_cast<unsigned long long *>(h->d_hmisc) : nullptr;
         bi.launches = 0;
         bool second = false;
+        reinterpret_cast<uint32_t *>(h->h_misc)[2 * MISC_U32 + 8] = 0;   // "report written" mark of the mapped copy
         if (n) {
-            cudaEventRecord(h->ev[3], h->stream);
-            launch_triage(b, dbv, (int)std::min<uint64_t>((n + 1023) / 1024, (uint64_t)h->sm_count * 8), h->stream);
-            cudaEventRecord(h->ev[4], h->stream);
+            if (kevents) cudaEventRecord(h->ev[3], h->stream);
+            launch_triage(b, dbv, h->sm_count, h->stream);
+            if (kevents) cudaEventRecord(h->ev[4], h->stream);
             launch_small(dbv, b, cap, bps * h->sm_count, h->stream);
-            cudaEventRecord(h->ev[5], h->stream);
+            if (kevents) cudaEventRecord(h->ev[5], h->stream);
             bi.launches += 2;
             if (implied) {
                 if (!launch_scan_gather(b, 0, h->sg_blocks, false, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
@@ -292,9 +303,14 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             cudaMemsetAsync(b.zero_next, 0, MISC_WORDS64 * 8, h->stream);
             cudaMemsetAsync(h->d_off.p, 0, 8, h->stream);
         }
-        cudaMemcpyAsync(h->h_misc, misc, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (!zero_copy) cudaMemcpyAsync(h->h_misc, misc, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
         cudaEventRecord(h->ev[2], h->stream);
         if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "propagate kernels")) return BBCP_ERR_CUDA;
+        if (zero_copy && h_u32[8] == 0) {
+            // k_scan_gather returned early (probes wait for the CTA-per-probe tiers): only then the report is missing
+            cudaMemcpyAsync(h->h_misc, misc, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
+            if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "counter read-back")) return BBCP_ERR_CUDA;
+        }
         if (n && h_u32[3] != 0) {
             // some probes outgrew the first tier: CTA-per-probe tiers, then the compaction for real
             second = true;
@@ -317,9 +333,10 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             cudaEventRecord(h->ev[2], h->stream);
             if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "propagate kernels (CTA-per-probe tiers)")) return BBCP_ERR_CUDA;
         }
-        if (n) {
+        if (n && kevents) {
             cudaEventElapsedTime(&triage_ms, h->ev[3], h->ev[4]);
             cudaEventElapsedTime(&deep_ms, h->ev[4], h->ev[5]);
+            cudaEventElapsedTime(&compact_ms, second ? h->ev[6] : h->ev[5], h->ev[2]);
             if (second) {
                 cudaEventElapsedTime(&block_ms, h->ev[1], h->ev[6]);
                 cudaEventElapsedTime(&mid_ms, h->ev[1], h->ev[7]);
@@ -360,6 +377,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     bi.deep_ms = deep_ms;
     bi.block_ms = block_ms;
     bi.mid_ms = mid_ms;
+    bi.compact_ms = implied ? compact_ms : 0.f;
     bi.tier1_ms = triage_ms + deep_ms;
     bi.kernel_ms = triage_ms + deep_ms + block_ms;
     h->last_n = n;

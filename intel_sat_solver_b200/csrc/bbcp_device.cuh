@@ -62,6 +62,7 @@ struct BatchView {
     unsigned long long *tile_state;   // per-CTA segment sums of k_scan_gather
     uint32_t *tile_ticket;            // its grid barrier word (zero before the launch)
     unsigned long long *total;  // off[n]
+    unsigned long long *host_report;  // mapped pinned host copy of the counter block, written by k_scan_gather (or nullptr)
     unsigned long long *zero_next;    // the counter block of the NEXT launch sequence, zeroed by k_triage
     uint32_t zero_words;
     uint32_t opts;
@@ -79,7 +80,7 @@ struct LargeState {
     uint32_t *trail;   // [slabs][max_var + 1]
 };
 
-void launch_triage(const BatchView &b, const DbView &db, int blocks, cudaStream_t s);
+void launch_triage(const BatchView &b, const DbView &db, int sm_count, cudaStream_t s);
 void launch_small(const DbView &db, const BatchView &b, uint32_t trail_cap, int blocks, cudaStream_t s);
 void launch_mid(const DbView &db, const BatchView &b, uint32_t cap, int blocks, cudaStream_t s);
 void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s);

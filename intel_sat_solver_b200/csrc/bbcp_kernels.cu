@@ -485,97 +485,122 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
     __syncwarp();
 }
 
-// Triage: four consecutive items per thread (four independent litinfo loads in flight, flag / size written as
-// one 4-byte / 16-byte store). Decides every depth-1 item that needs no propagation (unmapped / assigned at
-// level 0 / no binary clause on the negation => the implied set is the literal itself, marked LEN_SELF so
-// that nothing but the size is written here) and queues the rest for k_deep.
-constexpr int TRIAGE_ITEMS = 4;
+// Triage: eight consecutive items per thread. Decides every depth-1 item that needs no propagation (unmapped /
+// assigned at level 0 / no binary clause on the negation => the implied set is the literal itself, marked
+// LEN_SELF so that nothing but the size is written here) and queues the rest for k_deep. The kernel is
+// instruction-issue-bound, not bandwidth-bound (6 bytes per item), so the per-item work is a table look-up:
+// the five litinfo bits index a 32-entry shared-memory table of (flag, self, counts-as-propagation); in
+// universe mode the eight litinfo bytes of a thread are two aligned 32-bit loads + funnel shifts, flags leave
+// as one 8-byte store and sizes as two 16-byte stores.
+constexpr int TRIAGE_ITEMS = 8;
+constexpr int TM_UNIVERSE = 0, TM_LIST = 1, TM_CUBES = 2;
+constexpr uint32_t TQ_SELF = 0x100u, TQ_REF = 0x200u, TQ_DEEP = 0x400u, TQ_NONE = 0x8000u;   // NONE: past the end of the batch
+
+template <int MODE>
 __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView b)
 {
     __shared__ unsigned int s_cnt[4];  // ok, skipped, props_ref
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
+    __shared__ uint16_t s_lut[32];
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
-    const bool want_len = (b.opts & OPT_IMPLIED) != 0;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 32) {
+        const uint32_t li = threadIdx.x;
+        uint32_t q;
+        if (!(li & LI_MAPPED)) q = FLAG_UNMAPPED;
+        else if (li & LI_FALSE_L0) q = FLAG_FALSE_L0;
+        else if (li & LI_TRUE_L0) q = FLAG_TRIVIAL_L0;
+        else if (prune && !(li & LI_HAS_BIN)) q = FLAG_OK | TQ_SELF | ((li & LI_NONEMPTY) ? TQ_REF : 0u);  // implies exactly itself
+        else q = 0xffu | TQ_DEEP;
+        s_lut[li] = (uint16_t)q;
+    }
     // housekeeping: the counter block of the NEXT launch sequence starts from zero (no memset nodes on the stream)
     if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < b.zero_words; i += 256) b.zero_next[i] = 0ull;
+    __syncthreads();
+    const uint32_t selflen = (b.opts & OPT_IMPLIED) ? (LEN_SELF | 1u) : 0u;
+    const uint32_t n = (uint32_t)b.n;   // run_batch refuses n >= 2^31
     uint32_t n_ok = 0, n_skip = 0, n_ref = 0;
-    const uint64_t stride = (uint64_t)gridDim.x * 256 * TRIAGE_ITEMS;
-    for (uint64_t wb = (uint64_t)blockIdx.x * 256 * TRIAGE_ITEMS; wb < b.n; wb += stride) {
-        const uint64_t base = wb + (uint64_t)threadIdx.x * TRIAGE_ITEMS;
-        int32_t lit[TRIAGE_ITEMS];
-        bool single[TRIAGE_ITEMS];
+    const uint32_t stride = gridDim.x * 256u * TRIAGE_ITEMS;
+    for (uint32_t wb = blockIdx.x * 256u * TRIAGE_ITEMS; wb < n; wb += stride) {
+        const uint32_t base = wb + threadIdx.x * TRIAGE_ITEMS;
+        if (base >= n) continue;   // (no barrier below)
+        const bool full = base + TRIAGE_ITEMS <= n;
+        uint32_t q[TRIAGE_ITEMS];
+        if (MODE == TM_UNIVERSE) {
+            // item i is internal literal first + i + 2: eight consecutive litinfo bytes
+            const uint64_t il0 = b.first + base + 2;
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(db.litinfo) + (il0 >> 2);
+            const uint32_t sh = (uint32_t)(il0 & 3u) * 8u;
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = sh ? __ldg(w + 2) : 0u;   // litinfo is padded by 16 bytes
+            const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
 #pragma unroll
-        for (int k = 0; k < TRIAGE_ITEMS; ++k) {
-            const uint64_t item = base + k;
-            lit[k] = 0;
-            single[k] = false;
-            if (item < b.n) {
-                if (b.cube_off) {
-                    const uint64_t o = b.cube_off[item];
-                    if (b.cube_off[item + 1] - o == 1) { lit[k] = b.cube_lits[o]; single[k] = true; }
-                } else if (b.cube_lits) {
-                    lit[k] = b.cube_lits[item];
-                    single[k] = true;
-                } else {
-                    const uint64_t idx = b.first + item;
-                    const int32_t pv = (int32_t)(idx / 2 + 1);
-                    lit[k] = (idx & 1) ? -pv : pv;
-                    single[k] = true;
+            for (int k = 0; k < TRIAGE_ITEMS; ++k) {
+                const uint32_t li = ((k < 4 ? lo : hi) >> ((k & 3) * 8)) & 31u;
+                q[k] = (full || base + k < n) ? s_lut[li] : TQ_NONE;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < TRIAGE_ITEMS; ++k) {
+                const uint32_t item = base + k;
+                q[k] = TQ_NONE;   // past the end
+                if (full || item < n) {
+                    int32_t lit;
+                    bool single = true;
+                    if (MODE == TM_LIST) lit = b.cube_lits[item];
+                    else {
+                        const uint64_t o = b.cube_off[item];
+                        single = b.cube_off[item + 1] - o == 1;
+                        lit = single ? b.cube_lits[o] : 0;
+                    }
+                    if (lit != 0) {
+                        const uint32_t v = (uint32_t)(lit < 0 ? -lit : lit);
+                        q[k] = s_lut[v <= (uint32_t)db.max_var ? (db.litinfo[2u * v + (lit < 0)] & 31u) : 0u];
+                    } else q[k] = (MODE == TM_LIST) ? FLAG_UNMAPPED : (0xffu | TQ_DEEP);   // a 0 in a probe list names no variable
                 }
             }
         }
-        uint8_t li[TRIAGE_ITEMS];
+        uint32_t deepmask = 0;
 #pragma unroll
         for (int k = 0; k < TRIAGE_ITEMS; ++k) {
-            const uint32_t v = (uint32_t)(lit[k] < 0 ? -lit[k] : lit[k]);
-            li[k] = (lit[k] != 0 && v <= (uint32_t)db.max_var) ? db.litinfo[2u * v + (lit[k] < 0)] : (uint8_t)0;
+            const uint32_t x = q[k];
+            n_ok += (x >> 8) & 1u;
+            n_ref += (x >> 9) & 1u;
+            n_skip += (x & 0xffu) >= FLAG_TRIVIAL_L0 && (x & 0xffu) <= FLAG_UNMAPPED;
+            deepmask |= ((x >> 10) & 1u) << k;
         }
-        uint8_t flag[TRIAGE_ITEMS];
-        uint32_t len[TRIAGE_ITEMS];
-        bool deep[TRIAGE_ITEMS];
-#pragma unroll
-        for (int k = 0; k < TRIAGE_ITEMS; ++k) {
-            uint8_t f = 0xff;
-            bool self = false;
-            if (single[k] && lit[k] == 0 && !b.cube_off) f = FLAG_UNMAPPED;   // a 0 in a probe list names no variable
-            if (lit[k] != 0) {
-                if (!(li[k] & LI_MAPPED)) f = FLAG_UNMAPPED;
-                else if (li[k] & LI_FALSE_L0) f = FLAG_FALSE_L0;
-                else if (li[k] & LI_TRUE_L0) f = FLAG_TRIVIAL_L0;
-                else if (prune && !(li[k] & LI_HAS_BIN)) {
-                    f = FLAG_OK;   // no binary clause on the negation: the probe implies exactly itself
-                    self = true;
-                    n_ref += (li[k] & LI_NONEMPTY) != 0;
-                }
-            }
-            const bool valid = base + k < b.n;
-            deep[k] = valid && f == 0xff;
-            flag[k] = f;
-            len[k] = self && want_len ? (LEN_SELF | 1u) : 0u;
-            if (valid && f != 0xff) { n_ok += self; n_skip += !self; }
-        }
-        if (base + TRIAGE_ITEMS <= b.n) {
-            // deep items get their flag / size from the propagate kernels; writing a placeholder first is harmless
-            *reinterpret_cast<uchar4 *>(b.flag + base) = make_uchar4(flag[0], flag[1], flag[2], flag[3]);
-            *reinterpret_cast<uint4 *>(b.len + base) = make_uint4(len[0], len[1], len[2], len[3]);
+        if (full) {
+            // deep items get their flag / size from the propagate kernels; the placeholder written here is overwritten
+            *reinterpret_cast<uint2 *>(b.flag + base) =
+                make_uint2((q[0] & 0xffu) | ((q[1] & 0xffu) << 8) | ((q[2] & 0xffu) << 16) | (q[3] << 24),
+                           (q[4] & 0xffu) | ((q[5] & 0xffu) << 8) | ((q[6] & 0xffu) << 16) | (q[7] << 24));
+            uint4 *lp = reinterpret_cast<uint4 *>(b.len + base);
+            lp[0] = make_uint4((q[0] & TQ_SELF) ? selflen : 0u, (q[1] & TQ_SELF) ? selflen : 0u, (q[2] & TQ_SELF) ? selflen : 0u, (q[3] & TQ_SELF) ? selflen : 0u);
+            lp[1] = make_uint4((q[4] & TQ_SELF) ? selflen : 0u, (q[5] & TQ_SELF) ? selflen : 0u, (q[6] & TQ_SELF) ? selflen : 0u, (q[7] & TQ_SELF) ? selflen : 0u);
         } else {
 #pragma unroll
             for (int k = 0; k < TRIAGE_ITEMS; ++k)
-                if (base + k < b.n) { b.flag[base + k] = flag[k]; b.len[base + k] = len[k]; }
+                if (base + k < n) { b.flag[base + k] = (uint8_t)q[k]; b.len[base + k] = (q[k] & TQ_SELF) ? selflen : 0u; }
         }
-        unsigned dm[TRIAGE_ITEMS];
-        uint32_t total = 0;
+        // queue the deep items (the active lanes of the warp reserve one run of the list together)
+        const unsigned act = __activemask();
+        if (__any_sync(act, deepmask != 0)) {
+            const uint32_t cnt = __popc(deepmask);
+            uint32_t incl = cnt;
 #pragma unroll
-        for (int k = 0; k < TRIAGE_ITEMS; ++k) { dm[k] = __ballot_sync(FULL, deep[k]); total += __popc(dm[k]); }
-        if (total) {
-            unsigned pos = 0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(act, incl, d);
+                if (lane_id() >= d) incl += t;
+            }
+            // lanes are active from 0 upwards (base grows with the lane), so the last active lane holds the total
+            const int last = 31 - __clz(act);
+            const uint32_t total = __shfl_sync(act, incl, last);
+            uint32_t pos = 0;
             if (lane_id() == 0) pos = atomicAdd(b.deep_count, total);
-            pos = __shfl_sync(FULL, pos, 0);
-#pragma unroll
-            for (int k = 0; k < TRIAGE_ITEMS; ++k) {
-                if (deep[k]) b.deep_list[pos + __popc(dm[k] & lanemask_lt())] = (uint32_t)(base + k);
-                pos += __popc(dm[k]);
+            pos = __shfl_sync(act, pos, 0) + incl - cnt;
+            uint32_t m = deepmask;
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                b.deep_list[pos++] = base + k;
             }
         }
     }
@@ -907,6 +932,7 @@ __device__ __forceinline__ int32_t item_self_lit(const BatchView &b, uint64_t it
 // (from L2 now), 2048 items per step in a warp-striped arrangement -- lane l of warp w owns items
 // w*256 + j*32 + l, j = 0..7, so every load and store of a warp is one contiguous 128/256-byte run -- turns
 // sizes into offsets with warp shuffles, writes the offsets and moves the literals.
+template <bool OFF32>
 __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, const int pass, const uint64_t seg)
 {
     // first pass of a batch: if some probes still wait for the CTA-per-probe tiers the sizes are not final
@@ -918,13 +944,22 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
     __shared__ unsigned long long s_bigdst[SG_TILE];
     const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const uint64_t n = b.n;
-    const bool off32 = (b.opts & OPT_OFF32) != 0;
+    constexpr bool off32 = OFF32;
     int32_t *__restrict__ dst = b.impl;
     const uint64_t lo = min((unsigned long long)blockIdx.x * seg, (unsigned long long)n), hi = min((unsigned long long)(lo + seg), (unsigned long long)n);
 
     // ---- phase 1: segment sum
     unsigned long long sum = 0;
-    for (uint64_t i = lo + tid; i < hi; i += SG_THREADS) sum += b.len[i] & 0x7fffffffu;
+    {
+        // lo is a multiple of 2048 and the buffer is 256-byte aligned: 16-byte loads, four sizes each
+        const uint32_t cnt = (uint32_t)(hi - lo);
+        const uint4 *p4 = reinterpret_cast<const uint4 *>(b.len + lo);
+        for (uint32_t i = tid; i < cnt / 4; i += SG_THREADS) {
+            const uint4 v = p4[i];
+            sum += (unsigned long long)(v.x & 0x7fffffffu) + (v.y & 0x7fffffffu) + (v.z & 0x7fffffffu) + (v.w & 0x7fffffffu);
+        }
+        for (uint32_t i = (cnt & ~3u) + tid; i < cnt; i += SG_THREADS) sum += b.len[lo + i] & 0x7fffffffu;
+    }
 #pragma unroll
     for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(FULL, sum, d);
     if (lane == 0) s_red[warp] = sum;
@@ -961,23 +996,51 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
 
     for (uint64_t cbase = lo; cbase < hi; cbase += SG_TILE) {
         if (tid == 0) s_nbig = 0;
-        const uint64_t wbase = cbase + (uint64_t)warp * (32 * SG_ITEMS);
+        const uint64_t wbase = cbase + (uint64_t)warp * (32 * SG_ITEMS) + lane;
+        const uint32_t nvalid = (uint32_t)min((unsigned long long)(32 * SG_ITEMS), (unsigned long long)(hi > wbase - lane ? hi - (wbase - lane) : 0));
         uint32_t len[SG_ITEMS];
+#pragma unroll
+        for (int j = 0; j < SG_ITEMS; ++j) len[j] = (uint32_t)(j * 32 + lane) < nvalid ? b.len[wbase + j * 32] : 0u;
+        // sizes -> offsets inside the warp's 256 items. 32-bit shuffles unless some set of the step is huge
+        // (then the row sums could leave 32 bits)
+        uint32_t mx = 0;
+#pragma unroll
+        for (int j = 0; j < SG_ITEMS; ++j) mx = max(mx, len[j] & 0x7fffffffu);
         unsigned long long o[SG_ITEMS];
         unsigned long long rowbase = 0;
+        if (!__any_sync(FULL, mx >= (1u << 20))) {
+            uint32_t rb = 0;
 #pragma unroll
-        for (int j = 0; j < SG_ITEMS; ++j) {
-            const uint64_t item = wbase + j * 32 + lane;
-            len[j] = item < hi ? b.len[item] : 0u;
-            const unsigned long long v = len[j] & 0x7fffffffu;
-            unsigned long long incl = v;
+            for (int j = 0; j < SG_ITEMS; ++j) {
+                const uint32_t v = len[j] & 0x7fffffffu;
+                if (__all_sync(FULL, v == 1u)) {   // a row of one-literal sets (self-implied probes): no scan needed
+                    o[j] = rb + lane;
+                    rb += 32;
+                    continue;
+                }
+                uint32_t incl = v;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long t = __shfl_up_sync(FULL, incl, d);
-                if (lane >= d) incl += t;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                o[j] = rb + incl - v;
+                rb += __shfl_sync(FULL, incl, 31);
             }
-            o[j] = rowbase + incl - v;
-            rowbase += __shfl_sync(FULL, incl, 31);
+            rowbase = rb;
+        } else {
+#pragma unroll
+            for (int j = 0; j < SG_ITEMS; ++j) {
+                const unsigned long long v = len[j] & 0x7fffffffu;
+                unsigned long long incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned long long t = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                o[j] = rowbase + incl - v;
+                rowbase += __shfl_sync(FULL, incl, 31);
+            }
         }
         if (lane == 0) s_warp[warp] = rowbase;
         __syncthreads();
@@ -987,22 +1050,22 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
         const unsigned long long wrun = run + before;
 #pragma unroll
         for (int j = 0; j < SG_ITEMS; ++j) {
-            const uint64_t item = wbase + j * 32 + lane;
             o[j] += wrun;
-            if (item < hi) { if (off32) ((uint32_t *)b.off)[item] = (uint32_t)o[j]; else ((uint64_t *)b.off)[item] = o[j]; }
+            if ((uint32_t)(j * 32 + lane) < nvalid) { if (OFF32) ((uint32_t *)b.off)[wbase + j * 32] = (uint32_t)o[j]; else ((uint64_t *)b.off)[wbase + j * 32] = o[j]; }
         }
         run += agg;
         if (cbase + SG_TILE >= hi && hi == n && tid == 0) {   // the step that holds the last item: off[n], total
-            if (off32) ((uint32_t *)b.off)[n] = (uint32_t)run; else ((uint64_t *)b.off)[n] = run;
+            if (OFF32) ((uint32_t *)b.off)[n] = (uint32_t)run; else ((uint64_t *)b.off)[n] = run;
             *b.total = run;
         }
         // literals
 #pragma unroll
         for (int j = 0; j < SG_ITEMS; ++j) {
-            const uint64_t item = wbase + j * 32 + lane;
+            const uint64_t item = wbase + j * 32;
             uint32_t l = len[j];
-            uint64_t src = 0;
             if (l & LEN_SELF) { dst[o[j]] = item_self_lit(b, item); l = 0; }
+            if (!__any_sync(FULL, l != 0)) continue;   // nothing stored for this row (the common case in a triage-only batch)
+            uint64_t src = 0;
             if (l) src = b.raw_off[item];
             if (l && l <= GATHER_WARP) {
                 for (uint32_t i = 0; i < l; ++i) dst[o[j] + i] = b.out_lits[src + i];
@@ -1038,7 +1101,22 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
             const uint64_t ss = b.raw_off[item], dd = s_bigdst[e];
             for (uint32_t i = tid; i < l; i += SG_THREADS) dst[dd + i] = b.out_lits[ss + i];
         }
+        if (nbig) __syncthreads();
+    }
+    // the last CTA to finish copies the counter block of this launch sequence into mapped host memory: the host
+    // reads it after the stream synchronisation it does anyway (no copy-engine round trip)
+    if (b.host_report) {
         __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            s_pos = atomicAdd(b.tile_ticket + 1, 1u);
+        }
+        __syncthreads();
+        if (s_pos == gridDim.x - 1) {
+            __threadfence();
+            for (uint32_t i = tid; i < b.zero_words; i += SG_THREADS) b.host_report[i] = ((volatile unsigned long long *)b.counters)[i];
+            __threadfence_system();
+        }
     }
 }
 
@@ -1078,9 +1156,12 @@ int small_blocks_per_sm(uint32_t cap)
     return nb;
 }
 
-void launch_triage(const BatchView &b, const DbView &db, int blocks, cudaStream_t s)
+void launch_triage(const BatchView &b, const DbView &db, int sm_count, cudaStream_t s)
 {
-    k_triage<<<blocks, 256, 0, s>>>(db, b);
+    const int blocks = (int)std::min<uint64_t>((b.n + 256 * TRIAGE_ITEMS - 1) / (256 * TRIAGE_ITEMS), (uint64_t)sm_count * 8);
+    if (b.cube_off) k_triage<TM_CUBES><<<blocks, 256, 0, s>>>(db, b);
+    else if (b.cube_lits) k_triage<TM_LIST><<<blocks, 256, 0, s>>>(db, b);
+    else k_triage<TM_UNIVERSE><<<blocks, 256, 0, s>>>(db, b);
 }
 
 void launch_small(const DbView &db, const BatchView &b, uint32_t cap, int blocks, cudaStream_t s)
@@ -1115,7 +1196,7 @@ void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int 
 int scan_gather_max_blocks(int sm_count)
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_gather, SG_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_gather<false>, SG_THREADS, 0);
     return std::max(1, std::min(nb, 4)) * sm_count;
 }
 
@@ -1129,7 +1210,8 @@ bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant
     BatchView bv = b;
     int p = pass;
     void *args[] = {&bv, &p, &seg};
-    if (cudaLaunchCooperativeKernel((const void *)k_scan_gather, dim3((unsigned)blocks), dim3(SG_THREADS), args, 0, s) != cudaSuccess) return false;
+    const void *fn = (b.opts & OPT_OFF32) ? (const void *)k_scan_gather<true> : (const void *)k_scan_gather<false>;
+    if (cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(SG_THREADS), args, 0, s) != cudaSuccess) return false;
     if (giant_sets_possible) k_gather_long<<<max_blocks, 256, 0, s>>>(b);
     return true;
 }
