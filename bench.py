@@ -196,15 +196,12 @@ def ours_arm(args, rank, local_rank, world):
     opts_timed = Opts(1 | 8, 0, 0, 0, 0)   # + BBCP_OPT_KERNEL_TIMES: per-kernel CUDA events (separate pass)
     info = BatchInfo()
     if world > 1:
-        failed_t = torch.as_tensor(DevArr(L.bbcp_device_failed_bitmap(h), words_total), device=dev)
-        unit_t = torch.as_tensor(DevArr(L.bbcp_device_unit_bitmap(h), words_total), device=dev)
+        sharding.peer_attach(eng, rank, world)   # CUDA IPC handles exchanged once; the merge itself is the engine's kernel
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    merged = {}
 
     def device_step():
         """all inputs resident: kernels + compaction (+ on-stream all-gather of the bitmap slices)"""
@@ -212,13 +209,8 @@ def ours_arm(args, rank, local_rank, world):
         assert rc == 0, eng.GetStatusExplanation()
         ms = info.total_ms
         if world > 1:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            merged["failed"] = sharding.allgather_bitmap(failed_t, shard)
-            merged["unit"] = sharding.allgather_bitmap(unit_t, shard)
-            e1.record()
-            e1.synchronize()
-            ms += e0.elapsed_time(e1)
+            # all-gather of the failed/unit bitmap slices over NVLink peer memory, on the engine's stream
+            ms += sharding.merge_bitmaps(eng, shard)
         return ms
 
     clocks = ClockSampler(local_rank)

@@ -168,6 +168,21 @@ void *bbcp_stream(bbcp_handle *h);
 /* blocks until the handle's stream is idle */
 int bbcp_sync(bbcp_handle *h);
 
+/* ---- multi-GPU: one handle per GPU (one process per GPU), the database replicated, the probe universe cut into
+ *      contiguous ranges aligned to bitmap words. bbcp_merge_bitmaps is the all-gather of the failed-literal and
+ *      unit bitmap slices, done by ONE kernel over NVLink peer memory: every rank stores its slice [word_lo,
+ *      word_hi) of both bitmaps straight into every peer's bitmaps (CUDA-IPC-mapped), raises an arrival flag in
+ *      every peer, and waits for the flags of all peers. Set-up: every rank calls bbcp_peer_export after
+ *      bbcp_finalize, the BBCP_PEER_HANDLE_BYTES blobs are exchanged by the host program (e.g. a
+ *      torch.distributed / MPI all-gather), every rank calls bbcp_peer_attach with all of them in rank order.
+ *      A re-finalize that changes the variable range needs bbcp_peer_detach + a new exchange. Every rank must
+ *      call bbcp_merge_bitmaps the same number of times. *ms (optional) = device time incl. the wait. */
+#define BBCP_PEER_HANDLE_BYTES 128
+int bbcp_peer_export(bbcp_handle *h, void *out /* BBCP_PEER_HANDLE_BYTES */);
+int bbcp_peer_attach(bbcp_handle *h, int rank, int world, const void *all /* world * BBCP_PEER_HANDLE_BYTES */);
+int bbcp_peer_detach(bbcp_handle *h);
+int bbcp_merge_bitmaps(bbcp_handle *h, uint64_t word_lo, uint64_t word_hi, float *ms);
+
 /* ---- single-cube convenience path with the Topor / IPASIR conventions:
  *      ipasir_assume / ipasir_solve / ipasir_val (ToporIpasir.cc:27-68), CTopor::Solve(assumps)
  *      (Topor.hpp:48), GetLitValue (Topor.hpp:80), GetLitDecLevel (Topor.hpp:88), Backtrack (Topor.hpp:68).

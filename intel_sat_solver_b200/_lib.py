@@ -66,6 +66,10 @@ _SIGS = {
     "bbcp_device_impl_lits": (C.c_void_p, [C.c_void_p]),
     "bbcp_stream": (C.c_void_p, [C.c_void_p]),
     "bbcp_sync": (C.c_int, [C.c_void_p]),
+    "bbcp_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bbcp_peer_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "bbcp_peer_detach": (C.c_int, [C.c_void_p]),
+    "bbcp_merge_bitmaps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_float)]),
     "bbcp_assume": (C.c_int, [C.c_void_p, C.c_int32]),
     "bbcp_solve": (C.c_int, [C.c_void_p]),
     "bbcp_val": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -74,6 +78,7 @@ _SIGS = {
     "bbcp_propagations": (C.c_uint64, [C.c_void_p]),
 }
 
+PEER_HANDLE_BYTES = 128
 _LIB = None
 
 

@@ -41,6 +41,7 @@ struct DevBuf {
 
 // misc device words (u64): [0..C_N) counters, cursor, six u32 {ticket[3], mid_count, big_count, deep_count},
 // total (a copy of off[n])
+constexpr int MERGE_CTRL_WORDS = 128;   // after the two bitmaps: [0..63] arrival flag per rank, [64] push-done counter, [65] error
 constexpr int MISC_CURSOR = C_N;
 constexpr int MISC_U32 = C_N + 1;       // as u32 index from 2*MISC_U32: +0..2 tickets, +3 mid_count, +4 big_count, +5 deep_count
                                         // +6 chunk_count of the giant-set gather, +7 grid barrier of the scan, +8 its finished-CTA count
@@ -63,7 +64,18 @@ struct bbcp_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
-    DevBuf d_hdr, d_slots, d_arena, d_litinfo, d_failed, d_unit;
+    DevBuf d_hdr, d_slots, d_arena, d_litinfo;
+    // ONE allocation shared with peer GPUs (CUDA IPC): [failed: bm_stride words][unit: bm_stride words]
+    // [arrival flags: one u32 per rank][push-done counter], see bbcp_merge_bitmaps
+    DevBuf d_bitmaps;
+    uint64_t bm_stride = 0;
+    uint32_t *failed_p() const { return d_bitmaps.as<uint32_t>(); }
+    uint32_t *unit_p() const { return d_bitmaps.as<uint32_t>() + bm_stride; }
+    int peer_rank = -1, peer_world = 0;
+    std::vector<void *> peer_base;          // mapped base of every rank's d_bitmaps (own entry = own pointer)
+    DevBuf d_peer_tab;                      // the same table on the device
+    uint32_t merge_epoch = 0;
+    cudaEvent_t ev_merge[2] = {nullptr, nullptr};
     uint64_t bitmap_words = 0;
     uint64_t device_db_bytes = 0;
 
@@ -155,9 +167,18 @@ bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo)
     if (!upload(h, h->d_arena, db.arena.data(), db.arena.size() * 4)) return false;
     if (!upload(h, h->d_litinfo, litinfo.data(), litinfo.size())) return false;
     h->bitmap_words = (2 * ((uint64_t)db.max_var + 1) + 31) / 32;
-    if (!h->d_failed.reserve(h->bitmap_words * 4) || !h->d_unit.reserve(h->bitmap_words * 4)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (bitmaps)"); return false; }
-    cudaMemsetAsync(h->d_failed.p, 0, h->bitmap_words * 4, h->stream);
-    cudaMemsetAsync(h->d_unit.p, 0, h->bitmap_words * 4, h->stream);
+    const uint64_t stride = (h->bitmap_words + 3) & ~3ull;
+    if (stride != h->bm_stride || !h->d_bitmaps.p) {
+        if (h->peer_world) { h->fail(BBCP_ERR_STATE, "the bitmap size changed while peers are attached: bbcp_peer_detach first"); return false; }
+        h->d_bitmaps.release();
+        // exact size, own cudaMalloc: the IPC handle of this allocation is what peers map
+        if (cudaMalloc(&h->d_bitmaps.p, (2 * stride + MERGE_CTRL_WORDS) * 4) != cudaSuccess) { cudaGetLastError(); h->d_bitmaps.p = nullptr; h->fail(BBCP_ERR_ALLOC, "device allocation failed (bitmaps)"); return false; }
+        h->d_bitmaps.bytes = (2 * stride + MERGE_CTRL_WORDS) * 4;
+        h->bm_stride = stride;
+        cudaMemsetAsync(h->d_bitmaps.p, 0, h->d_bitmaps.bytes, h->stream);
+    } else {
+        cudaMemsetAsync(h->d_bitmaps.p, 0, 2 * stride * 4, h->stream);   // keep the arrival flags: they are monotonic epochs
+    }
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "upload sync")) return false;
     h->device_db_bytes = db.hdr.size() * sizeof(RowHdr) + db.slots.size() * sizeof(Slot) + db.arena.size() * 4 + litinfo.size() + 2 * h->bitmap_words * 4;
     return true;
@@ -242,8 +263,8 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.flag = h->d_flag.as<uint8_t>();
     b.raw_off = h->d_raw_off.as<uint64_t>();
     b.len = h->d_len.as<uint32_t>();
-    b.failed = h->d_failed.as<uint32_t>();
-    b.unit = h->d_unit.as<uint32_t>();
+    b.failed = h->failed_p();
+    b.unit = h->unit_p();
     b.mid_list = h->d_overflow.as<uint32_t>();
     b.big_list = h->d_big.as<uint32_t>();
     b.deep_list = h->d_deep.as<uint32_t>();
@@ -414,7 +435,9 @@ void bbcp_release(bbcp_handle *h)
     if (h->device_ready) {
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
-        for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_failed, &h->d_unit, &h->d_flag, &h->d_raw_off, &h->d_len,
+        bbcp_peer_detach(h);
+        for (auto &e : h->ev_merge) if (e) cudaEventDestroy(e);
+        for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_bitmaps, &h->d_peer_tab, &h->d_flag, &h->d_raw_off, &h->d_len,
                           &h->d_out, &h->d_off, &h->d_impl, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_big, &h->d_deep, &h->d_chunks, &h->d_misc, &h->d_lbits,
                           &h->d_ltrail, &h->d_tiles})
             b->release();
@@ -685,8 +708,8 @@ int bbcp_fetch_bitmaps(bbcp_handle *h, uint32_t *failed, uint32_t *unit)
     int rc = need_final(h);
     if (rc) return rc;
     cudaSetDevice(h->device);
-    if (failed) cudaMemcpyAsync(failed, h->d_failed.p, h->bitmap_words * 4, cudaMemcpyDeviceToHost, h->stream);
-    if (unit) cudaMemcpyAsync(unit, h->d_unit.p, h->bitmap_words * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (failed) cudaMemcpyAsync(failed, h->failed_p(), h->bitmap_words * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (unit) cudaMemcpyAsync(unit, h->unit_p(), h->bitmap_words * 4, cudaMemcpyDeviceToHost, h->stream);
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "fetch bitmaps") ? BBCP_OK : BBCP_ERR_CUDA;
 }
 
@@ -695,13 +718,12 @@ int bbcp_clear_bitmaps(bbcp_handle *h)
     int rc = need_final(h);
     if (rc) return rc;
     cudaSetDevice(h->device);
-    cudaMemsetAsync(h->d_failed.p, 0, h->bitmap_words * 4, h->stream);
-    cudaMemsetAsync(h->d_unit.p, 0, h->bitmap_words * 4, h->stream);
+    cudaMemsetAsync(h->d_bitmaps.p, 0, 2 * h->bm_stride * 4, h->stream);
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "clear bitmaps") ? BBCP_OK : BBCP_ERR_CUDA;
 }
 
-void *bbcp_device_failed_bitmap(bbcp_handle *h) { return h ? h->d_failed.p : nullptr; }
-void *bbcp_device_unit_bitmap(bbcp_handle *h) { return h ? h->d_unit.p : nullptr; }
+void *bbcp_device_failed_bitmap(bbcp_handle *h) { return h ? h->failed_p() : nullptr; }
+void *bbcp_device_unit_bitmap(bbcp_handle *h) { return h ? h->unit_p() : nullptr; }
 void *bbcp_device_flags(bbcp_handle *h) { return h && h->have_batch ? h->d_flag.p : nullptr; }
 void *bbcp_device_impl_off(bbcp_handle *h) { return h && h->have_batch ? h->d_off.p : nullptr; }
 void *bbcp_device_impl_lits(bbcp_handle *h) { return h && h->have_batch ? h->d_impl.p : nullptr; }
@@ -711,6 +733,83 @@ int bbcp_sync(bbcp_handle *h)
     if (!h || !h->device_ready) return BBCP_ERR_STATE;
     cudaSetDevice(h->device);
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "sync") ? BBCP_OK : BBCP_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------- multi-GPU merge over NVLink peer memory
+int bbcp_peer_export(bbcp_handle *h, void *out)
+{
+    int rc = need_final(h);
+    if (rc) return rc;
+    if (!out) return h->fail(BBCP_ERR_ARG, "bbcp_peer_export: null buffer");
+    cudaSetDevice(h->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) <= BBCP_PEER_HANDLE_BYTES - 16, "IPC handle size");
+    memset(out, 0, BBCP_PEER_HANDLE_BYTES);
+    cudaIpcMemHandle_t ipc;
+    if (!h->cuda_ok(cudaIpcGetMemHandle(&ipc, h->d_bitmaps.p), "cudaIpcGetMemHandle")) return BBCP_ERR_CUDA;
+    memcpy(out, &ipc, sizeof(ipc));
+    memcpy(static_cast<char *>(out) + BBCP_PEER_HANDLE_BYTES - 16, &h->bm_stride, 8);
+    return BBCP_OK;
+}
+
+int bbcp_peer_detach(bbcp_handle *h)
+{
+    if (!h) return BBCP_ERR_ARG;
+    if (h->device_ready) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+    for (int r = 0; r < (int)h->peer_base.size(); ++r)
+        if (r != h->peer_rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    cudaGetLastError();
+    h->peer_base.clear();
+    h->peer_rank = -1;
+    h->peer_world = 0;
+    return BBCP_OK;
+}
+
+int bbcp_peer_attach(bbcp_handle *h, int rank, int world, const void *all)
+{
+    int rc = need_final(h);
+    if (rc) return rc;
+    if (!all || world < 1 || world > 64 || rank < 0 || rank >= world) return h->fail(BBCP_ERR_ARG, "bbcp_peer_attach: bad rank / world (at most 64 ranks)");
+    cudaSetDevice(h->device);
+    bbcp_peer_detach(h);
+    h->peer_base.assign(world, nullptr);
+    for (int r = 0; r < world; ++r) {
+        const char *e = static_cast<const char *>(all) + (size_t)r * BBCP_PEER_HANDLE_BYTES;
+        uint64_t stride = 0;
+        memcpy(&stride, e + BBCP_PEER_HANDLE_BYTES - 16, 8);
+        if (stride != h->bm_stride) { bbcp_peer_detach(h); return h->fail(BBCP_ERR_ARG, "bbcp_peer_attach: rank " + std::to_string(r) + " holds a different database (bitmap size differs)"); }
+        if (r == rank) { h->peer_base[r] = h->d_bitmaps.p; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, e, sizeof(ipc));
+        void *p = nullptr;
+        if (!h->cuda_ok(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (peer bitmaps)")) { h->peer_rank = rank; bbcp_peer_detach(h); return BBCP_ERR_CUDA; }
+        h->peer_base[r] = p;
+    }
+    h->peer_rank = rank;
+    h->peer_world = world;
+    if (!h->d_peer_tab.reserve(64 * sizeof(void *))) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (peer table)");
+    cudaMemcpyAsync(h->d_peer_tab.p, h->peer_base.data(), world * sizeof(void *), cudaMemcpyHostToDevice, h->stream);
+    for (auto &e : h->ev_merge) if (!e && !h->cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return BBCP_ERR_CUDA;
+    return h->cuda_ok(cudaStreamSynchronize(h->stream), "peer table upload") ? BBCP_OK : BBCP_ERR_CUDA;
+}
+
+int bbcp_merge_bitmaps(bbcp_handle *h, uint64_t word_lo, uint64_t word_hi, float *ms)
+{
+    int rc = need_final(h);
+    if (rc) return rc;
+    if (h->peer_world < 1) return h->fail(BBCP_ERR_STATE, "bbcp_merge_bitmaps: no peers attached");
+    if (word_lo > word_hi || word_hi > h->bitmap_words) return h->fail(BBCP_ERR_ARG, "bbcp_merge_bitmaps: slice outside the bitmap");
+    cudaSetDevice(h->device);
+    ++h->merge_epoch;
+    cudaEventRecord(h->ev_merge[0], h->stream);
+    launch_merge(static_cast<uint32_t *const *>(h->d_peer_tab.p), h->peer_rank, h->peer_world, h->bm_stride, word_lo, word_hi, h->merge_epoch,
+                 h->sm_count, h->stream);
+    cudaEventRecord(h->ev_merge[1], h->stream);
+    if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "bitmap merge")) return BBCP_ERR_CUDA;
+    uint32_t err = 0;
+    cudaMemcpy(&err, h->d_bitmaps.as<uint32_t>() + 2 * h->bm_stride + 65, 4, cudaMemcpyDeviceToHost);
+    if (err) return h->fail(BBCP_ERR_CUDA, "bbcp_merge_bitmaps: a peer did not arrive within the time-out");
+    if (ms) cudaEventElapsedTime(ms, h->ev_merge[0], h->ev_merge[1]);
+    return BBCP_OK;
 }
 
 int bbcp_assume(bbcp_handle *h, int32_t lit)

@@ -88,6 +88,8 @@ size_t mid_smem_bytes(uint32_t trail_cap);
 int mid_blocks_per_sm(uint32_t trail_cap);
 bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, cudaStream_t s);
 int scan_gather_max_blocks(int sm_count);
+void launch_merge(uint32_t *const *peer_base, int rank, int world, uint64_t stride, uint64_t lo, uint64_t hi, uint32_t epoch, int sm_count,
+                  cudaStream_t s);
 constexpr uint32_t SG_TILE = 2048;   // items per scan tile
 size_t small_smem_bytes(uint32_t trail_cap);
 int small_blocks_per_sm(uint32_t trail_cap);

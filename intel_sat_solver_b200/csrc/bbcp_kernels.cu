@@ -1138,6 +1138,54 @@ __global__ void __launch_bounds__(256) k_gather_long(const BatchView b)
     }
 }
 
+// ---------------------------------------------------------------- multi-GPU merge of the bitmap slices
+// All-gather over NVLink peer memory in one kernel (one process per GPU, every rank runs this on its own GPU at
+// the same point of its stream). peer_base[r] = rank r's [failed | unit | control] block, mapped through CUDA
+// IPC. Every rank STORES its own slice [lo, hi) of both bitmaps into every peer's block (remote writes, no
+// reads over the link), the last CTA to finish raises this rank's arrival flag in every peer with the epoch of
+// this merge and then waits until every peer's flag in the local control words has reached the epoch.
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_merge(uint32_t *const *peer_base, const int rank, const int world, const uint64_t stride,
+                                               const uint64_t lo, const uint64_t hi, const uint32_t epoch)
+{
+    uint32_t *mine = peer_base[rank];
+    uint32_t *ctrl = mine + 2 * stride;
+    const uint64_t cnt = hi - lo;
+    if (cnt && world > 1) {
+        const uint64_t per_peer = 2 * cnt, total = per_peer * (uint64_t)(world - 1);
+        for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (uint64_t)gridDim.x * 256) {
+            const int pi = (int)(i / per_peer);
+            const uint64_t r = i - (uint64_t)pi * per_peer;
+            const uint64_t which = r >= cnt ? 1 : 0, w = lo + r - which * cnt;
+            const int p = pi + (pi >= rank);
+            peer_base[p][which * stride + w] = mine[which * stride + w];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (atomicAdd(&ctrl[64], 1u) != gridDim.x - 1) return;
+    ctrl[64] = 0;   // for the next merge
+    __threadfence_system();
+    for (int p = 0; p < world; ++p)
+        if (p != rank) *(volatile uint32_t *)(peer_base[p] + 2 * stride + rank) = epoch;
+    const unsigned long long t0 = global_ns();
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        while ((int32_t)(*(volatile uint32_t *)&ctrl[p] - epoch) < 0) {
+            if (global_ns() - t0 > 20000000000ull) { ctrl[65] = 1; return; }   // 20 s: a peer died; reported by the host call
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
 }  // namespace
 
 size_t small_smem_bytes(uint32_t cap)
@@ -1214,6 +1262,14 @@ bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant
     if (cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(SG_THREADS), args, 0, s) != cudaSuccess) return false;
     if (giant_sets_possible) k_gather_long<<<max_blocks, 256, 0, s>>>(b);
     return true;
+}
+
+void launch_merge(uint32_t *const *peer_base, int rank, int world, uint64_t stride, uint64_t lo, uint64_t hi, uint32_t epoch, int sm_count,
+                  cudaStream_t s)
+{
+    const uint64_t total = 2 * (hi - lo) * (uint64_t)std::max(world - 1, 0);
+    const int blocks = (int)std::min<uint64_t>(std::max<uint64_t>((total + 1023) / 1024, 1), (uint64_t)sm_count * 2);
+    k_merge<<<blocks, 256, 0, s>>>(peer_base, rank, world, stride, lo, hi, epoch);
 }
 
 }  // namespace bbcp

@@ -5,6 +5,14 @@ aligned to 32-bit words of the failed-literal bitmap (bit index = internal liter
 that each rank owns a whole slice of bitmap words and ONE all-gather of the slices (NCCL over NVLink on the
 GPU box, gloo in the CPU tests) merges them -- no reduction, no second pass. The clause database is
 replicated; nothing else is exchanged on the data path.
+
+Two implementations of that all-gather:
+
+* ``peer_attach`` + ``merge_bitmaps``: the engine's own kernel over NVLink peer memory (``bbcp_merge_bitmaps``:
+  every rank stores its slice of both bitmaps straight into every peer's bitmaps, then a flag handshake; one
+  launch, no staging copies). ``torch.distributed`` is used once, at set-up, to exchange the CUDA IPC handles.
+* ``allgather_bitmap``: ``torch.distributed.all_gather_into_tensor`` (NCCL / gloo) -- the baseline the kernel
+  is checked against, and the path the CPU tests cover.
 """
 from __future__ import annotations
 
@@ -55,3 +63,35 @@ def allgather_bitmap(local: torch.Tensor, shard: Shard, group=None) -> torch.Ten
     out = torch.empty(shard.words_per_rank * shard.world, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, send, group=group)
     return out[:words]
+
+
+def peer_attach(engine, rank: int, world: int, group=None) -> None:
+    """Exchange the CUDA IPC handles of every rank's bitmap block and map the peers (once per finalize)."""
+    import ctypes as C
+
+    from ._lib import PEER_HANDLE_BYTES
+    L, h = engine.lib, engine.handle
+    mine = (C.c_ubyte * PEER_HANDLE_BYTES)()
+    rc = L.bbcp_peer_export(h, mine)
+    if rc:
+        raise RuntimeError(f"bbcp_peer_export: {rc}: {engine.GetStatusExplanation()}")
+    blobs = [None] * world
+    if world > 1:
+        dist.all_gather_object(blobs, bytes(mine), group=group)
+    else:
+        blobs[0] = bytes(mine)
+    allb = (C.c_ubyte * (PEER_HANDLE_BYTES * world)).from_buffer_copy(b"".join(blobs))
+    rc = L.bbcp_peer_attach(h, rank, world, allb)
+    if rc:
+        raise RuntimeError(f"bbcp_peer_attach: {rc}: {engine.GetStatusExplanation()}")
+
+
+def merge_bitmaps(engine, shard: Shard) -> float:
+    """All-gather of the failed-literal and unit bitmap slices over NVLink peer memory; blocks until every
+    peer's slice has arrived. Returns the device time in milliseconds (incl. waiting for the slowest rank)."""
+    import ctypes as C
+    ms = C.c_float(0.0)
+    rc = engine.lib.bbcp_merge_bitmaps(engine.handle, shard.word_lo, shard.word_hi, C.byref(ms))
+    if rc:
+        raise RuntimeError(f"bbcp_merge_bitmaps: {rc}: {engine.GetStatusExplanation()}")
+    return ms.value
