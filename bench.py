@@ -192,8 +192,11 @@ def ours_arm(args, rank, local_rank, world):
     n_local = last - first
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    opts = Opts(1, 0, 0, 0, 0)
-    opts_timed = Opts(1 | 8, 0, 0, 0, 0)   # + BBCP_OPT_KERNEL_TIMES: per-kernel CUDA events (separate pass)
+    # world > 1: BBCP_OPT_MERGE (16) = the bitmap all-gather over NVLink peer memory is the last kernel of the batch;
+    # BBCP_OPT_RENDEZVOUS (32) = device-side barrier with all peers right before the timed batch
+    mg = (16 | 32) if world > 1 else 0
+    opts = Opts(1 | mg, 0, 0, 0, shard.words_per_rank)
+    opts_timed = Opts(1 | 8 | mg, 0, 0, 0, shard.words_per_rank)   # + BBCP_OPT_KERNEL_TIMES: per-kernel CUDA events (separate pass)
     info = BatchInfo()
     if world > 1:
         sharding.peer_attach(eng, rank, world)   # CUDA IPC handles exchanged once; the merge itself is the engine's kernel
@@ -207,14 +210,10 @@ def ours_arm(args, rank, local_rank, world):
         """all inputs resident: kernels + compaction (+ on-stream all-gather of the bitmap slices)"""
         rc = L.bbcp_probe_range(h, first, last, C.byref(opts), C.byref(info))
         assert rc == 0, eng.GetStatusExplanation()
-        ms = info.total_ms
-        if world > 1:
-            # all-gather of the failed/unit bitmap slices over NVLink peer memory, on the engine's stream
-            ms += sharding.merge_bitmaps(eng, shard)
-        return ms
+        return info.total_ms   # CUDA events on the engine's stream: first kernel .. end of the merge kernel
 
     clocks = ClockSampler(local_rank)
-    stats = {"triage_ms": [], "deep_ms": [], "compact_ms": [], "block_ms": [], "kernel_bytes": 0, "triage_bytes": 0, "launches": 0, "props_ref": 0, "props_all": 0}
+    stats = {"triage_ms": [], "deep_ms": [], "compact_ms": [], "block_ms": [], "merge_ms": [], "kernel_bytes": 0, "triage_bytes": 0, "launches": 0, "props_ref": 0, "props_all": 0}
     step_ms = []
     for it in range(args.warmup + args.steps):
         flush.fill_(it & 0xff)       # L2 flush between iterations
@@ -235,7 +234,7 @@ def ours_arm(args, rank, local_rank, world):
         barrier()
         rc = L.bbcp_probe_range(h, first, last, C.byref(opts_timed), C.byref(info))
         assert rc == 0, eng.GetStatusExplanation()
-        for k in ("triage_ms", "deep_ms", "compact_ms", "block_ms"):
+        for k in ("triage_ms", "deep_ms", "compact_ms", "block_ms", "merge_ms"):
             stats[k].append(getattr(info, k))
     barrier()
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -328,7 +327,7 @@ def ours_arm(args, rank, local_rank, world):
             "gpu_launches": stats["launches"],
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
-                         "bytes_per_launch": kbytes, "kernel_ms": 1e3 * t1, "triage_ms": 1e3 * tri, "deep_ms": 1e3 * dee, "compact_ms": 1e3 * com,
+                         "bytes_per_launch": kbytes, "kernel_ms": 1e3 * t1, "triage_ms": 1e3 * tri, "deep_ms": 1e3 * dee, "compact_ms": 1e3 * com, "merge_ms": 1e3 * avg("merge_ms"),
                          "all_kernels": {"bytes": stats["triage_bytes"] + prop_bytes + compact_bytes, "ms": 1e3 * (tri + dee + blk + com),
                                          "frac": (stats["triage_bytes"] + prop_bytes + compact_bytes) / max(tri + dee + blk + com, 1e-12) / 1e9 / peak},
                          "traffic": traffic,

@@ -50,6 +50,10 @@ enum {
     BBCP_OPT_NO_LEN_PRUNE = 2u,/* diagnostic: scan ternary/long rows even while only one literal is assigned */
     BBCP_OPT_KERNEL_TIMES = 8u,/* record CUDA events between the kernels and fill triage_ms / deep_ms / block_ms (a few
                                   microseconds of stream time per batch; total_ms is always measured) */
+    BBCP_OPT_MERGE = 16u,      /* bbcp_probe_range with peers attached: the all-gather of this range's slice of the failed /
+                                  unit bitmaps (bbcp_merge_bitmaps) runs as the last kernel of the batch, no host round trip */
+    BBCP_OPT_RENDEZVOUS = 32u, /* bbcp_probe_range with peers attached: wait on the device for every peer before the batch
+                                  starts (aligns the ranks' device clocks; every rank must pass the same flags) */
     BBCP_OPT_OFF32 = 4u        /* produce impl_off as uint32 (fetch with bbcp_fetch_implied32): halves the offset
                                   read-back; the batch fails with BBCP_ERR_ARG if it implies >= 2^32 literals */
 };
@@ -59,7 +63,7 @@ typedef struct {
     uint32_t small_trail;      /* trail capacity of the warp-per-probe tier, shared memory (0 = 512) */
     uint64_t out_capacity;     /* device capacity for implied literals per launch, in literals (0 = auto) */
     uint32_t mid_trail;        /* trail capacity of the CTA-per-probe shared-memory tier (0 = 4096) */
-    uint32_t reserved;
+    uint32_t merge_words_per_rank; /* BBCP_OPT_MERGE: bitmap words owned by each rank (as in bbcp_merge_bitmaps) */
 } bbcp_opts;
 
 typedef struct {
@@ -85,7 +89,7 @@ typedef struct {
     float mid_ms;              /* of which the shared-memory one */
     uint64_t n_mid;            /* probes that ran in the second tier (CTA per probe, state in shared memory) */
     float compact_ms;          /* device time of k_scan_gather (+ k_gather_long), last sequence */
-    float reserved_f;
+    float merge_ms;            /* device time of the in-batch bitmap all-gather (BBCP_OPT_MERGE), incl. waiting for peers */
 } bbcp_batch_info;
 
 typedef struct {
@@ -169,19 +173,21 @@ void *bbcp_stream(bbcp_handle *h);
 int bbcp_sync(bbcp_handle *h);
 
 /* ---- multi-GPU: one handle per GPU (one process per GPU), the database replicated, the probe universe cut into
- *      contiguous ranges aligned to bitmap words. bbcp_merge_bitmaps is the all-gather of the failed-literal and
- *      unit bitmap slices, done by ONE kernel over NVLink peer memory: every rank stores its slice [word_lo,
- *      word_hi) of both bitmaps straight into every peer's bitmaps (CUDA-IPC-mapped), raises an arrival flag in
- *      every peer, and waits for the flags of all peers. Set-up: every rank calls bbcp_peer_export after
- *      bbcp_finalize, the BBCP_PEER_HANDLE_BYTES blobs are exchanged by the host program (e.g. a
- *      torch.distributed / MPI all-gather), every rank calls bbcp_peer_attach with all of them in rank order.
- *      A re-finalize that changes the variable range needs bbcp_peer_detach + a new exchange. Every rank must
- *      call bbcp_merge_bitmaps the same number of times. *ms (optional) = device time incl. the wait. */
+ *      contiguous ranges aligned to bitmap words: rank r probes the literals whose bits live in bitmap words
+ *      [r*wpr, (r+1)*wpr), wpr = words_per_rank, a multiple of 4. bbcp_merge_bitmaps is the all-gather of those
+ *      slices of the failed-literal and unit bitmaps, done by ONE kernel over NVLink peer memory: every rank
+ *      raises a flag in every peer, waits for the flags of all peers and copies the peers' slices out of their
+ *      (CUDA-IPC-mapped) bitmaps with remote loads. words_per_rank == 0: the handshake alone (a device-side
+ *      barrier across the GPUs). Set-up: every rank calls bbcp_peer_export after bbcp_finalize, the
+ *      BBCP_PEER_HANDLE_BYTES blobs are exchanged by the host program (e.g. a torch.distributed / MPI all-gather),
+ *      every rank calls bbcp_peer_attach with all of them in rank order. A re-finalize that changes the variable
+ *      range needs bbcp_peer_detach + a new exchange. Every rank must make the same sequence of merging calls.
+ *      *ms (optional) = device time incl. the wait. */
 #define BBCP_PEER_HANDLE_BYTES 128
 int bbcp_peer_export(bbcp_handle *h, void *out /* BBCP_PEER_HANDLE_BYTES */);
 int bbcp_peer_attach(bbcp_handle *h, int rank, int world, const void *all /* world * BBCP_PEER_HANDLE_BYTES */);
 int bbcp_peer_detach(bbcp_handle *h);
-int bbcp_merge_bitmaps(bbcp_handle *h, uint64_t word_lo, uint64_t word_hi, float *ms);
+int bbcp_merge_bitmaps(bbcp_handle *h, uint64_t words_per_rank, float *ms);
 
 /* ---- single-cube convenience path with the Topor / IPASIR conventions:
  *      ipasir_assume / ipasir_solve / ipasir_val (ToporIpasir.cc:27-68), CTopor::Solve(assumps)

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libbbcp.so")
 
 
 class Opts(C.Structure):
-    _fields_ = [("flags", C.c_uint32), ("small_trail", C.c_uint32), ("out_capacity", C.c_uint64), ("mid_trail", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("flags", C.c_uint32), ("small_trail", C.c_uint32), ("out_capacity", C.c_uint64), ("mid_trail", C.c_uint32), ("merge_words_per_rank", C.c_uint32)]
 
 
 class BatchInfo(C.Structure):
@@ -19,7 +19,7 @@ class BatchInfo(C.Structure):
                 ("triage_bytes", C.c_uint64), ("n_deep", C.c_uint64),
                 ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("tier1_ms", C.c_float),
                 ("triage_ms", C.c_float), ("deep_ms", C.c_float), ("block_ms", C.c_float), ("mid_ms", C.c_float), ("n_mid", C.c_uint64),
-                ("compact_ms", C.c_float), ("reserved_f", C.c_float)]
+                ("compact_ms", C.c_float), ("merge_ms", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -69,7 +69,7 @@ _SIGS = {
     "bbcp_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bbcp_peer_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "bbcp_peer_detach": (C.c_int, [C.c_void_p]),
-    "bbcp_merge_bitmaps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_float)]),
+    "bbcp_merge_bitmaps": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_float)]),
     "bbcp_assume": (C.c_int, [C.c_void_p, C.c_int32]),
     "bbcp_solve": (C.c_int, [C.c_void_p]),
     "bbcp_val": (C.c_int, [C.c_void_p, C.c_int32]),

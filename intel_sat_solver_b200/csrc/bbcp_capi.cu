@@ -44,7 +44,8 @@ struct DevBuf {
 constexpr int MERGE_CTRL_WORDS = 128;   // after the two bitmaps: [0..63] arrival flag per rank, [64] push-done counter, [65] error
 constexpr int MISC_CURSOR = C_N;
 constexpr int MISC_U32 = C_N + 1;       // as u32 index from 2*MISC_U32: +0..2 tickets, +3 mid_count, +4 big_count, +5 deep_count
-                                        // +6 chunk_count of the giant-set gather, +7 grid barrier of the scan, +8 its finished-CTA count
+                                        // +6 chunk_count of the giant-set gather, +7 grid barrier of the scan, +8 its finished-CTA count,
+                                        // +9 its pushed-CTA count (merge)
 constexpr int MISC_TOTAL = C_N + 6;
 constexpr int MISC_WORDS64 = C_N + 7;
 // two counter blocks used alternately: the triage kernel of one launch sequence zeroes the block of the next one
@@ -276,7 +277,21 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     const int bps = small_blocks_per_sm(cap);
     if (bps <= 0) return h->fail(BBCP_ERR_CUDA, "propagate kernel does not fit (shared memory)");
     const uint32_t *h_u32 = reinterpret_cast<uint32_t *>(h->h_misc) + 2 * MISC_U32;
-    float triage_ms = 0, deep_ms = 0, block_ms = 0, mid_ms = 0, compact_ms = 0;
+    float triage_ms = 0, deep_ms = 0, block_ms = 0, mid_ms = 0, compact_ms = 0, merge_ms = 0;
+
+    // multi-GPU options (bbcp_probe_range only): device-side rendezvous with all peers before the batch, and the
+    // all-gather of this rank's bitmap slice as the last kernel of the batch
+    const bool peers = h->peer_world > 1 && !d_lits && !d_off;
+    uint32_t *const *ptab = static_cast<uint32_t *const *>(h->d_peer_tab.p);
+    if (peers && (opts.flags & BBCP_OPT_RENDEZVOUS))
+        launch_merge(MergeArgs{ptab, h->peer_rank, h->peer_world, h->bm_stride, 0, ++h->merge_epoch}, h->sm_count, h->stream);
+    const bool do_merge = peers && (opts.flags & BBCP_OPT_MERGE);
+    if (do_merge && (opts.merge_words_per_rank == 0 || (opts.merge_words_per_rank & 3)))
+        return h->fail(BBCP_ERR_ARG, "BBCP_OPT_MERGE: opts.merge_words_per_rank must be a non-zero multiple of 4");
+    const uint32_t mepoch = do_merge ? ++h->merge_epoch : 0;
+    // with implied sets the merge rides inside k_scan_gather (stores at its start, handshake at its end)
+    const MergeArgs no_merge{nullptr, 0, 0, 0, 0, 0};
+    const MergeArgs in_batch = do_merge ? MergeArgs{ptab, h->peer_rank, h->peer_world, h->bm_stride, opts.merge_words_per_rank, mepoch} : no_merge;
 
     cudaEventRecord(h->ev[0], h->stream);
     for (int attempt = 0;; ++attempt) {
@@ -316,7 +331,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             if (kevents) cudaEventRecord(h->ev[5], h->stream);
             bi.launches += 2;
             if (implied) {
-                if (!launch_scan_gather(b, 0, h->sg_blocks, false, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
+                if (!launch_scan_gather(b, 0, h->sg_blocks, false, in_batch, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
                 ++bi.launches;
             }
         } else {
@@ -347,7 +362,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             cudaEventRecord(h->ev[6], h->stream);
             bi.launches += 2;
             if (implied) {
-                if (!launch_scan_gather(b, 1, h->sg_blocks, true, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
+                if (!launch_scan_gather(b, 1, h->sg_blocks, true, in_batch, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
                 bi.launches += 2;
             }
             cudaMemcpyAsync(h->h_misc, misc, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
@@ -371,7 +386,20 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     }
     if (!implied) {
         cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
+        if (do_merge) {
+            // flags-only batch: no compaction kernel to ride in, the merge is its own launch
+            cudaEventRecord(h->ev_merge[0], h->stream);
+            launch_merge(in_batch, h->sm_count, h->stream);
+            cudaEventRecord(h->ev[2], h->stream);
+            ++bi.launches;
+        }
         if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "batch")) return BBCP_ERR_CUDA;
+        if (do_merge) cudaEventElapsedTime(&merge_ms, h->ev_merge[0], h->ev[2]);
+    }
+    if (do_merge) {
+        uint32_t err = 0;
+        cudaMemcpy(&err, h->d_bitmaps.as<uint32_t>() + 2 * h->bm_stride + 65, 4, cudaMemcpyDeviceToHost);
+        if (err) return h->fail(BBCP_ERR_CUDA, "bitmap merge: a peer did not arrive within the time-out");
     }
     if (off32 && bi.n_implied > 0xffffffffull) return h->fail(BBCP_ERR_ARG, "BBCP_OPT_OFF32: more than 2^32-1 implied literals in one batch (split it)");
     h->last_off32 = off32 && implied;
@@ -399,6 +427,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     bi.block_ms = block_ms;
     bi.mid_ms = mid_ms;
     bi.compact_ms = implied ? compact_ms : 0.f;
+    bi.merge_ms = merge_ms;
     bi.tier1_ms = triage_ms + deep_ms;
     bi.kernel_ms = triage_ms + deep_ms + block_ms;
     h->last_n = n;
@@ -792,16 +821,16 @@ int bbcp_peer_attach(bbcp_handle *h, int rank, int world, const void *all)
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "peer table upload") ? BBCP_OK : BBCP_ERR_CUDA;
 }
 
-int bbcp_merge_bitmaps(bbcp_handle *h, uint64_t word_lo, uint64_t word_hi, float *ms)
+int bbcp_merge_bitmaps(bbcp_handle *h, uint64_t words_per_rank, float *ms)
 {
     int rc = need_final(h);
     if (rc) return rc;
     if (h->peer_world < 1) return h->fail(BBCP_ERR_STATE, "bbcp_merge_bitmaps: no peers attached");
-    if (word_lo > word_hi || word_hi > h->bitmap_words) return h->fail(BBCP_ERR_ARG, "bbcp_merge_bitmaps: slice outside the bitmap");
+    if (words_per_rank & 3) return h->fail(BBCP_ERR_ARG, "bbcp_merge_bitmaps: words_per_rank must be a multiple of 4");
     cudaSetDevice(h->device);
     ++h->merge_epoch;
     cudaEventRecord(h->ev_merge[0], h->stream);
-    launch_merge(static_cast<uint32_t *const *>(h->d_peer_tab.p), h->peer_rank, h->peer_world, h->bm_stride, word_lo, word_hi, h->merge_epoch,
+    launch_merge(MergeArgs{static_cast<uint32_t *const *>(h->d_peer_tab.p), h->peer_rank, h->peer_world, h->bm_stride, words_per_rank, h->merge_epoch},
                  h->sm_count, h->stream);
     cudaEventRecord(h->ev_merge[1], h->stream);
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "bitmap merge")) return BBCP_ERR_CUDA;

@@ -86,13 +86,20 @@ void launch_mid(const DbView &db, const BatchView &b, uint32_t cap, int blocks, 
 void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s);
 size_t mid_smem_bytes(uint32_t trail_cap);
 int mid_blocks_per_sm(uint32_t trail_cap);
-bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, cudaStream_t s);
-int scan_gather_max_blocks(int sm_count);
-void launch_merge(uint32_t *const *peer_base, int rank, int world, uint64_t stride, uint64_t lo, uint64_t hi, uint32_t epoch, int sm_count,
-                  cudaStream_t s);
-constexpr uint32_t SG_TILE = 2048;   // items per scan tile
+constexpr uint32_t SG_TILE = 2048;   // items per step of the compaction kernel
 size_t small_smem_bytes(uint32_t trail_cap);
 int small_blocks_per_sm(uint32_t trail_cap);
+struct MergeArgs;
+bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s);
+int scan_gather_max_blocks(int sm_count);
+struct MergeArgs {
+    uint32_t *const *peer_base;   // [world] every rank's [failed | unit | control] block (own entry = own memory)
+    int rank, world;              // world <= 1: nothing to merge
+    uint64_t stride;              // words between the failed and the unit bitmap
+    uint64_t wp;                  // bitmap words owned by each rank (multiple of 4): rank r owns [r*wp, (r+1)*wp); 0 = rendezvous only
+    uint32_t epoch;
+};
+void launch_merge(const MergeArgs &m, int sm_count, cudaStream_t s);
 constexpr int SMALL_WARPS = 4;   // warps (= concurrent probes) per CTA, first tier
 constexpr int MID_THREADS = 128;   // second tier: 4 warps share one probe, state in shared memory
 constexpr int BIG_THREADS = 512;   // third tier: 16 warps share one probe, state in a global slab

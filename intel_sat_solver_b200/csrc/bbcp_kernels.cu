@@ -904,6 +904,79 @@ __global__ void __launch_bounds__(512) k_block(const DbView db, const BatchView 
     wc.flush(b.counters);
 }
 
+// ---------------------------------------------------------------- multi-GPU merge of the bitmap slices
+// All-gather over NVLink peer memory (one process per GPU, every rank runs this on its own GPU at the same
+// point of its stream). peer_base[r] = rank r's [failed | unit | control] block, mapped through CUDA IPC; rank
+// r owns bitmap words [r*wp, (r+1)*wp). PULL protocol, no system-scope fence anywhere (measured here: a
+// fence.sys behind remote stores costs ~10 us, a remote load round trip ~2 us):
+//   signal  as soon as this rank's bitmaps are final (they were written by EARLIER kernels of the stream, so
+//           they are already performed in this GPU's L2, which also serves the peers' reads) one thread stores
+//           the merge epoch into this rank's flag word in every peer;
+//   wait    before reading, a thread spins on the local flag words until every peer's epoch has arrived;
+//   pull    every thread then copies its share of every peer's slice of both bitmaps with 16-byte remote loads.
+// Inside a batch the signal is the first thing k_scan_gather does and wait + pull are the last, so the flags
+// travel while the compaction runs; k_merge is the stand-alone form.
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void merge_signal(const MergeArgs &m)
+{
+    for (int p = 0; p < m.world; ++p)
+        if (p != m.rank) *(volatile uint32_t *)(m.peer_base[p] + 2 * m.stride + m.rank) = m.epoch;
+}
+
+// one thread; returns false on time-out (a peer died; the host call reports it)
+__device__ bool merge_wait(const MergeArgs &m)
+{
+    uint32_t *ctrl = m.peer_base[m.rank] + 2 * m.stride;
+    const unsigned long long t0 = global_ns();
+    for (int p = 0; p < m.world; ++p) {
+        if (p == m.rank) continue;
+        uint32_t spins = 0;
+        while ((int32_t)(*(volatile uint32_t *)&ctrl[p] - m.epoch) < 0) {
+            if ((++spins & 0xfffu) == 0 && global_ns() - t0 > 20000000000ull) { ctrl[65] = 1; return false; }
+        }
+    }
+    __threadfence();   // the loads of the pull stay behind the flag reads
+    return true;
+}
+
+__device__ __forceinline__ uint4 ld_remote(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void merge_pull(const MergeArgs &m, uint64_t gtid, uint64_t gsize)
+{
+    uint32_t *mine = m.peer_base[m.rank];
+    const uint64_t wp4 = m.wp / 4, s4 = m.stride / 4;           // both multiples of 4 words
+    const uint64_t per_peer = 2 * wp4, total = per_peer * (uint64_t)(m.world - 1);
+    for (uint64_t i = gtid; i < total; i += gsize) {
+        const int pi = (int)(i / per_peer);
+        const uint64_t r = i - (uint64_t)pi * per_peer;
+        const uint64_t which = r >= wp4 ? 1 : 0;
+        const int p = pi + (pi >= m.rank);
+        const uint64_t v = (uint64_t)p * wp4 + (r - which * wp4);   // vector index inside one bitmap
+        if (v >= s4) continue;                                      // the last rank's slice may be short
+        reinterpret_cast<uint4 *>(mine)[which * s4 + v] = ld_remote(reinterpret_cast<const uint4 *>(m.peer_base[p]) + which * s4 + v);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_merge(const MergeArgs m)
+{
+    __shared__ int s_ok;
+    if (blockIdx.x == 0 && threadIdx.x == 0) merge_signal(m);
+    if (threadIdx.x == 0) s_ok = merge_wait(m);
+    __syncthreads();
+    if (s_ok && m.wp) merge_pull(m, (uint64_t)blockIdx.x * 256 + threadIdx.x, (uint64_t)gridDim.x * 256);
+}
+
 // ---------------------------------------------------------------- result compaction into canonical CSR order
 // One pass: sizes -> exclusive prefix sum (single-pass scan with decoupled look-back over 2048-item tiles)
 // -> CSR offsets written, every implied set copied from its allocation-order position in the pool to its
@@ -933,11 +1006,15 @@ __device__ __forceinline__ int32_t item_self_lit(const BatchView &b, uint64_t it
 // w*256 + j*32 + l, j = 0..7, so every load and store of a warp is one contiguous 128/256-byte run -- turns
 // sizes into offsets with warp shuffles, writes the offsets and moves the literals.
 template <bool OFF32>
-__global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, const int pass, const uint64_t seg)
+__global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, const int pass, const uint64_t seg, const MergeArgs mg)
 {
     // first pass of a batch: if some probes still wait for the CTA-per-probe tiers the sizes are not final
     // (uniform over the grid, so nobody is left waiting at the barrier)
     if (pass == 0 && *(volatile uint32_t *)b.mid_count != 0) return;
+    // the bitmaps are final (every propagate kernel of the batch is done): start sending this rank's slice to the
+    // peers now -- unless the implied-literal pool overflowed and the whole batch is about to be re-run
+    const bool merging = mg.world > 1 && *(volatile unsigned long long *)b.out_cursor <= b.out_cap;
+    if (merging && blockIdx.x == 0 && threadIdx.x == 0) merge_signal(mg);
     __shared__ unsigned long long s_warp[SG_THREADS / 32], s_red[SG_THREADS / 32];
     __shared__ uint32_t s_nbig, s_pos;
     __shared__ uint16_t s_big[SG_TILE];
@@ -1103,8 +1180,16 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
         }
         if (nbig) __syncthreads();
     }
+    // merge: by now the peers' flags have had a whole compaction to arrive; copy their slices
+    if (merging) {
+        __syncthreads();
+        if (tid == 0) s_pos = merge_wait(mg);
+        __syncthreads();
+        if (s_pos) merge_pull(mg, (uint64_t)blockIdx.x * SG_THREADS + tid, (uint64_t)gridDim.x * SG_THREADS);
+    }
     // the last CTA to finish copies the counter block of this launch sequence into mapped host memory: the host
-    // reads it after the stream synchronisation it does anyway (no copy-engine round trip)
+    // reads it after the stream synchronisation it does anyway (no copy-engine round trip, and no fence: the
+    // kernel has completed by then)
     if (b.host_report) {
         __syncthreads();
         if (tid == 0) {
@@ -1112,11 +1197,8 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
             s_pos = atomicAdd(b.tile_ticket + 1, 1u);
         }
         __syncthreads();
-        if (s_pos == gridDim.x - 1) {
-            __threadfence();
+        if (s_pos == gridDim.x - 1)
             for (uint32_t i = tid; i < b.zero_words; i += SG_THREADS) b.host_report[i] = ((volatile unsigned long long *)b.counters)[i];
-            __threadfence_system();
-        }
     }
 }
 
@@ -1136,54 +1218,6 @@ __global__ void __launch_bounds__(256) k_gather_long(const BatchView b)
             if (i < m) b.impl[d + i] = b.out_lits[src + i];
         }
     }
-}
-
-// ---------------------------------------------------------------- multi-GPU merge of the bitmap slices
-// All-gather over NVLink peer memory in one kernel (one process per GPU, every rank runs this on its own GPU at
-// the same point of its stream). peer_base[r] = rank r's [failed | unit | control] block, mapped through CUDA
-// IPC. Every rank STORES its own slice [lo, hi) of both bitmaps into every peer's block (remote writes, no
-// reads over the link), the last CTA to finish raises this rank's arrival flag in every peer with the epoch of
-// this merge and then waits until every peer's flag in the local control words has reached the epoch.
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-__global__ void __launch_bounds__(256) k_merge(uint32_t *const *peer_base, const int rank, const int world, const uint64_t stride,
-                                               const uint64_t lo, const uint64_t hi, const uint32_t epoch)
-{
-    uint32_t *mine = peer_base[rank];
-    uint32_t *ctrl = mine + 2 * stride;
-    const uint64_t cnt = hi - lo;
-    if (cnt && world > 1) {
-        const uint64_t per_peer = 2 * cnt, total = per_peer * (uint64_t)(world - 1);
-        for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (uint64_t)gridDim.x * 256) {
-            const int pi = (int)(i / per_peer);
-            const uint64_t r = i - (uint64_t)pi * per_peer;
-            const uint64_t which = r >= cnt ? 1 : 0, w = lo + r - which * cnt;
-            const int p = pi + (pi >= rank);
-            peer_base[p][which * stride + w] = mine[which * stride + w];
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    if (atomicAdd(&ctrl[64], 1u) != gridDim.x - 1) return;
-    ctrl[64] = 0;   // for the next merge
-    __threadfence_system();
-    for (int p = 0; p < world; ++p)
-        if (p != rank) *(volatile uint32_t *)(peer_base[p] + 2 * stride + rank) = epoch;
-    const unsigned long long t0 = global_ns();
-    for (int p = 0; p < world; ++p) {
-        if (p == rank) continue;
-        while ((int32_t)(*(volatile uint32_t *)&ctrl[p] - epoch) < 0) {
-            if (global_ns() - t0 > 20000000000ull) { ctrl[65] = 1; return; }   // 20 s: a peer died; reported by the host call
-            __nanosleep(100);
-        }
-    }
-    __threadfence_system();
 }
 
 }  // namespace
@@ -1248,7 +1282,7 @@ int scan_gather_max_blocks(int sm_count)
     return std::max(1, std::min(nb, 4)) * sm_count;
 }
 
-bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, cudaStream_t s)
+bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s)
 {
     // one contiguous segment of whole 2048-item steps per CTA
     uint64_t blocks = std::min<uint64_t>(std::max<uint64_t>((b.n + SG_TILE - 1) / SG_TILE, 1), (uint64_t)max_blocks);
@@ -1256,20 +1290,20 @@ bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant
     if (seg == 0) seg = SG_TILE;
     blocks = std::max<uint64_t>((b.n + seg - 1) / seg, 1);
     BatchView bv = b;
+    MergeArgs m = mg;
     int p = pass;
-    void *args[] = {&bv, &p, &seg};
+    void *args[] = {&bv, &p, &seg, &m};
     const void *fn = (b.opts & OPT_OFF32) ? (const void *)k_scan_gather<true> : (const void *)k_scan_gather<false>;
     if (cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(SG_THREADS), args, 0, s) != cudaSuccess) return false;
     if (giant_sets_possible) k_gather_long<<<max_blocks, 256, 0, s>>>(b);
     return true;
 }
 
-void launch_merge(uint32_t *const *peer_base, int rank, int world, uint64_t stride, uint64_t lo, uint64_t hi, uint32_t epoch, int sm_count,
-                  cudaStream_t s)
+void launch_merge(const MergeArgs &m, int sm_count, cudaStream_t s)
 {
-    const uint64_t total = 2 * (hi - lo) * (uint64_t)std::max(world - 1, 0);
-    const int blocks = (int)std::min<uint64_t>(std::max<uint64_t>((total + 1023) / 1024, 1), (uint64_t)sm_count * 2);
-    k_merge<<<blocks, 256, 0, s>>>(peer_base, rank, world, stride, lo, hi, epoch);
+    const uint64_t total = (m.wp / 4) * 2 * (uint64_t)std::max(m.world - 1, 0);
+    const int blocks = (int)std::min<uint64_t>(std::max<uint64_t>((total + 255) / 256, 1), (uint64_t)sm_count * 2);
+    k_merge<<<blocks, 256, 0, s>>>(m);
 }
 
 }  // namespace bbcp

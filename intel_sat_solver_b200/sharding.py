@@ -40,7 +40,7 @@ def bitmap_words(max_var: int) -> int:
 def shard_for(rank: int, world: int, max_var: int) -> Shard:
     universe = 2 * max_var
     words = bitmap_words(max_var)
-    wp = (words + world - 1) // world
+    wp = ((words + world - 1) // world + 3) & ~3    # multiple of 4 words: the merge kernel moves 16-byte vectors
     word_lo, word_hi = min(rank * wp, words), min((rank + 1) * wp, words)
     first = min(max(32 * word_lo - 2, 0), universe)
     last = min(max(32 * word_hi - 2, 0), universe)
@@ -86,12 +86,19 @@ def peer_attach(engine, rank: int, world: int, group=None) -> None:
         raise RuntimeError(f"bbcp_peer_attach: {rc}: {engine.GetStatusExplanation()}")
 
 
+def device_barrier(engine) -> None:
+    """The handshake of the merge alone: returns when every rank's stream has reached this point."""
+    rc = engine.lib.bbcp_merge_bitmaps(engine.handle, 0, None)
+    if rc:
+        raise RuntimeError(f"bbcp_merge_bitmaps: {rc}: {engine.GetStatusExplanation()}")
+
+
 def merge_bitmaps(engine, shard: Shard) -> float:
     """All-gather of the failed-literal and unit bitmap slices over NVLink peer memory; blocks until every
     peer's slice has arrived. Returns the device time in milliseconds (incl. waiting for the slowest rank)."""
     import ctypes as C
     ms = C.c_float(0.0)
-    rc = engine.lib.bbcp_merge_bitmaps(engine.handle, shard.word_lo, shard.word_hi, C.byref(ms))
+    rc = engine.lib.bbcp_merge_bitmaps(engine.handle, shard.words_per_rank, C.byref(ms))
     if rc:
         raise RuntimeError(f"bbcp_merge_bitmaps: {rc}: {engine.GetStatusExplanation()}")
     return ms.value

@@ -21,6 +21,9 @@ from ._lib import BatchInfo, DbInfo, Opts
 OPT_IMPLIED = 1
 OPT_NO_LEN_PRUNE = 2
 OPT_OFF32 = 4
+OPT_KERNEL_TIMES = 8
+OPT_MERGE = 16
+OPT_RENDEZVOUS = 32
 
 
 class TToporReturnVal(enum.IntEnum):
@@ -126,9 +129,12 @@ class BatchedTopor:
         return rc
 
     @staticmethod
-    def _opts(implied=True, small_trail=0, out_capacity=0, no_len_prune=False, mid_trail=0, off32=False) -> Opts:
-        return Opts((OPT_IMPLIED if implied else 0) | (OPT_NO_LEN_PRUNE if no_len_prune else 0) | (OPT_OFF32 if off32 else 0),
-                    small_trail, out_capacity, mid_trail, 0)
+    def _opts(implied=True, small_trail=0, out_capacity=0, no_len_prune=False, mid_trail=0, off32=False, kernel_times=False,
+              merge=0, rendezvous=False) -> Opts:
+        """merge: 0, or the bitmap words owned by each rank (sharding.Shard.words_per_rank) to all-gather the slices in the batch"""
+        return Opts((OPT_IMPLIED if implied else 0) | (OPT_NO_LEN_PRUNE if no_len_prune else 0) | (OPT_OFF32 if off32 else 0)
+                    | (OPT_KERNEL_TIMES if kernel_times else 0) | (OPT_MERGE if merge else 0) | (OPT_RENDEZVOUS if rendezvous else 0),
+                    small_trail, out_capacity, mid_trail, int(merge))
 
     def _fetch(self, info: BatchInfo, implied: bool, fetch: bool, off32: bool = False) -> BatchResult:
         res = BatchResult(info.as_dict())

@@ -33,6 +33,12 @@ def _worker(rank, world, port, names, q):
         for rep in range(3):   # repeated merges: epochs advance, bitmaps accumulate
             res = t.ProbeRange(s.first, s.last)
             ms = sharding.merge_bitmaps(t, s)
+        # the same with the merge as the last kernel of the batch (and a device-side rendezvous before it), with
+        # state budgets that send some probes through the second launch sequence on some ranks only
+        t.ClearBitmaps()
+        dist.barrier()
+        for kw in (dict(), dict(small_trail=32, mid_trail=32), dict(out_capacity=16)):
+            res = t.ProbeRange(s.first, s.last, merge=s.words_per_rank, rendezvous=True, **kw)
         flag, off, lits = golden[f"{name}/probe_flag"], golden[f"{name}/probe_off"], golden[f"{name}/probe_lits"]
         ok &= bool(np.array_equal(res.flag, flag[s.first:s.last]))
         ok &= bool(np.array_equal(res.impl_lits, lits[int(off[s.first]):int(off[s.last])]))
