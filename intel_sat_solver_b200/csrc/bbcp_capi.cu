@@ -384,10 +384,10 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         out_cap = std::max<uint64_t>(cursor + cursor / 8, out_cap * 2);
         if (attempt == 7) return h->fail(BBCP_ERR_ALLOC, "implied-literal buffer keeps overflowing");
     }
-    if (!implied) {
-        cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
+    if (!implied || n == 0) {
+        if (!implied) cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
         if (do_merge) {
-            // flags-only batch: no compaction kernel to ride in, the merge is its own launch
+            // flags-only or empty batch: no compaction kernel to ride in, the merge is its own launch
             cudaEventRecord(h->ev_merge[0], h->stream);
             launch_merge(in_batch, h->sm_count, h->stream);
             cudaEventRecord(h->ev[2], h->stream);

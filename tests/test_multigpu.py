@@ -37,8 +37,9 @@ def _worker(rank, world, port, names, q):
         # state budgets that send some probes through the second launch sequence on some ranks only
         t.ClearBitmaps()
         dist.barrier()
-        for kw in (dict(), dict(small_trail=32, mid_trail=32), dict(out_capacity=16)):
+        for kw in (dict(), dict(small_trail=32, mid_trail=32), dict(out_capacity=16), dict(implied=False)):
             res = t.ProbeRange(s.first, s.last, merge=s.words_per_rank, rendezvous=True, **kw)
+        res = t.ProbeRange(s.first, s.last, merge=s.words_per_rank)
         flag, off, lits = golden[f"{name}/probe_flag"], golden[f"{name}/probe_off"], golden[f"{name}/probe_lits"]
         ok &= bool(np.array_equal(res.flag, flag[s.first:s.last]))
         ok &= bool(np.array_equal(res.impl_lits, lits[int(off[s.first]):int(off[s.last])]))
@@ -73,7 +74,7 @@ def test_p2p_merge_matches_golden_and_nccl(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, names, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=300) for _ in range(world)]
+    got = [q.get(timeout=120) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
