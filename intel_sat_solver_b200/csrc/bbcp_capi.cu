@@ -45,9 +45,9 @@ constexpr int MERGE_CTRL_WORDS = 128;   // after the two bitmaps: [0..63] arriva
 constexpr int MISC_CURSOR = C_N;
 constexpr int MISC_U32 = C_N + 1;       // as u32 index from 2*MISC_U32: +0..2 tickets, +3 mid_count, +4 big_count, +5 deep_count
                                         // +6 chunk_count of the giant-set gather, +7 grid barrier of the scan, +8 its finished-CTA count,
-                                        // +9 its pushed-CTA count (merge)
-constexpr int MISC_TOTAL = C_N + 6;
-constexpr int MISC_WORDS64 = C_N + 7;
+                                        // +10 sort_count (second-tier sets waiting for k_sort_sets)
+constexpr int MISC_TOTAL = C_N + 7;
+constexpr int MISC_WORDS64 = C_N + 8;
 // two counter blocks used alternately: the triage kernel of one launch sequence zeroes the block of the next one
 
 }  // namespace
@@ -88,6 +88,9 @@ struct bbcp_handle {
     int lean = 3;                           // bit 0: counters reach the host through mapped memory; bit 1: no per-kernel events
     uint64_t out_cap_hint = 0;   // stored literals the last batch needed (sizes the next batch's buffer)
     uint32_t big_slabs = 0;
+    DevBuf d_mid_slab;           // second tier: per-warp hash + trail
+    uint32_t mid_slab_cap = 0;   // trail capacity the slab is laid out (and zeroed) for
+    uint64_t mid_slab_groups = 0;
     uint32_t slab_version = 0;   // db_version the slabs were sized for
 
     uint64_t last_n = 0, last_n_implied = 0;
@@ -185,6 +188,18 @@ bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo)
     return true;
 }
 
+// BBCP_DEBUG_SYNC=1: synchronise after every kernel of a batch and name the one that faulted
+bool dbg_check(bbcp_handle *h, const char *what)
+{
+    static const bool on = getenv("BBCP_DEBUG_SYNC") != nullptr;
+    if (!on) return true;
+    const cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) return true;
+    h->fail(BBCP_ERR_CUDA, std::string("[debug] fault in ") + what + ": " + cudaGetErrorString(e));
+    fprintf(stderr, "bbcp: %s\n", h->err.c_str());
+    return false;
+}
+
 DbView db_view(const bbcp_handle *h)
 {
     DbView v;
@@ -193,6 +208,8 @@ DbView db_view(const bbcp_handle *h)
     v.arena = h->d_arena.as<uint4>();
     v.litinfo = h->d_litinfo.as<uint8_t>();
     v.max_var = h->db.max_var;
+    v.n_slots = (uint32_t)h->db.slots.size();
+    v.n_arena_units = (uint32_t)(h->db.arena.size() / 4);
     v.nvars_words16 = (uint32_t)(((uint64_t)h->db.max_var + 1 + 15) / 16);
     return v;
 }
@@ -243,9 +260,12 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         !h->d_overflow.reserve(n1 * 4) || !h->d_big.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_tiles.reserve(((size_t)h->sg_blocks + 4) * 8))
         return h->fail(BBCP_ERR_ALLOC, "device allocation failed (batch buffers)");
 
-    uint32_t cap = opts.small_trail ? pow2_at_least(opts.small_trail) : 512;
+    // lanes per probe (bbcp_propagate.cuh): a full warp. Narrower groups were measured and rejected, see DESIGN.md
+    const int width = 32;
+    uint32_t cap = opts.small_trail ? pow2_at_least(opts.small_trail) : 512u;
     if (cap > 8192) cap = 8192;
-    uint32_t cap_mid = opts.mid_trail ? pow2_at_least(opts.mid_trail) : 4096;
+    while (small_smem_bytes(cap, width) > 200 * 1024 && cap > 32) cap >>= 1;
+    uint32_t cap_mid = opts.mid_trail ? pow2_at_least(opts.mid_trail) : 8192;
     if (cap_mid > 16384) cap_mid = 16384;
     const bool implied = (opts.flags & BBCP_OPT_IMPLIED) != 0;
     const bool off32 = (opts.flags & BBCP_OPT_OFF32) != 0;
@@ -274,7 +294,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.zero_words = MISC_WORDS64;
     b.opts = opts.flags;
 
-    const int bps = small_blocks_per_sm(cap);
+    const int bps = small_blocks_per_sm(cap, width);
     if (bps <= 0) return h->fail(BBCP_ERR_CUDA, "propagate kernel does not fit (shared memory)");
     const uint32_t *h_u32 = reinterpret_cast<uint32_t *>(h->h_misc) + 2 * MISC_U32;
     float triage_ms = 0, deep_ms = 0, block_ms = 0, mid_ms = 0, compact_ms = 0, merge_ms = 0;
@@ -297,7 +317,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     for (int attempt = 0;; ++attempt) {
         // room for every self-implying probe (n) plus out_cap stored literals
         if (!h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4) || (implied && !h->d_impl.reserve((n + out_cap + 4) * 4)) ||
-            !h->d_chunks.reserve((out_cap / 2048 + 64) * 8))
+            !h->d_chunks.reserve((out_cap / 2048 + out_cap / 16384 + 64) * 8))   // sets above 16384 literals, 2048 per chunk, rounded up per set
             return h->fail(BBCP_ERR_ALLOC, "device allocation failed (implied literals)");
         b.out_lits = h->d_out.as<int32_t>();
         b.impl = h->d_impl.as<int32_t>();
@@ -317,6 +337,8 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         b.deep_count = u32 + 5;
         b.chunk_count = u32 + 6;
         b.tile_ticket = u32 + 7;
+        b.sort_count = u32 + 10;
+        b.sort_list = h->d_deep.as<uint32_t>();   // the triage queue is spent by the time the second tier runs
         const bool zero_copy = implied && n && (h->lean & 1);
         const bool kevents = want_kernel_times;
         b.host_report = zero_copy ? static_cast<unsigned long long *>(h->d_hmisc) : nullptr;
@@ -326,12 +348,15 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         if (n) {
             if (kevents) cudaEventRecord(h->ev[3], h->stream);
             launch_triage(b, dbv, h->sm_count, h->stream);
+            if (!dbg_check(h, "k_triage")) return BBCP_ERR_CUDA;
             if (kevents) cudaEventRecord(h->ev[4], h->stream);
-            launch_small(dbv, b, cap, bps * h->sm_count, h->stream);
+            launch_small(dbv, b, cap, width, bps * h->sm_count, h->stream);
+            if (!dbg_check(h, "k_deep")) return BBCP_ERR_CUDA;
             if (kevents) cudaEventRecord(h->ev[5], h->stream);
             bi.launches += 2;
             if (implied) {
                 if (!launch_scan_gather(b, 0, h->sg_blocks, false, in_batch, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
+                if (!dbg_check(h, "k_scan_gather (first sequence)")) return BBCP_ERR_CUDA;
                 ++bi.launches;
             }
         } else {
@@ -350,19 +375,35 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         if (n && h_u32[3] != 0) {
             // some probes outgrew the first tier: CTA-per-probe tiers, then the compaction for real
             second = true;
-            const int bps_mid = mid_blocks_per_sm(cap_mid);
-            if (bps_mid <= 0) return h->fail(BBCP_ERR_CUDA, "propagate kernel does not fit (shared memory)");
+            const int bps_mid = mid_blocks_per_sm(width);
+            if (bps_mid <= 0) return h->fail(BBCP_ERR_CUDA, "second-tier kernel does not fit");
+            const uint64_t gpc = MID2_THREADS / width;   // probes in flight per CTA
+            const uint64_t mid_blocks = std::min<uint64_t>((uint64_t)bps_mid * h->sm_count, ((uint64_t)h_u32[3] + gpc - 1) / gpc);
+            const uint64_t mid_groups = (uint64_t)bps_mid * h->sm_count * gpc;
+            if (h->mid_slab_cap != cap_mid || h->mid_slab_groups < mid_groups || !h->d_mid_slab.p) {
+                // (re)lay out the per-group slabs; the hash tables must start from zero
+                const size_t bytes = mid_groups * mid_slab_words_per_group(cap_mid) * 4;
+                if (!h->d_mid_slab.reserve(bytes)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (second-tier state)");
+                cudaMemsetAsync(h->d_mid_slab.p, 0, bytes, h->stream);
+                h->mid_slab_cap = cap_mid;
+                h->mid_slab_groups = mid_groups;
+            }
             if (!ensure_slabs(h, dbv)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (third-tier state)");
             ls.bits = h->d_lbits.as<uint32_t>();
             ls.trail = h->d_ltrail.as<uint32_t>();
             cudaEventRecord(h->ev[1], h->stream);
-            launch_mid(dbv, b, cap_mid, bps_mid * h->sm_count, h->stream);
+            launch_mid(dbv, b, h->d_mid_slab.as<uint32_t>(), cap_mid, width, (int)mid_blocks, h->stream);
+            if (!dbg_check(h, "k_deep2")) return BBCP_ERR_CUDA;
             cudaEventRecord(h->ev[7], h->stream);
             launch_big(dbv, b, ls, (int)h->big_slabs, h->stream);
+            if (!dbg_check(h, "k_big")) return BBCP_ERR_CUDA;
+            if (implied) { launch_sort_sets(b, cap_mid, h->sm_count, h->stream); ++bi.launches; }
+            if (!dbg_check(h, "k_sort_sets")) return BBCP_ERR_CUDA;
             cudaEventRecord(h->ev[6], h->stream);
             bi.launches += 2;
             if (implied) {
                 if (!launch_scan_gather(b, 1, h->sg_blocks, true, in_batch, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
+                if (!dbg_check(h, "k_scan_gather / k_gather_long (second sequence)")) return BBCP_ERR_CUDA;
                 bi.launches += 2;
             }
             cudaMemcpyAsync(h->h_misc, misc, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
@@ -468,7 +509,7 @@ void bbcp_release(bbcp_handle *h)
         for (auto &e : h->ev_merge) if (e) cudaEventDestroy(e);
         for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_bitmaps, &h->d_peer_tab, &h->d_flag, &h->d_raw_off, &h->d_len,
                           &h->d_out, &h->d_off, &h->d_impl, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_big, &h->d_deep, &h->d_chunks, &h->d_misc, &h->d_lbits,
-                          &h->d_ltrail, &h->d_tiles})
+                          &h->d_ltrail, &h->d_tiles, &h->d_mid_slab})
             b->release();
         if (h->h_misc) cudaFreeHost(h->h_misc);
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);

@@ -23,6 +23,7 @@ struct DbView {
     const uint4 *arena;
     const uint8_t *litinfo;     // per internal literal l (as a probe): LI_* bits
     int32_t max_var;
+    uint32_t n_slots, n_arena_units;   // extents (bounds checks of debug builds: -DBBCP_CHECKS)
     uint32_t nvars_words16;    // words of a 2-bit-per-var dense assignment: ceil((max_var+1)/16)
 };
 
@@ -54,6 +55,8 @@ struct BatchView {
     unsigned int *ticket;       // [3] dynamic schedulers of k_deep / k_block<mid> / k_block<big>
     uint32_t *deep_list;        // items queued by the triage for propagation
     uint32_t *deep_count;
+    uint32_t *sort_list;        // second-tier items whose implied set waits in the pool unsorted (k_sort_sets)
+    uint32_t *sort_count;
     uint2 *chunk_list;          // (item, chunk) pairs of giant implied sets, filled by k_scan_gather for k_gather_long
     uint32_t *chunk_count;
     // result compaction (k_scan_gather): canonical CSR offsets + literals
@@ -81,14 +84,15 @@ struct LargeState {
 };
 
 void launch_triage(const BatchView &b, const DbView &db, int sm_count, cudaStream_t s);
-void launch_small(const DbView &db, const BatchView &b, uint32_t trail_cap, int blocks, cudaStream_t s);
-void launch_mid(const DbView &db, const BatchView &b, uint32_t cap, int blocks, cudaStream_t s);
+void launch_small(const DbView &db, const BatchView &b, uint32_t trail_cap, int width, int blocks, cudaStream_t s);
+void launch_mid(const DbView &db, const BatchView &b, uint32_t *slab, uint32_t cap, int width, int blocks, cudaStream_t s);
+void launch_sort_sets(const BatchView &b, uint32_t cap, int sm_count, cudaStream_t s);
+size_t mid_slab_words_per_group(uint32_t cap);
+int mid_blocks_per_sm(int width);
 void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s);
-size_t mid_smem_bytes(uint32_t trail_cap);
-int mid_blocks_per_sm(uint32_t trail_cap);
 constexpr uint32_t SG_TILE = 2048;   // items per step of the compaction kernel
-size_t small_smem_bytes(uint32_t trail_cap);
-int small_blocks_per_sm(uint32_t trail_cap);
+size_t small_smem_bytes(uint32_t trail_cap, int width);
+int small_blocks_per_sm(uint32_t trail_cap, int width);
 struct MergeArgs;
 bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s);
 int scan_gather_max_blocks(int sm_count);
@@ -100,8 +104,8 @@ struct MergeArgs {
     uint32_t epoch;
 };
 void launch_merge(const MergeArgs &m, int sm_count, cudaStream_t s);
-constexpr int SMALL_WARPS = 4;   // warps (= concurrent probes) per CTA, first tier
-constexpr int MID_THREADS = 128;   // second tier: 4 warps share one probe, state in shared memory
+constexpr int SMALL_THREADS = 128;  // first tier: SMALL_THREADS / W probes in flight per CTA (W lanes per probe)
+constexpr int MID2_THREADS = 256;   // second tier: MID2_THREADS / W probes per CTA, state in a global slab
 constexpr int BIG_THREADS = 512;   // third tier: 16 warps share one probe, state in a global slab
 
 }  // namespace bbcp

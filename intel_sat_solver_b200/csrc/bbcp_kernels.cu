@@ -27,6 +27,7 @@
 // A conflict ends the probe (NewContradiction's same-level branch, TopiBcp.cc:141-158); only the flag is
 // part of the contract for conflicting probes.
 #include "bbcp_device.cuh"
+#include "bbcp_propagate.cuh"
 
 #include <algorithm>
 
@@ -34,425 +35,17 @@ namespace bbcp {
 
 namespace {
 
-constexpr unsigned FULL = 0xffffffffu;
-
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
-__device__ __forceinline__ int32_t to_ext(uint32_t il) { return (il & 1u) ? -(int32_t)(il >> 1) : (int32_t)(il >> 1); }
-
-// ---------------------------------------------------------------- per-probe state, first tier (shared memory)
-struct SmemState {
-    uint32_t *hash;    // [1 << log_hs] true literals, 0 = empty
-    uint32_t *trail;   // [cap]
-    uint16_t *tslot;   // [cap] hash slot of each trail entry (for the O(|trail|) clean-up)
-    uint32_t log_hs, cap;
-
-    __device__ __forceinline__ uint32_t h(uint32_t var) const { return (var * 0x9E3779B1u) >> (32 - log_hs); }
-    // 0 unassigned, 1 true, 2 false
-    __device__ __forceinline__ int lookup(uint32_t lit) const
-    {
-        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
-        uint32_t s = h(var);
-        for (;;) {
-            const uint32_t k = hash[s];
-            if (k == 0) return 0;
-            if ((k >> 1) == var) return k == lit ? 1 : 2;
-            s = (s + 1) & mask;
-        }
-    }
-    // 0 newly assigned, 1 already true, 2 already false (conflict)
-    __device__ __forceinline__ int insert(uint32_t lit, uint32_t &slot)
-    {
-        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
-        uint32_t s = h(var);
-        for (;;) {
-            const uint32_t old = atomicCAS(&hash[s], 0u, lit);
-            if (old == 0) { slot = s; return 0; }
-            if ((old >> 1) == var) return old == lit ? 1 : 2;
-            s = (s + 1) & mask;
-        }
-    }
-    __device__ __forceinline__ uint32_t tget(uint32_t i) const { return trail[i]; }
-    __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t slot) { trail[i] = lit; tslot[i] = (uint16_t)slot; }
-    __device__ __forceinline__ void cleanup(uint32_t tail)
-    {
-        for (uint32_t i = lane_id(); i < tail; i += 32) hash[tslot[i]] = 0;
-        __syncwarp();
-    }
-    // after an overflow some table entries have no trail entry: wipe everything
-    __device__ __forceinline__ void wipe()
-    {
-        for (uint32_t i = lane_id(); i < (1u << log_hs); i += 32) hash[i] = 0;
-        __syncwarp();
-    }
-};
-
-// ---------------------------------------------------------------- per-probe state, second tier (global slab)
-struct GmemState {
-    uint32_t *bits;   // 2 bits per var: 1 = var true, 2 = var false
-    uint32_t *trail;
-    uint32_t cap;
-
-    __device__ __forceinline__ int lookup(uint32_t lit) const
-    {
-        const uint32_t var = lit >> 1;
-        const uint32_t o = (__ldcg(&bits[var >> 4]) >> ((var & 15u) * 2u)) & 3u;
-        if (o == 0) return 0;
-        return (o == 1u) == ((lit & 1u) == 0u) ? 1 : 2;
-    }
-    __device__ __forceinline__ int insert(uint32_t lit, uint32_t &slot)
-    {
-        const uint32_t var = lit >> 1, sh = (var & 15u) * 2u, bit = (lit & 1u) ? 2u : 1u;
-        const uint32_t o = (atomicOr(&bits[var >> 4], bit << sh) >> sh) & 3u;
-        slot = 0;
-        if (o == 0) return 0;
-        return o == bit ? 1 : 2;
-    }
-    __device__ __forceinline__ uint32_t tget(uint32_t i) const { return __ldcg(&trail[i]); }
-    __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t) { __stcg(&trail[i], lit); }
-    __device__ __forceinline__ void cleanup(uint32_t tail)
-    {
-        for (uint32_t i = lane_id(); i < tail; i += 32) {
-            const uint32_t var = __ldcg(&trail[i]) >> 1;
-            atomicAnd(&bits[var >> 4], ~(3u << ((var & 15u) * 2u)));
-        }
-        __syncwarp();
-    }
-    __device__ __forceinline__ void wipe() {}  // cannot overflow: the trail holds every variable
-};
-
-struct WarpCounters {
-    unsigned long long props_all = 0, props_ref = 0, slots = 0, fetches = 0, bytes = 0;
-    uint32_t n_ok = 0, n_conf = 0, n_skip = 0;
-    __device__ void flush(unsigned long long *c)
-    {
-        if (lane_id() == 0) {
-            if (props_all) atomicAdd(&c[C_PROPS_ALL], props_all);
-            if (props_ref) atomicAdd(&c[C_PROPS_REF], props_ref);
-            if (slots) atomicAdd(&c[C_SLOTS], slots);
-            if (fetches) atomicAdd(&c[C_CLAUSE_FETCH], fetches);
-            if (bytes) atomicAdd(&c[C_BYTES], bytes);
-            if (n_ok) atomicAdd(&c[C_OK], (unsigned long long)n_ok);
-            if (n_conf) atomicAdd(&c[C_CONFLICT], (unsigned long long)n_conf);
-            if (n_skip) atomicAdd(&c[C_SKIPPED], (unsigned long long)n_skip);
-        }
-    }
-};
-
-// ---------------------------------------------------------------- where newly implied literals go
-// WarpTail: one warp owns the probe, the trail tail is a register. BlockTail: the warps of a CTA share one
-// probe, the tail and the conflict / overflow latches live in shared memory.
-struct WarpTail {
-    uint32_t tail;
-    __device__ __forceinline__ uint32_t get() const { return tail; }
-    __device__ __forceinline__ bool aborted() const { return false; }
-    __device__ __forceinline__ void latch_conflict() {}
-    // Commit one round of candidate implications (one candidate per lane, 0 = none). Warp-converged.
-    // Returns 0 ok, 1 conflict, 2 state overflow.
-    template <class S>
-    __device__ __forceinline__ int commit(S &st, uint32_t cand)
-    {
-        const bool has = cand != 0;
-        // same literal implied by several clauses in this step: keep the lowest lane (deterministic trail order)
-        const unsigned same = __match_any_sync(FULL, has ? cand : (0x80000000u | (uint32_t)lane_id()));
-        const bool leader = has && (lane_id() == __ffs(same) - 1);
-        uint32_t slot = 0;
-        const int r = leader ? st.insert(cand, slot) : 1;
-        const bool any_conf = __any_sync(FULL, r == 2);
-        const unsigned newm = __ballot_sync(FULL, leader && r == 0);
-        const uint32_t nnew = __popc(newm);
-        if (tail + nnew > st.cap) return 2;  // caller wipes the whole table: the new entries are not on the trail
-        if (leader && r == 0) st.tset(tail + __popc(newm & lanemask_lt()), cand, slot);
-        tail += nnew;
-        return any_conf ? 1 : 0;
-    }
-};
-
-struct BlockTail {
-    uint32_t *ctl;  // shared: [0] tail, [1] conflict latch, [2] overflow latch
-    __device__ __forceinline__ uint32_t get() const { return *(volatile uint32_t *)&ctl[0]; }
-    __device__ __forceinline__ bool aborted() const { return (*(volatile uint32_t *)&ctl[1] | *(volatile uint32_t *)&ctl[2]) != 0; }
-    __device__ __forceinline__ void latch_conflict() { if (lane_id() == 0) ctl[1] = 1; }
-    template <class S>
-    __device__ __forceinline__ int commit(S &st, uint32_t cand)
-    {
-        const bool has = cand != 0;
-        const unsigned same = __match_any_sync(FULL, has ? cand : (0x80000000u | (uint32_t)lane_id()));
-        const bool leader = has && (lane_id() == __ffs(same) - 1);
-        uint32_t slot = 0;
-        const int r = leader ? st.insert(cand, slot) : 1;   // duplicates across warps: only one insert returns 0
-        const bool any_conf = __any_sync(FULL, r == 2);
-        const unsigned newm = __ballot_sync(FULL, leader && r == 0);
-        const uint32_t nnew = __popc(newm);
-        int ret = 0;
-        if (nnew) {
-            uint32_t pos = 0;
-            if (lane_id() == 0) pos = atomicAdd(&ctl[0], nnew);
-            pos = __shfl_sync(FULL, pos, 0);
-            if (pos + nnew > st.cap) { if (lane_id() == 0) ctl[2] = 1; ret = 2; }
-            else if (leader && r == 0) st.tset(pos + __popc(newm & lanemask_lt()), cand, slot);
-        }
-        if (any_conf) { if (lane_id() == 0) ctl[1] = 1; if (!ret) ret = 1; }
-        return ret;
-    }
-};
-
-// Judge a long clause (>= 4 literals) from scratch: TopiBcp.cc:262-367 without the watch bookkeeping.
-// Returns the literal to imply (0 = none); sets confl when every literal is false.
-template <class S>
-__device__ __forceinline__ uint32_t visit_long(const DbView &db, const S &st, uint32_t cref, bool &confl, uint32_t &units16)
-{
-    const uint4 *cp = db.arena + cref;
-    uint4 w = __ldg(cp);
-    const uint32_t size = w.x;
-    uint32_t nfree = 0, cand = 0, i = 0;
-    bool sat = false;
-    units16 = 1;
-    uint32_t l[4] = {w.y, w.z, w.w, 0};
-    int have = 3;
-    for (;;) {
-        for (int k = 0; k < have && i < size; ++k, ++i) {
-            const int v = st.lookup(l[k]);
-            if (v == 1) { sat = true; break; }
-            if (v == 0) { ++nfree; cand = l[k]; }
-        }
-        if (sat || nfree >= 2 || i >= size) break;
-        w = __ldg(++cp);
-        ++units16;
-        l[0] = w.x; l[1] = w.y; l[2] = w.z; l[3] = w.w;
-        have = 4;
-    }
-    if (sat || nfree >= 2) return 0;
-    if (nfree == 0) { confl = true; return 0; }
-    return cand;
-}
-
-// One warp scans the rows of up to 32 newly true literals (lane i holds literal p for i < B): one header
-// gather, then the union of the rows is flattened and walked 32 eight-byte slots at a time.
-// Returns 0 ok, 1 conflict, 2 overflow.
-template <class S, class T>
-__device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t p, uint32_t B, bool bins_only, WarpCounters &wc)
-{
-    const int lane = lane_id();
-    uint4 hd = make_uint4(0, 0, 0, 0);
-    if (lane < (int)B) hd = __ldg(&db.hdr[p ^ 1u]);
-    const uint32_t nb2 = (hd.y + 1u) >> 1;
-    const uint32_t cnt = bins_only ? nb2 : nb2 + hd.z + hd.w;
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += t;
-    }
-    const uint32_t excl = incl - cnt;
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    wc.props_all += B;
-    wc.props_ref += __popc(__ballot_sync(FULL, (hd.y | hd.z | hd.w) != 0));
-    wc.slots += total;
-    wc.bytes += 16ull * B + 8ull * total;
-
-    for (uint32_t base = 0; base < total; base += 32) {
-        const uint32_t g = base + lane;
-        const bool active = g < total;
-        // owner row of slot g: the largest lane i with excl_i <= g
-        int lo = 0;
-#pragma unroll
-        for (int step = 16; step; step >>= 1) {
-            const int mid = lo + step;
-            const uint32_t e = __shfl_sync(FULL, excl, mid & 31);
-            if (mid < 32 && e <= g) lo = mid;
-        }
-        const uint32_t r_start = __shfl_sync(FULL, hd.x, lo);
-        const uint32_t r_nb2 = (__shfl_sync(FULL, hd.y, lo) + 1u) >> 1;
-        const uint32_t r_nt = __shfl_sync(FULL, hd.z, lo);
-        const uint32_t k = g - __shfl_sync(FULL, excl, lo);
-        uint32_t c0 = 0, c1 = 0;
-        bool confl = false;
-        uint32_t fetched16 = 0;
-        if (active) {
-            const uint2 s = __ldg(&db.slots[r_start + k]);
-            if (k < r_nb2) {
-                // binary clauses (TopiBcp.cc:207-246)
-                int v = st.lookup(s.x);
-                if (v == 0) c0 = s.x; else if (v == 2) confl = true;
-                if (s.y) {
-                    v = st.lookup(s.y);
-                    if (v == 0) c1 = s.y; else if (v == 2) confl = true;
-                }
-            } else if (k < r_nb2 + r_nt) {
-                // inline ternary clause (falsified literal, s.x, s.y)
-                const int va = st.lookup(s.x);
-                if (va != 1) {
-                    const int vb = st.lookup(s.y);
-                    if (vb != 1) {
-                        if (va == 2 && vb == 2) confl = true;
-                        else if (va == 2) c0 = s.y;
-                        else if (vb == 2) c0 = s.x;
-                    }
-                }
-            } else {
-                // long clause: cached literal first (TopiBcp.cc:255-259), then the clause itself
-                if (st.lookup(s.x) != 1) c0 = visit_long(db, st, s.y, confl, fetched16);
-            }
-        }
-        const unsigned fm = __ballot_sync(FULL, fetched16 != 0);
-        if (fm) {
-            uint32_t f = fetched16;
-#pragma unroll
-            for (int d = 16; d; d >>= 1) f += __shfl_xor_sync(FULL, f, d);
-            wc.fetches += __popc(fm);
-            wc.bytes += 16ull * f;
-        }
-        if (__any_sync(FULL, confl)) { tl.latch_conflict(); return 1; }
-        if (__any_sync(FULL, c0 != 0)) {
-            const int r = tl.commit(st, c0);
-            if (r) return r;
-        }
-        if (__any_sync(FULL, c1 != 0)) {
-            const int r = tl.commit(st, c1);
-            if (r) return r;
-        }
-        __syncwarp();
-        if (tl.aborted()) return 1;  // another warp of the CTA hit a conflict / overflow
-    }
-    return 0;
-}
-
-// Breadth-first unit propagation of trail[0..tail) to fixpoint by ONE warp. Returns 0 fixpoint, 1 conflict, 2 overflow.
-template <class S>
-__device__ int propagate(const DbView &db, S &st, WarpTail &tl, bool prune, WarpCounters &wc)
-{
-    const int lane = lane_id();
-    uint32_t head = 0;
-    while (head < tl.tail) {
-        const uint32_t B = min(32u, tl.tail - head);
-        const uint32_t p = lane < (int)B ? st.tget(head + lane) : 0u;
-        // while a single literal is assigned only binary clauses can become unit
-        const int r = process_batch(db, st, tl, p, B, prune && tl.tail == 1, wc);
-        if (r) return r;
-        head += B;
-    }
-    return 0;
-}
-
-// Load a cube into the (empty) state with the semantics of HandleAssumptions (Topi.cc:797-938).
-// Returns the flag to report if the cube is decided here (2,3,4 or 1), FLAG_OVERFLOW, or 0xff = propagate.
-template <class S, class T>
-__device__ int load_cube(const DbView &db, S &st, const int32_t *lits, uint32_t n, T &tl)
-{
-    const int lane = lane_id();
-    bool unmapped = false, false_l0 = false, conflict = false, overflow = false;
-    for (uint32_t base = 0; base < n; base += 32) {
-        const uint32_t i = base + lane;
-        uint32_t cand = 0;
-        if (i < n) {
-            const int32_t l = lits[i];
-            const uint32_t v = (uint32_t)(l < 0 ? -l : l);
-            if (l != 0) {
-                const uint32_t il = 2u * v + (l < 0);
-                const uint8_t li = (int32_t)v <= db.max_var ? db.litinfo[il] : 0;
-                if (!(li & LI_MAPPED)) unmapped = true;
-                else if (li & LI_FALSE_L0) false_l0 = true;
-                else if (!(li & LI_TRUE_L0)) cand = il;
-            }
-        }
-        if (!overflow && !conflict) {
-            const int r = tl.commit(st, cand);
-            if (r == 1) conflict = true;
-            if (r == 2) overflow = true;
-        }
-        __syncwarp();
-    }
-    if (__any_sync(FULL, unmapped)) return FLAG_UNMAPPED;
-    if (__any_sync(FULL, false_l0)) return FLAG_FALSE_L0;
-    if (overflow) return FLAG_OVERFLOW;
-    if (conflict) return FLAG_CONFLICT;
-    if (tl.get() == 0) return FLAG_TRIVIAL_L0;
-    return 0xff;
-}
-
-// warp bitonic sort of a[0..n2) ascending, n2 a power of two (shared or global memory)
-__device__ void bitonic_sort(uint32_t *a, uint32_t n2)
-{
-    const int lane = lane_id();
-    for (uint32_t k = 2; k <= n2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t t = lane; t < n2 / 2; t += 32) {
-                // t-th compare-exchange pair of this stage
-                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const uint32_t ixj = i | j;
-                const bool up = (i & k) == 0;
-                const uint32_t x = a[i], y = a[ixj];
-                if ((x > y) == up) { a[i] = y; a[ixj] = x; }
-            }
-            __syncwarp();
-        }
-    }
-}
-
-// allocate `count` output literals for this warp (uniform); returns ~0 if the buffer is full
-__device__ __forceinline__ unsigned long long out_alloc(const BatchView &b, uint32_t count)
-{
-    unsigned long long base = 0;
-    if (lane_id() == 0) base = atomicAdd(b.out_cursor, (unsigned long long)count);
-    base = __shfl_sync(FULL, base, 0);
-    return base + count <= b.out_cap ? base : ~0ull;
-}
-
-__device__ __forceinline__ void mark_failed(const BatchView &b, uint32_t ilit)
-{
-    atomicOr(&b.failed[ilit >> 5], 1u << (ilit & 31));
-    atomicOr(&b.unit[(ilit ^ 1u) >> 5], 1u << ((ilit ^ 1u) & 31));
-}
-
-struct Item {
-    const int32_t *lits;
-    uint32_t n;
-    int32_t probe_lit;  // depth-1 item: its literal (0 otherwise)
-};
-
-__device__ __forceinline__ Item get_item(const BatchView &b, uint64_t item)
-{
-    Item it;
-    if (b.cube_off) {
-        const uint64_t o = b.cube_off[item];
-        it.lits = b.cube_lits + o;
-        it.n = (uint32_t)(b.cube_off[item + 1] - o);
-        it.probe_lit = it.n == 1 ? it.lits[0] : 0;  // a depth-1 cube is a probe
-    } else if (b.cube_lits) {
-        it.probe_lit = b.cube_lits[item];   // probe-list mode; 0 is reported as unmapped by the triage
-        it.lits = b.cube_lits + item;
-        it.n = 1;
-    } else {
-        const uint64_t idx = b.first + item;
-        const int32_t v = (int32_t)(idx / 2 + 1);
-        it.probe_lit = (idx & 1) ? -v : v;
-        it.lits = nullptr;
-        it.n = 1;
-    }
-    return it;
-}
-
-// load_cube for probe mode (a single literal, no memory to read)
-template <class S, class T>
-__device__ int load_probe(const DbView &db, S &st, int32_t l, T &tl)
-{
-    const uint32_t v = (uint32_t)(l < 0 ? -l : l);
-    const uint8_t li = (int32_t)v <= db.max_var ? db.litinfo[2u * v + (l < 0)] : 0;
-    if (!(li & LI_MAPPED)) return FLAG_UNMAPPED;
-    if (li & LI_FALSE_L0) return FLAG_FALSE_L0;
-    if (li & LI_TRUE_L0) return FLAG_TRIVIAL_L0;
-    const int r = tl.commit(st, lane_id() == 0 ? 2u * v + (l < 0) : 0u);
-    __syncwarp();
-    return r == 2 ? FLAG_OVERFLOW : 0xff;
-}
 
 // ---------------------------------------------------------------- first tier: shared-memory state
+// Result of one probe of the first tier: flag, implied set (sorted in shared memory, written to the pool as
+// external literals) or hand-over to the second tier.
+template <class G>
 __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, const Item &it, int res, uint32_t tail,
-                             WarpCounters &wc)
+                             WorkCounters &wc)
 {
-    const int lane = lane_id();
-    if (res == 2) st.wipe(); else st.cleanup(tail);
+    const int lane = G::lane();
+    if (res == 2) st.template wipe<G>(); else st.template cleanup<G>(tail);
     uint8_t flag;
     uint32_t len = 0;
     unsigned long long off = 0;
@@ -467,14 +60,14 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
         if (b.opts & OPT_IMPLIED) {
             uint32_t n2 = 1;
             while (n2 < tail) n2 <<= 1;
-            for (uint32_t i = tail + lane; i < n2; i += 32) st.trail[i] = 0xffffffffu;
-            __syncwarp();
-            if (tail > 1) bitonic_sort(st.trail, n2);
-            off = out_alloc(b, tail);
+            for (uint32_t i = tail + lane; i < n2; i += G::width) st.trail[i] = 0xffffffffu;
+            G::sync();
+            if (tail > 1) bitonic_sort<G>(st.trail, n2);
+            off = out_alloc<G>(b, tail);
             if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
             else {
                 len = tail;
-                for (uint32_t i = lane; i < tail; i += 32) b.out_lits[off + i] = to_ext(st.trail[i]);
+                for (uint32_t i = lane; i < tail; i += G::width) b.out_lits[off + i] = to_ext(st.trail[i]);
                 wc.bytes += 4ull * tail;
             }
         }
@@ -482,7 +75,7 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
     if (lane == 0) { b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off; }
     wc.n_ok += flag == FLAG_OK;
     wc.n_conf += flag == FLAG_CONFLICT;
-    __syncwarp();
+    G::sync();
 }
 
 // Triage: eight consecutive items per thread. Decides every depth-1 item that needs no propagation (unmapped /
@@ -521,8 +114,9 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
     uint32_t n_ok = 0, n_skip = 0, n_ref = 0;
     const uint32_t stride = gridDim.x * 256u * TRIAGE_ITEMS;
     for (uint32_t wb = blockIdx.x * 256u * TRIAGE_ITEMS; wb < n; wb += stride) {
+        // every lane of the warp walks every iteration (the queueing below uses full-warp collectives); lanes past
+        // the end of the batch carry TQ_NONE items
         const uint32_t base = wb + threadIdx.x * TRIAGE_ITEMS;
-        if (base >= n) continue;   // (no barrier below)
         const bool full = base + TRIAGE_ITEMS <= n;
         uint32_t q[TRIAGE_ITEMS];
         if (MODE == TM_UNIVERSE) {
@@ -530,7 +124,8 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
             const uint64_t il0 = b.first + base + 2;
             const uint32_t *w = reinterpret_cast<const uint32_t *>(db.litinfo) + (il0 >> 2);
             const uint32_t sh = (uint32_t)(il0 & 3u) * 8u;
-            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = sh ? __ldg(w + 2) : 0u;   // litinfo is padded by 16 bytes
+            const bool in = base < n;   // litinfo is padded by 16 bytes past its last literal, no further
+            const uint32_t w0 = in ? __ldg(w) : 0u, w1 = in ? __ldg(w + 1) : 0u, w2 = (in && sh) ? __ldg(w + 2) : 0u;
             const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
 #pragma unroll
             for (int k = 0; k < TRIAGE_ITEMS; ++k) {
@@ -580,22 +175,19 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
             for (int k = 0; k < TRIAGE_ITEMS; ++k)
                 if (base + k < n) { b.flag[base + k] = (uint8_t)q[k]; b.len[base + k] = (q[k] & TQ_SELF) ? selflen : 0u; }
         }
-        // queue the deep items (the active lanes of the warp reserve one run of the list together)
-        const unsigned act = __activemask();
-        if (__any_sync(act, deepmask != 0)) {
+        // queue the deep items (the warp reserves one run of the list)
+        if (__any_sync(FULL, deepmask != 0)) {
             const uint32_t cnt = __popc(deepmask);
             uint32_t incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(act, incl, d);
+                const uint32_t t = __shfl_up_sync(FULL, incl, d);
                 if (lane_id() >= d) incl += t;
             }
-            // lanes are active from 0 upwards (base grows with the lane), so the last active lane holds the total
-            const int last = 31 - __clz(act);
-            const uint32_t total = __shfl_sync(act, incl, last);
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
             uint32_t pos = 0;
             if (lane_id() == 0) pos = atomicAdd(b.deep_count, total);
-            pos = __shfl_sync(act, pos, 0) + incl - cnt;
+            pos = __shfl_sync(FULL, pos, 0) + incl - cnt;
             uint32_t m = deepmask;
             while (m) {
                 const int k = __ffs(m) - 1;
@@ -624,109 +216,176 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
     }
 }
 
-// Warp-per-probe propagation of the queued items, per-probe state in shared memory.
-__global__ void __launch_bounds__(SMALL_WARPS * 32)
+// Group-per-probe propagation of the queued items, per-probe state in shared memory. W lanes per probe
+// (bbcp_propagate.cuh), SMALL_THREADS / W probes in flight per CTA.
+template <int W>
+__global__ void __launch_bounds__(SMALL_THREADS)
 k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t cap)
 {
+    using G = Grp<W>;
     extern __shared__ uint32_t smem[];
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    constexpr int GROUPS = SMALL_THREADS / W;
+    const int lane = G::lane(), grp = threadIdx.x / W;
     const uint32_t ndeep = *b.deep_count;
-    if ((uint64_t)blockIdx.x * SMALL_WARPS >= ndeep) return;
+    if ((uint64_t)blockIdx.x * GROUPS >= ndeep) return;
     const uint32_t hs = 1u << log_hs;
-    const uint32_t per_warp = hs + cap + cap / 2;  // words: hash, trail, tslot (u16)
+    const uint32_t per_grp = hs + cap + cap / 2;  // words: hash, trail, tslot (u16)
     SmemState st;
-    st.hash = smem + warp * per_warp;
+    st.hash = smem + grp * per_grp;
     st.trail = st.hash + hs;
     st.tslot = reinterpret_cast<uint16_t *>(st.trail + cap);
     st.log_hs = log_hs;
     st.cap = cap;
-    for (uint32_t i = lane; i < hs; i += 32) st.hash[i] = 0;
-    __syncwarp();
+    for (uint32_t i = lane; i < hs; i += W) st.hash[i] = 0;
+    G::sync();
 
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
-    WarpCounters wc;
+    WorkCounters wc;
     for (;;) {
         unsigned t = 0;
         if (lane == 0) t = atomicAdd(b.ticket, 1u);
-        t = __shfl_sync(FULL, t, 0);
+        t = G::shfl(t, 0);
         if (t >= ndeep) break;
         const uint64_t it_idx = b.deep_list[t];
+        BBCP_CHECK(it_idx < b.n, "deep_list[%u] = %llu of %llu (ndeep %u)\n", t, (unsigned long long)it_idx, (unsigned long long)b.n, ndeep);
         const Item it = get_item(b, it_idx);
-        WarpTail tl{0};
-        int f = it.probe_lit ? load_probe(db, st, it.probe_lit, tl) : load_cube(db, st, it.lits, it.n, tl);
+        GroupTail tl{0};
+        int f = it.probe_lit ? load_probe<G>(db, st, it.probe_lit, tl) : load_cube<G>(db, st, it.lits, it.n, tl);
         int res;
-        if (f == 0xff) res = propagate(db, st, tl, prune, wc);
+        if (f == 0xff) res = propagate<G>(db, st, tl, prune, wc);
         else if (f == FLAG_OVERFLOW) res = 2;
         else if (f == FLAG_CONFLICT) res = 1;
         else {
-            st.cleanup(tl.tail);
+            st.template cleanup<G>(tl.tail);
             if (lane == 0) { b.flag[it_idx] = (uint8_t)f; b.len[it_idx] = 0; b.raw_off[it_idx] = 0; }
             ++wc.n_skip;
-            __syncwarp();
+            G::sync();
             continue;
         }
-        finish_small(b, st, it_idx, it, res, tl.tail, wc);
+        finish_small<G>(b, st, it_idx, it, res, tl.tail, wc);
     }
-    wc.flush(b.counters);
+    wc.template flush<G>(b.counters);
 }
 
-// ---------------------------------------------------------------- block-cooperative tiers
-// One CTA per probe: the warps share the per-probe state and walk each breadth-first level of the trail
-// together (level-synchronous, two barriers per level). Second tier: state in shared memory (hash + trail
-// of cap_mid literals); third tier: dense 2-bit assignment + trail in a per-CTA global slab, any size.
-struct SmemBlockState {
-    uint32_t *hash;
-    uint32_t *trail;
-    uint32_t log_hs, cap;
-    __device__ __forceinline__ uint32_t h(uint32_t var) const { return (var * 0x9E3779B1u) >> (32 - log_hs); }
-    __device__ __forceinline__ int lookup(uint32_t lit) const
-    {
-        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
-        uint32_t s = h(var);
-        for (;;) {
-            const uint32_t k = *(volatile uint32_t *)&hash[s];
-            if (k == 0) return 0;
-            if ((k >> 1) == var) return k == lit ? 1 : 2;
-            s = (s + 1) & mask;
-        }
-    }
-    __device__ __forceinline__ int insert(uint32_t lit, uint32_t &slot)
-    {
-        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
-        uint32_t s = h(var);
-        slot = 0;
-        for (;;) {
-            const uint32_t old = atomicCAS(&hash[s], 0u, lit);
-            if (old == 0) return 0;
-            if ((old >> 1) == var) return old == lit ? 1 : 2;
-            s = (s + 1) & mask;
-        }
-    }
-    __device__ __forceinline__ uint32_t tget(uint32_t i) const { return trail[i]; }
-    __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t) { trail[i] = lit; }
-};
-
-// block bitonic sort of a[0..n2) ascending, n2 a power of two, in shared memory
-__device__ void block_bitonic_sort(uint32_t *a, uint32_t n2)
+// ---------------------------------------------------------------- second tier: group per probe, global hash state
+// Probes that outgrew the shared-memory state. Same propagation code, state in a per-group slab (GhashState).
+// The implied set is written to the pool UNSORTED as internal literals and the item is queued for k_sort_sets.
+template <int W>
+__global__ void __launch_bounds__(MID2_THREADS)
+k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_hs, const uint32_t cap)
 {
-    for (uint32_t k = 2; k <= n2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t t = threadIdx.x; t < n2 / 2; t += blockDim.x) {
-                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const uint32_t ixj = i | j;
-                const bool up = (i & k) == 0;
-                const uint32_t x = a[i], y = a[ixj];
-                if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+    using G = Grp<W>;
+    constexpr int GROUPS = MID2_THREADS / W;
+    const int lane = G::lane();
+    const uint32_t count = *b.mid_count;
+    const uint32_t ggrp = blockIdx.x * GROUPS + threadIdx.x / W;
+    if (ggrp >= count) return;
+    GhashState st;
+    st.hash = slab + (size_t)ggrp * ((1u << log_hs) + cap);
+    st.trail = st.hash + (1u << log_hs);
+    st.log_hs = log_hs;
+    st.cap = cap;
+    const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
+    WorkCounters wc;
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(b.ticket + 1, 1u);
+        t = G::shfl(t, 0);
+        if (t >= count) break;
+        const uint64_t item = b.mid_list[t];
+        const Item it = get_item(b, item);
+        GroupTail tl{0};
+        const int f = it.probe_lit ? load_probe<G>(db, st, it.probe_lit, tl) : load_cube<G>(db, st, it.lits, it.n, tl);
+        int res;
+        if (f == 0xff) res = propagate<G>(db, st, tl, prune, wc);
+        else if (f == FLAG_OVERFLOW) res = 2;
+        else if (f == FLAG_CONFLICT) res = 1;
+        else {
+            st.template cleanup<G>(tl.tail);
+            if (lane == 0) { b.flag[item] = (uint8_t)f; b.len[item] = 0; b.raw_off[item] = 0; atomicAdd(&b.counters[C_MID], 1ull); }
+            ++wc.n_skip;
+            G::sync();
+            continue;
+        }
+        uint8_t flag;
+        uint32_t len = 0;
+        unsigned long long off = 0;
+        const uint32_t tail = tl.tail;
+        if (res == 2) {
+            flag = FLAG_OVERFLOW;
+            if (lane == 0) b.big_list[atomicAdd(b.big_count, 1u)] = (uint32_t)item;
+            st.template wipe<G>();   // some table entries have no trail entry
+        } else {
+            if (res == 1) {
+                flag = FLAG_CONFLICT;
+                if (it.probe_lit && lane == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
+            } else {
+                flag = FLAG_OK;
+                if (b.opts & OPT_IMPLIED) {
+                    off = out_alloc<G>(b, tail);
+                    if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
+                    else {
+                        len = tail;
+                        for (uint32_t i = lane; i < tail; i += W) b.out_lits[off + i] = (int32_t)st.tget(i);   // internal literals, trail order
+                        if (lane == 0) b.sort_list[atomicAdd(b.sort_count, 1u)] = (uint32_t)item;
+                        wc.bytes += 4ull * tail;
+                    }
+                }
             }
-            __syncthreads();
+            G::sync();
+            st.template cleanup<G>(tail);
         }
+        if (lane == 0) {
+            b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
+            if (flag != FLAG_OVERFLOW) atomicAdd(&b.counters[C_MID], 1ull);
+        }
+        wc.n_ok += flag == FLAG_OK;
+        wc.n_conf += flag == FLAG_CONFLICT;
+        G::sync();
+    }
+    wc.template flush<G>(b.counters);
+}
+
+// Sorts the implied sets the second tier left unsorted in the pool (ascending internal literal = ascending
+// variable) and rewrites them as external literals. One CTA per set, in shared memory.
+constexpr int SORT_THREADS = 256;
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_sets(const BatchView b, const uint32_t cap)
+{
+    extern __shared__ uint32_t s_keys[];
+    const uint32_t count = *b.sort_count;
+    for (uint32_t e = blockIdx.x; e < count; e += gridDim.x) {
+        const uint32_t item = b.sort_list[e];
+        const uint32_t len = b.len[item] & 0x7fffffffu;
+        int32_t *set = b.out_lits + b.raw_off[item];
+        uint32_t n2 = 1;
+        while (n2 < len) n2 <<= 1;
+        for (uint32_t i = threadIdx.x; i < n2; i += SORT_THREADS) s_keys[i] = i < len ? (uint32_t)set[i] : 0xffffffffu;
+        __syncthreads();
+        for (uint32_t k = 2; k <= n2; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = threadIdx.x; t < n2 / 2; t += SORT_THREADS) {
+                    const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const uint32_t ixj = i | j;
+                    const bool up = (i & k) == 0;
+                    const uint32_t x = s_keys[i], y = s_keys[ixj];
+                    if ((x > y) == up) { s_keys[i] = y; s_keys[ixj] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t i = threadIdx.x; i < len; i += SORT_THREADS) set[i] = to_ext(s_keys[i]);
+        __syncthreads();
     }
 }
 
-// level-synchronous propagation by all warps of the CTA. ctl[0] tail, ctl[1] conflict, ctl[2] overflow.
+// ---------------------------------------------------------------- third tier: one CTA per probe, dense state
+// Probes of any size: the warps of a CTA share the per-probe state (dense 2-bit assignment + full-length trail in
+// a per-CTA slab in global memory) and walk each breadth-first level of the trail together (level-synchronous,
+// two barriers per level).
 template <class S>
-__device__ void block_propagate(const DbView &db, S &st, uint32_t *ctl, bool prune, WarpCounters &wc)
+__device__ void block_propagate(const DbView &db, S &st, uint32_t *ctl, bool prune, WorkCounters &wc)
 {
+    using G = Grp<32>;
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     BlockTail tl{ctl};
     uint32_t head = 0;
@@ -740,40 +399,29 @@ __device__ void block_propagate(const DbView &db, S &st, uint32_t *ctl, bool pru
         for (uint32_t bse = head + warp * 32; bse < level_end; bse += nwarps * 32) {
             const uint32_t B = min(32u, level_end - bse);
             const uint32_t p = lane < (int)B ? st.tget(bse + lane) : 0u;
-            if (process_batch(db, st, tl, p, B, bins_only, wc)) break;
+            if (process_batch<G>(db, st, tl, p, B, bins_only, wc)) break;
         }
         head = level_end;
     }
 }
 
-template <bool GMEM>
-__global__ void __launch_bounds__(512) k_block(const DbView db, const BatchView b, const LargeState ls, const uint32_t log_hs, const uint32_t cap)
+__global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const BatchView b, const LargeState ls)
 {
-    extern __shared__ uint32_t smem[];
+    using G = Grp<32>;
     __shared__ uint32_t ctl[8];      // 0 tail, 1 conflict, 2 overflow, 3 load result, 4 ticket, 5 vmin, 6 vmax
     __shared__ unsigned long long s_off;
-    __shared__ uint32_t s_warp[17];
+    __shared__ uint32_t s_warp[BIG_THREADS / 32 + 1];
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t *list = GMEM ? b.big_list : b.mid_list;
-    const uint32_t count = GMEM ? *b.big_count : *b.mid_count;
+    const uint32_t count = *b.big_count;
     if (blockIdx.x >= count) return;
-    unsigned int *ticket = b.ticket + (GMEM ? 2 : 1);
+    unsigned int *ticket = b.ticket + 2;
 
-    SmemBlockState ss;
     GmemState gs;
-    if (GMEM) {
-        gs.bits = ls.bits + (size_t)blockIdx.x * db.nvars_words16;
-        gs.trail = ls.trail + (size_t)blockIdx.x * ((size_t)db.max_var + 1);
-        gs.cap = (uint32_t)db.max_var + 1;
-    } else {
-        ss.hash = smem;
-        ss.trail = smem + (1u << log_hs);
-        ss.log_hs = log_hs;
-        ss.cap = cap;
-        for (uint32_t i = threadIdx.x; i < (1u << log_hs); i += blockDim.x) ss.hash[i] = 0;
-    }
+    gs.bits = ls.bits + (size_t)blockIdx.x * db.nvars_words16;
+    gs.trail = ls.trail + (size_t)blockIdx.x * ((size_t)db.max_var + 1);
+    gs.cap = (uint32_t)db.max_var + 1;
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
-    WarpCounters wc;
+    WorkCounters wc;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -786,32 +434,24 @@ __global__ void __launch_bounds__(512) k_block(const DbView db, const BatchView 
         __syncthreads();
         const uint32_t t = ctl[4];
         if (t >= count) break;
-        const uint64_t item = list[t];
+        const uint64_t item = b.big_list[t];
         const Item it = get_item(b, item);
         if (warp == 0) {
             BlockTail tl{ctl};
-            int f;
-            if (GMEM) f = it.probe_lit ? load_probe(db, gs, it.probe_lit, tl) : load_cube(db, gs, it.lits, it.n, tl);
-            else f = it.probe_lit ? load_probe(db, ss, it.probe_lit, tl) : load_cube(db, ss, it.lits, it.n, tl);
+            const int f = it.probe_lit ? load_probe<G>(db, gs, it.probe_lit, tl) : load_cube<G>(db, gs, it.lits, it.n, tl);
             if (lane == 0) ctl[3] = (uint32_t)f;
         }
         __syncthreads();
         const uint32_t f = ctl[3];
-        if (f == 0xff) {
-            if (GMEM) block_propagate(db, gs, ctl, prune, wc); else block_propagate(db, ss, ctl, prune, wc);
-        }
+        if (f == 0xff) block_propagate(db, gs, ctl, prune, wc);
         __syncthreads();
-        const uint32_t tail = min(ctl[0], GMEM ? gs.cap : ss.cap);
-        const bool overflow = ctl[2] != 0 || f == FLAG_OVERFLOW;
+        const uint32_t tail = min(ctl[0], gs.cap);
         const bool conflict = ctl[1] != 0 || f == FLAG_CONFLICT;
         uint8_t flag = (uint8_t)f;
         uint32_t len = 0;
         unsigned long long off = 0;
-        if (f == 0xff || f == FLAG_CONFLICT || f == FLAG_OVERFLOW) {
-            if (overflow && !GMEM) {
-                flag = FLAG_OVERFLOW;
-                if (threadIdx.x == 0) b.big_list[atomicAdd(b.big_count, 1u)] = (uint32_t)item;
-            } else if (conflict) {
+        if (f == 0xff || f == FLAG_CONFLICT) {
+            if (conflict) {
                 flag = FLAG_CONFLICT;
                 if (it.probe_lit && threadIdx.x == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
             } else {
@@ -824,16 +464,7 @@ __global__ void __launch_bounds__(512) k_block(const DbView db, const BatchView 
                     __syncthreads();
                     off = s_off;
                     if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
-                    else if (!GMEM) {
-                        len = tail;
-                        uint32_t n2 = 1;
-                        while (n2 < tail) n2 <<= 1;
-                        for (uint32_t i = tail + threadIdx.x; i < n2; i += blockDim.x) ss.trail[i] = 0xffffffffu;
-                        __syncthreads();
-                        if (tail > 1) block_bitonic_sort(ss.trail, n2);
-                        for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) b.out_lits[off + i] = to_ext(ss.trail[i]);
-                        wc.bytes += warp == 0 ? 4ull * tail : 0ull;
-                    } else {
+                    else {
                         // ordered emission: sweep the dense assignment between the smallest and largest assigned var
                         len = tail;
                         uint32_t vmin = 0xffffffffu, vmax = 0;
@@ -885,23 +516,19 @@ __global__ void __launch_bounds__(512) k_block(const DbView db, const BatchView 
         }
         __syncthreads();
         // leave the state empty for the next probe
-        if (GMEM) {
-            for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
-                const uint32_t var = gs.tget(i) >> 1;
-                atomicAnd(&gs.bits[var >> 4], ~(3u << ((var & 15u) * 2u)));
-            }
-        } else {
-            for (uint32_t i = threadIdx.x; i < (1u << log_hs); i += blockDim.x) ss.hash[i] = 0;
+        for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
+            const uint32_t var = gs.tget(i) >> 1;
+            atomicAnd(&gs.bits[var >> 4], ~(3u << ((var & 15u) * 2u)));
         }
         if (threadIdx.x == 0) {
             b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
-            if (flag != FLAG_OVERFLOW) atomicAdd(&b.counters[GMEM ? C_LARGE : C_MID], 1ull);
+            atomicAdd(&b.counters[C_LARGE], 1ull);
             wc.n_ok += flag == FLAG_OK;
             wc.n_conf += flag == FLAG_CONFLICT;
             wc.n_skip += flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED;
         }
     }
-    wc.flush(b.counters);
+    wc.flush<G>(b.counters);
 }
 
 // ---------------------------------------------------------------- multi-GPU merge of the bitmap slices
@@ -1222,21 +849,21 @@ __global__ void __launch_bounds__(256) k_gather_long(const BatchView b)
 
 }  // namespace
 
-size_t small_smem_bytes(uint32_t cap)
-{
-    const uint32_t hs = 2 * cap;
-    return (size_t)SMALL_WARPS * (hs + cap + cap / 2) * 4;
-}
-
 static uint32_t ilog2(uint32_t x) { uint32_t l = 0; while ((1u << l) < x) ++l; return l; }
 
-int small_blocks_per_sm(uint32_t cap)
+// first tier: (hash 2*cap + trail cap + slot indices cap/2) words per probe, SMALL_THREADS / W probes per CTA
+size_t small_smem_bytes(uint32_t cap, int width) { return (size_t)(SMALL_THREADS / width) * (2 * cap + cap + cap / 2) * 4; }
+
+template <int W> static int small_bps_w(uint32_t cap)
 {
     int nb = 0;
-    cudaFuncSetAttribute(k_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes(cap));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_deep, SMALL_WARPS * 32, small_smem_bytes(cap));
+    const size_t smem = small_smem_bytes(cap, W);
+    if (cudaFuncSetAttribute(k_deep<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_deep<W>, SMALL_THREADS, smem);
     return nb;
 }
+
+int small_blocks_per_sm(uint32_t cap, int width) { return small_bps_w<32>(cap); }
 
 void launch_triage(const BatchView &b, const DbView &db, int sm_count, cudaStream_t s)
 {
@@ -1246,33 +873,38 @@ void launch_triage(const BatchView &b, const DbView &db, int sm_count, cudaStrea
     else k_triage<TM_UNIVERSE><<<blocks, 256, 0, s>>>(db, b);
 }
 
-void launch_small(const DbView &db, const BatchView &b, uint32_t cap, int blocks, cudaStream_t s)
+void launch_small(const DbView &db, const BatchView &b, uint32_t cap, int width, int blocks, cudaStream_t s)
 {
-    const size_t smem = small_smem_bytes(cap);
-    cudaFuncSetAttribute(k_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_deep<<<blocks, SMALL_WARPS * 32, smem, s>>>(db, b, ilog2(2 * cap), cap);
+    const size_t smem = small_smem_bytes(cap, width);
+    const uint32_t lh = ilog2(2 * cap);
+    k_deep<32><<<blocks, SMALL_THREADS, smem, s>>>(db, b, lh, cap);
 }
 
-size_t mid_smem_bytes(uint32_t cap) { return (size_t)(2 * cap + cap) * 4; }
+size_t mid_slab_words_per_group(uint32_t cap) { return (size_t)2 * cap + cap; }
 
-int mid_blocks_per_sm(uint32_t cap)
+int mid_blocks_per_sm(int width)
 {
     int nb = 0;
-    cudaFuncSetAttribute(k_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem_bytes(cap));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_block<false>, MID_THREADS, mid_smem_bytes(cap));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_deep2<32>, MID2_THREADS, 0);
     return nb;
 }
 
-void launch_mid(const DbView &db, const BatchView &b, uint32_t cap, int blocks, cudaStream_t s)
+void launch_mid(const DbView &db, const BatchView &b, uint32_t *slab, uint32_t cap, int width, int blocks, cudaStream_t s)
 {
-    const size_t smem = mid_smem_bytes(cap);
-    cudaFuncSetAttribute(k_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_block<false><<<blocks, MID_THREADS, smem, s>>>(db, b, LargeState{nullptr, nullptr}, ilog2(2 * cap), cap);
+    const uint32_t lh = ilog2(2 * cap);
+    k_deep2<32><<<blocks, MID2_THREADS, 0, s>>>(db, b, slab, lh, cap);
+}
+
+void launch_sort_sets(const BatchView &b, uint32_t cap, int sm_count, cudaStream_t s)
+{
+    const size_t smem = (size_t)cap * 4;
+    cudaFuncSetAttribute(k_sort_sets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_sort_sets<<<sm_count * 4, SORT_THREADS, smem, s>>>(b, cap);
 }
 
 void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s)
 {
-    k_block<true><<<blocks, BIG_THREADS, 0, s>>>(db, b, ls, 0, 0);
+    k_big<<<blocks, BIG_THREADS, 0, s>>>(db, b, ls);
 }
 
 int scan_gather_max_blocks(int sm_count)

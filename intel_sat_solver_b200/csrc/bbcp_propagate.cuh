@@ -1,0 +1,524 @@
+// bbcp_propagate.cuh -- the propagation core shared by every tier: per-probe state, the row scan, the commit
+// of implied literals. Included by bbcp_kernels.cu only.
+//
+// A probe is owned by a group of W lanes (Grp<W>); every collective carries the group's lane mask. The engine
+// instantiates W = 32 (one warp per probe) only. W = 8 / 16 (four / two probes per warp, diverging freely) was
+// built to put more probes in flight on structured instances, whose rows keep ~10 % of a warp's lanes busy, and
+// measured on the Tseitin/BMC shape on a B200: 2.3x SLOWER at W = 8, 1.5x slower at W = 16 -- divergent groups of one
+// warp are issued one after the other, so the instruction stream per warp quadruples while the latency it was
+// meant to hide does not overlap any better -- and it showed a rare fault under divergence that full warps
+// never showed. Rejected; the template parameter stays because the code reads no worse for it.
+#pragma once
+#include "bbcp_device.cuh"
+
+#ifdef BBCP_CHECKS
+#include <cstdio>
+#define BBCP_CHECK(cond, ...) do { if (!(cond)) { printf("BBCP_CHECK failed: " #cond " | " __VA_ARGS__); __trap(); } } while (0)
+#else
+#define BBCP_CHECK(cond, ...) do { } while (0)
+#endif
+
+namespace bbcp {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int32_t to_ext(uint32_t il) { return (il & 1u) ? -(int32_t)(il >> 1) : (int32_t)(il >> 1); }
+
+template <int W>
+struct Grp {
+    static_assert(W == 8 || W == 16 || W == 32, "group width");
+    static constexpr int width = W;
+    __device__ __forceinline__ static int lane() { return threadIdx.x & (W - 1); }
+    __device__ __forceinline__ static int shift() { return (threadIdx.x & 31) & ~(W - 1); }   // first warp lane of the group
+    __device__ __forceinline__ static unsigned mask()
+    {
+        if (W == 32) return FULL;
+        return ((1u << (W & 31)) - 1u) << shift();
+    }
+    __device__ __forceinline__ static unsigned rel(unsigned warp_bits)
+    {
+        if (W == 32) return warp_bits;
+        return (warp_bits >> shift()) & ((1u << (W & 31)) - 1u);
+    }
+    template <class T> __device__ __forceinline__ static T shfl(T v, int src) { return __shfl_sync(mask(), v, src, W); }
+    template <class T> __device__ __forceinline__ static T shfl_up(T v, int d) { return __shfl_up_sync(mask(), v, d, W); }
+    template <class T> __device__ __forceinline__ static T shfl_xor(T v, int d) { return __shfl_xor_sync(mask(), v, d, W); }
+    __device__ __forceinline__ static unsigned ballot(bool p) { return rel(__ballot_sync(mask(), p)); }
+    __device__ __forceinline__ static bool any(bool p) { return __any_sync(mask(), p) != 0; }
+    __device__ __forceinline__ static unsigned match_any(uint32_t v) { return rel(__match_any_sync(mask(), v)); }
+    __device__ __forceinline__ static void sync() { __syncwarp(mask()); }
+    __device__ __forceinline__ static unsigned lt() { return (1u << lane()) - 1u; }   // group lanes below mine
+};
+
+// ---------------------------------------------------------------- per-probe state, first tier (shared memory)
+struct SmemState {
+    uint32_t *hash;    // [1 << log_hs] true literals, 0 = empty
+    uint32_t *trail;   // [cap]
+    uint16_t *tslot;   // [cap] hash slot of each trail entry (for the O(|trail|) clean-up)
+    uint32_t log_hs, cap;
+
+    __device__ __forceinline__ uint32_t h(uint32_t var) const { return (var * 0x9E3779B1u) >> (32 - log_hs); }
+    // 0 unassigned, 1 true, 2 false
+    __device__ __forceinline__ int lookup(uint32_t lit) const
+    {
+        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
+        uint32_t s = h(var);
+        for (;;) {
+            const uint32_t k = *(volatile uint32_t *)&hash[s];
+            if (k == 0) return 0;
+            if ((k >> 1) == var) return k == lit ? 1 : 2;
+            s = (s + 1) & mask;
+        }
+    }
+    // 0 newly assigned, 1 already true, 2 already false (conflict)
+    __device__ __forceinline__ int insert(uint32_t lit, uint32_t &slot)
+    {
+        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
+        uint32_t s = h(var);
+        for (;;) {
+            const uint32_t old = atomicCAS(&hash[s], 0u, lit);
+            if (old == 0) { slot = s; return 0; }
+            if ((old >> 1) == var) return old == lit ? 1 : 2;
+            s = (s + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ uint32_t tget(uint32_t i) const { return *(volatile uint32_t *)&trail[i]; }
+    __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t slot) { trail[i] = lit; tslot[i] = (uint16_t)slot; }
+    template <class G> __device__ __forceinline__ void cleanup(uint32_t tail)
+    {
+        for (uint32_t i = G::lane(); i < tail; i += G::width) hash[tslot[i]] = 0;
+        G::sync();
+    }
+    // after an overflow some table entries have no trail entry: wipe everything
+    template <class G> __device__ __forceinline__ void wipe()
+    {
+        for (uint32_t i = G::lane(); i < (1u << log_hs); i += G::width) hash[i] = 0;
+        G::sync();
+    }
+};
+
+// ---------------------------------------------------------------- per-probe state, second tier (global hash)
+// Same open-addressed set + trail, but in a per-group slab in global memory (L2-resident while hot): a probe
+// with a trail of thousands of literals still occupies one group of lanes, so hundreds of them run per SM,
+// where a shared-memory state of that size would allow four.
+struct GhashState {
+    uint32_t *hash;   // [1 << log_hs] true literals, 0 = empty
+    uint32_t *trail;  // [cap]
+    uint32_t log_hs, cap;
+
+    __device__ __forceinline__ uint32_t h(uint32_t var) const { return (var * 0x9E3779B1u) >> (32 - log_hs); }
+    __device__ __forceinline__ int lookup(uint32_t lit) const
+    {
+        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
+        uint32_t s = h(var);
+        for (;;) {
+            const uint32_t k = __ldcg(&hash[s]);
+            if (k == 0) return 0;
+            if ((k >> 1) == var) return k == lit ? 1 : 2;
+            s = (s + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ int insert(uint32_t lit, uint32_t &slot)
+    {
+        const uint32_t var = lit >> 1, mask = (1u << log_hs) - 1u;
+        uint32_t s = h(var);
+        slot = 0;
+        for (;;) {
+            const uint32_t old = atomicCAS(&hash[s], 0u, lit);
+            if (old == 0) return 0;
+            if ((old >> 1) == var) return old == lit ? 1 : 2;
+            s = (s + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ uint32_t tget(uint32_t i) const { return __ldcg(&trail[i]); }
+    __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t) { __stcg(&trail[i], lit); }
+    // leave the table empty for the next probe: short trails are removed entry by entry (slots found first, then
+    // cleared, so that no probe chain is cut while it is still needed), long ones by wiping the table
+    template <class G> __device__ __forceinline__ void cleanup(uint32_t tail)
+    {
+        const uint32_t hs = 1u << log_hs, mask = hs - 1u;
+        if (tail * 8u >= hs) { wipe<G>(); return; }
+        for (uint32_t i = G::lane(); i < tail; i += G::width) {
+            const uint32_t lit = __ldcg(&trail[i]);
+            uint32_t s = h(lit >> 1);
+            while (__ldcg(&hash[s]) != lit) s = (s + 1) & mask;
+            __stcg(&trail[i], s);
+        }
+        G::sync();
+        for (uint32_t i = G::lane(); i < tail; i += G::width) __stcg(&hash[__ldcg(&trail[i])], 0u);
+        G::sync();
+    }
+    template <class G> __device__ __forceinline__ void wipe()
+    {
+        uint4 *p = reinterpret_cast<uint4 *>(hash);
+        for (uint32_t i = G::lane(); i < (1u << log_hs) / 4; i += G::width) __stcg(&p[i], make_uint4(0, 0, 0, 0));
+        G::sync();
+    }
+};
+
+// ---------------------------------------------------------------- per-probe state, third tier (dense, global slab)
+struct GmemState {
+    uint32_t *bits;   // 2 bits per var: 1 = var true, 2 = var false
+    uint32_t *trail;
+    uint32_t cap;
+
+    __device__ __forceinline__ int lookup(uint32_t lit) const
+    {
+        const uint32_t var = lit >> 1;
+        const uint32_t o = (__ldcg(&bits[var >> 4]) >> ((var & 15u) * 2u)) & 3u;
+        if (o == 0) return 0;
+        return (o == 1u) == ((lit & 1u) == 0u) ? 1 : 2;
+    }
+    __device__ __forceinline__ int insert(uint32_t lit, uint32_t &slot)
+    {
+        const uint32_t var = lit >> 1, sh = (var & 15u) * 2u, bit = (lit & 1u) ? 2u : 1u;
+        const uint32_t o = (atomicOr(&bits[var >> 4], bit << sh) >> sh) & 3u;
+        slot = 0;
+        if (o == 0) return 0;
+        return o == bit ? 1 : 2;
+    }
+    __device__ __forceinline__ uint32_t tget(uint32_t i) const { return __ldcg(&trail[i]); }
+    __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t) { __stcg(&trail[i], lit); }
+};
+
+// per-group work counters, kept in registers (uniform over the group) and flushed once
+struct WorkCounters {
+    unsigned long long props_all = 0, props_ref = 0, slots = 0, fetches = 0, bytes = 0;
+    uint32_t n_ok = 0, n_conf = 0, n_skip = 0;
+    template <class G> __device__ void flush(unsigned long long *c)
+    {
+        if (G::lane() == 0) {
+            if (props_all) atomicAdd(&c[C_PROPS_ALL], props_all);
+            if (props_ref) atomicAdd(&c[C_PROPS_REF], props_ref);
+            if (slots) atomicAdd(&c[C_SLOTS], slots);
+            if (fetches) atomicAdd(&c[C_CLAUSE_FETCH], fetches);
+            if (bytes) atomicAdd(&c[C_BYTES], bytes);
+            if (n_ok) atomicAdd(&c[C_OK], (unsigned long long)n_ok);
+            if (n_conf) atomicAdd(&c[C_CONFLICT], (unsigned long long)n_conf);
+            if (n_skip) atomicAdd(&c[C_SKIPPED], (unsigned long long)n_skip);
+        }
+    }
+};
+
+// ---------------------------------------------------------------- where newly implied literals go
+// GroupTail: one group owns the probe, the trail tail is a register. BlockTail: the warps of a CTA share one
+// probe, the tail and the conflict / overflow latches live in shared memory.
+struct GroupTail {
+    uint32_t tail;
+    __device__ __forceinline__ uint32_t get() const { return tail; }
+    __device__ __forceinline__ bool aborted() const { return false; }
+    template <class G> __device__ __forceinline__ void latch_conflict() {}
+    // Commit one round of candidate implications (one candidate per lane, 0 = none). Group-converged.
+    // Returns 0 ok, 1 conflict, 2 state overflow.
+    template <class G, class S>
+    __device__ __forceinline__ int commit(S &st, uint32_t cand)
+    {
+        const bool has = cand != 0;
+        // same literal implied by several clauses in this step: keep the lowest lane (deterministic trail order)
+        const unsigned same = G::match_any(has ? cand : (0x80000000u | (uint32_t)G::lane()));
+        const bool leader = has && (G::lane() == __ffs(same) - 1);
+        uint32_t slot = 0;
+        const int r = leader ? st.insert(cand, slot) : 1;
+        const bool any_conf = G::any(r == 2);
+        const unsigned newm = G::ballot(leader && r == 0);
+        const uint32_t nnew = __popc(newm);
+        if (tail + nnew > st.cap) return 2;  // caller wipes the whole table: the new entries are not on the trail
+        if (leader && r == 0) st.tset(tail + __popc(newm & G::lt()), cand, slot);
+        tail += nnew;
+        return any_conf ? 1 : 0;
+    }
+};
+
+struct BlockTail {
+    uint32_t *ctl;  // shared: [0] tail, [1] conflict latch, [2] overflow latch
+    __device__ __forceinline__ uint32_t get() const { return *(volatile uint32_t *)&ctl[0]; }
+    __device__ __forceinline__ bool aborted() const { return (*(volatile uint32_t *)&ctl[1] | *(volatile uint32_t *)&ctl[2]) != 0; }
+    template <class G> __device__ __forceinline__ void latch_conflict() { if (G::lane() == 0) ctl[1] = 1; }
+    template <class G, class S>
+    __device__ __forceinline__ int commit(S &st, uint32_t cand)
+    {
+        const bool has = cand != 0;
+        const unsigned same = G::match_any(has ? cand : (0x80000000u | (uint32_t)G::lane()));
+        const bool leader = has && (G::lane() == __ffs(same) - 1);
+        uint32_t slot = 0;
+        const int r = leader ? st.insert(cand, slot) : 1;   // duplicates across warps: only one insert returns 0
+        const bool any_conf = G::any(r == 2);
+        const unsigned newm = G::ballot(leader && r == 0);
+        const uint32_t nnew = __popc(newm);
+        int ret = 0;
+        if (nnew) {
+            uint32_t pos = 0;
+            if (G::lane() == 0) pos = atomicAdd(&ctl[0], nnew);
+            pos = G::shfl(pos, 0);
+            if (pos + nnew > st.cap) { if (G::lane() == 0) ctl[2] = 1; ret = 2; }
+            else if (leader && r == 0) st.tset(pos + __popc(newm & G::lt()), cand, slot);
+        }
+        if (any_conf) { if (G::lane() == 0) ctl[1] = 1; if (!ret) ret = 1; }
+        return ret;
+    }
+};
+
+// Judge a long clause (>= 4 literals) from scratch: TopiBcp.cc:262-367 without the watch bookkeeping.
+// Returns the literal to imply (0 = none); sets confl when every literal is false.
+template <class S>
+__device__ __forceinline__ uint32_t visit_long(const DbView &db, const S &st, uint32_t cref, bool &confl, uint32_t &units16)
+{
+    BBCP_CHECK(cref >= 1 && cref < db.n_arena_units, "clause ref %u of %u\n", cref, db.n_arena_units);
+    const uint4 *cp = db.arena + cref;
+    uint4 w = __ldg(cp);
+    const uint32_t size = w.x;
+    uint32_t nfree = 0, cand = 0, i = 0;
+    bool sat = false;
+    units16 = 1;
+    uint32_t l[4] = {w.y, w.z, w.w, 0};
+    int have = 3;
+    for (;;) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < have && i < size && !sat) {
+                const int v = st.lookup(l[k]);
+                if (v == 1) sat = true;
+                else if (v == 0) { ++nfree; cand = l[k]; }
+                ++i;
+            }
+        }
+        if (sat || nfree >= 2 || i >= size) break;
+        w = __ldg(++cp);
+        ++units16;
+        l[0] = w.x; l[1] = w.y; l[2] = w.z; l[3] = w.w;
+        have = 4;
+    }
+    if (sat || nfree >= 2) return 0;
+    if (nfree == 0) { confl = true; return 0; }
+    return cand;
+}
+
+// One group scans the rows of up to W newly true literals (lane i holds literal p for i < B): one header
+// gather, then the union of the rows is flattened and walked W eight-byte slots at a time.
+// Returns 0 ok, 1 conflict, 2 overflow.
+template <class G, class S, class T>
+__device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t p, uint32_t B, bool bins_only, WorkCounters &wc)
+{
+    constexpr int W = G::width;
+    const int lane = G::lane();
+    uint4 hd = make_uint4(0, 0, 0, 0);
+    BBCP_CHECK(lane >= (int)B || (p >= 2 && p < 2u * ((uint32_t)db.max_var + 1)), "trail literal %u (B %u lane %d blk %d thr %d)\n", p, B, lane, blockIdx.x, threadIdx.x);
+    if (lane < (int)B) hd = __ldg(&db.hdr[p ^ 1u]);
+    const uint32_t nb2 = (hd.y + 1u) >> 1;
+    const uint32_t cnt = bins_only ? nb2 : nb2 + hd.z + hd.w;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < W; d <<= 1) {
+        const uint32_t t = G::shfl_up(incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t excl = incl - cnt;
+    const uint32_t total = G::shfl(incl, W - 1);
+    wc.props_all += B;
+    wc.props_ref += __popc(G::ballot((hd.y | hd.z | hd.w) != 0));
+    wc.slots += total;
+    wc.bytes += 16ull * B + 8ull * total;
+
+    for (uint32_t base = 0; base < total; base += W) {
+        const uint32_t g = base + lane;
+        const bool active = g < total;
+        // owner row of slot g: the largest lane i with excl_i <= g
+        int lo = 0;
+#pragma unroll
+        for (int step = W / 2; step; step >>= 1) {
+            const int mid = lo + step;
+            const uint32_t e = G::shfl(excl, mid & (W - 1));
+            if (mid < W && e <= g) lo = mid;
+        }
+        const uint32_t r_start = G::shfl(hd.x, lo);
+        const uint32_t r_nb2 = (G::shfl(hd.y, lo) + 1u) >> 1;
+        const uint32_t r_nt = G::shfl(hd.z, lo);
+        const uint32_t k = g - G::shfl(excl, lo);
+        uint32_t c0 = 0, c1 = 0;
+        bool confl = false;
+        uint32_t fetched16 = 0;
+        if (active) {
+            BBCP_CHECK(r_start + k < db.n_slots, "slot %u + %u of %u (lo %d total %u base %u)\n", r_start, k, db.n_slots, lo, total, base);
+            const uint2 s = __ldg(&db.slots[r_start + k]);
+            if (k < r_nb2) {
+                // binary clauses (TopiBcp.cc:207-246)
+                int v = st.lookup(s.x);
+                if (v == 0) c0 = s.x; else if (v == 2) confl = true;
+                if (s.y) {
+                    v = st.lookup(s.y);
+                    if (v == 0) c1 = s.y; else if (v == 2) confl = true;
+                }
+            } else if (k < r_nb2 + r_nt) {
+                // inline ternary clause (falsified literal, s.x, s.y)
+                const int va = st.lookup(s.x);
+                if (va != 1) {
+                    const int vb = st.lookup(s.y);
+                    if (vb != 1) {
+                        if (va == 2 && vb == 2) confl = true;
+                        else if (va == 2) c0 = s.y;
+                        else if (vb == 2) c0 = s.x;
+                    }
+                }
+            } else {
+                // long clause: cached literal first (TopiBcp.cc:255-259), then the clause itself
+                if (st.lookup(s.x) != 1) c0 = visit_long(db, st, s.y, confl, fetched16);
+            }
+        }
+        const unsigned fm = G::ballot(fetched16 != 0);
+        if (fm) {
+            uint32_t f = fetched16;
+#pragma unroll
+            for (int d = W / 2; d; d >>= 1) f += G::shfl_xor(f, d);
+            wc.fetches += __popc(fm);
+            wc.bytes += 16ull * f;
+        }
+        if (G::any(confl)) { tl.template latch_conflict<G>(); return 1; }
+        if (G::any(c0 != 0)) {
+            const int r = tl.template commit<G>(st, c0);
+            if (r) return r;
+        }
+        if (G::any(c1 != 0)) {
+            const int r = tl.template commit<G>(st, c1);
+            if (r) return r;
+        }
+        G::sync();
+        if (tl.aborted()) return 1;  // another warp of the CTA hit a conflict / overflow
+    }
+    return 0;
+}
+
+// Breadth-first unit propagation of trail[0..tail) to fixpoint by ONE group. Returns 0 fixpoint, 1 conflict, 2 overflow.
+template <class G, class S>
+__device__ int propagate(const DbView &db, S &st, GroupTail &tl, bool prune, WorkCounters &wc)
+{
+    const int lane = G::lane();
+    uint32_t head = 0;
+    while (head < tl.tail) {
+        const uint32_t B = min((uint32_t)G::width, tl.tail - head);
+        const uint32_t p = lane < (int)B ? st.tget(head + lane) : 0u;
+        // while a single literal is assigned only binary clauses can become unit
+        const int r = process_batch<G>(db, st, tl, p, B, prune && tl.tail == 1, wc);
+        if (r) return r;
+        head += B;
+    }
+    return 0;
+}
+
+// Load a cube into the (empty) state with the semantics of HandleAssumptions (Topi.cc:797-938).
+// Returns the flag to report if the cube is decided here (2,3,4 or 1), FLAG_OVERFLOW, or 0xff = propagate.
+template <class G, class S, class T>
+__device__ int load_cube(const DbView &db, S &st, const int32_t *lits, uint32_t n, T &tl)
+{
+    const int lane = G::lane();
+    bool unmapped = false, false_l0 = false, conflict = false, overflow = false;
+    for (uint32_t base = 0; base < n; base += G::width) {
+        const uint32_t i = base + lane;
+        uint32_t cand = 0;
+        if (i < n) {
+            const int32_t l = lits[i];
+            const uint32_t v = (uint32_t)(l < 0 ? -l : l);
+            if (l != 0) {
+                const uint32_t il = 2u * v + (l < 0);
+                const uint8_t li = v <= (uint32_t)db.max_var ? db.litinfo[il] : 0;
+                if (!(li & LI_MAPPED)) unmapped = true;
+                else if (li & LI_FALSE_L0) false_l0 = true;
+                else if (!(li & LI_TRUE_L0)) cand = il;
+            }
+        }
+        if (!overflow && !conflict) {
+            const int r = tl.template commit<G>(st, cand);
+            if (r == 1) conflict = true;
+            if (r == 2) overflow = true;
+        }
+        G::sync();
+    }
+    if (G::any(unmapped)) return FLAG_UNMAPPED;
+    if (G::any(false_l0)) return FLAG_FALSE_L0;
+    if (overflow) return FLAG_OVERFLOW;
+    if (conflict) return FLAG_CONFLICT;
+    if (tl.get() == 0) return FLAG_TRIVIAL_L0;
+    return 0xff;
+}
+
+// load_cube for a depth-1 probe (a single literal, no memory to read)
+template <class G, class S, class T>
+__device__ int load_probe(const DbView &db, S &st, int32_t l, T &tl)
+{
+    const uint32_t v = (uint32_t)(l < 0 ? -l : l);
+    const uint8_t li = (l != 0 && v <= (uint32_t)db.max_var) ? db.litinfo[2u * v + (l < 0)] : 0;
+    if (!(li & LI_MAPPED)) return FLAG_UNMAPPED;
+    if (li & LI_FALSE_L0) return FLAG_FALSE_L0;
+    if (li & LI_TRUE_L0) return FLAG_TRIVIAL_L0;
+    const int r = tl.template commit<G>(st, G::lane() == 0 ? 2u * v + (l < 0) : 0u);
+    G::sync();
+    return r == 2 ? FLAG_OVERFLOW : 0xff;
+}
+
+// group bitonic sort of a[0..n2) ascending, n2 a power of two (shared memory)
+template <class G>
+__device__ void bitonic_sort(uint32_t *a, uint32_t n2)
+{
+    const int lane = G::lane();
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = lane; t < n2 / 2; t += G::width) {
+                // t-th compare-exchange pair of this stage
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t ixj = i | j;
+                const bool up = (i & k) == 0;
+                const uint32_t x = a[i], y = a[ixj];
+                if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+            }
+            G::sync();
+        }
+    }
+}
+
+// allocate `count` output literals for this group (uniform); returns ~0 if the pool is full
+template <class G>
+__device__ __forceinline__ unsigned long long out_alloc(const BatchView &b, uint32_t count)
+{
+    unsigned long long base = 0;
+    if (G::lane() == 0) base = atomicAdd(b.out_cursor, (unsigned long long)count);
+    base = G::shfl(base, 0);
+    return base + count <= b.out_cap ? base : ~0ull;
+}
+
+__device__ __forceinline__ void mark_failed(const BatchView &b, uint32_t ilit)
+{
+    atomicOr(&b.failed[ilit >> 5], 1u << (ilit & 31));
+    atomicOr(&b.unit[(ilit ^ 1u) >> 5], 1u << ((ilit ^ 1u) & 31));
+}
+
+struct Item {
+    const int32_t *lits;
+    uint32_t n;
+    int32_t probe_lit;  // depth-1 item: its literal (0 otherwise)
+};
+
+__device__ __forceinline__ Item get_item(const BatchView &b, uint64_t item)
+{
+    Item it;
+    if (b.cube_off) {
+        const uint64_t o = b.cube_off[item];
+        it.lits = b.cube_lits + o;
+        it.n = (uint32_t)(b.cube_off[item + 1] - o);
+        it.probe_lit = it.n == 1 ? it.lits[0] : 0;  // a depth-1 cube is a probe
+    } else if (b.cube_lits) {
+        it.probe_lit = b.cube_lits[item];   // probe-list mode; 0 is reported as unmapped by the triage
+        it.lits = b.cube_lits + item;
+        it.n = 1;
+    } else {
+        const uint64_t idx = b.first + item;
+        const int32_t v = (int32_t)(idx / 2 + 1);
+        it.probe_lit = (idx & 1) ? -v : v;
+        it.lits = nullptr;
+        it.n = 1;
+    }
+    return it;
+}
+
+}  // namespace
+}  // namespace bbcp

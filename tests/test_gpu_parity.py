@@ -92,6 +92,10 @@ SHAPES = [
 
 @pytest.mark.parametrize("kind,kw,cubekw", SHAPES, ids=[s[0] for s in SHAPES])
 def test_synthetic_shapes_against_checker(kind, kw, cubekw):
+    _synthetic_shape(kind, kw, cubekw, 0)
+
+
+def _synthetic_shape(kind, kw, cubekw, width):
     with tempfile.TemporaryDirectory() as d:
         gkw = dict(kw)
         if cubekw:

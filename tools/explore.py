@@ -42,13 +42,13 @@ def main():
         tot_ms = 0.0
         agg = {}
         for a in range(0, limit, chunk):
-            r = t.ProbeRange(a, min(a + chunk, limit), implied=implied, fetch=False, small_trail=trail)
+            r = t.ProbeRange(a, min(a + chunk, limit), implied=implied, fetch=False, small_trail=trail, mid_trail=opt("mid", 0), kernel_times="--notimes" not in flags)
             tot_ms += r.info["total_ms"]
             for k, v in r.info.items():
                 agg[k] = agg.get(k, 0) + v
         agg["probes_per_s"] = limit / (tot_ms / 1e3)
         agg["props_per_s"] = agg["props_ref"] / (tot_ms / 1e3)
-        agg["GBps_tier1"] = agg["kernel_bytes"] / (agg["tier1_ms"] / 1e3) / 1e9
+        agg["GBps_kernels"] = agg["kernel_bytes"] / (max(agg["kernel_ms"], 1e-9) / 1e3) / 1e9
         print(f"rep{rep}", json.dumps(agg), flush=True)
     if "--check" in flags:
         stride = opt("stride", 1)
