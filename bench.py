@@ -259,10 +259,10 @@ def ours_arm(args, rank, local_rank, world):
         flush.fill_(it & 0xff)
         barrier()
         t0 = time.perf_counter()
-        rc = L.bbcp_probe_lits(h, h_lits.data_ptr(), n_local, C.byref(opts_e2e), C.byref(info))
-        assert rc == 0 and info.n_implied <= o_lits.numel()
-        L.bbcp_fetch_flags(h, o_flag.data_ptr())
-        L.bbcp_fetch_implied32(h, o_off.data_ptr(), o_lits.data_ptr())
+        # ONE call, host buffers in and out: chunks of the list are uploaded, propagated and read back overlapped
+        rc = L.bbcp_probe_lits_to_host(h, h_lits.data_ptr(), n_local, C.byref(opts_e2e), o_flag.data_ptr(), o_off.data_ptr(), o_lits.data_ptr(),
+                                       o_lits.numel(), C.byref(info))
+        assert rc == 0, eng.GetStatusExplanation()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if it >= args.warmup:

@@ -50,6 +50,8 @@ _SIGS = {
     "bbcp_error_string": (C.c_char_p, [C.c_void_p]),
     "bbcp_propagate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Opts), C.POINTER(BatchInfo)]),
     "bbcp_probe_lits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Opts), C.POINTER(BatchInfo)]),
+    "bbcp_probe_lits_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Opts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.POINTER(BatchInfo)]),
     "bbcp_probe_range": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(Opts), C.POINTER(BatchInfo)]),
     "bbcp_probe_all": (C.c_int, [C.c_void_p, C.POINTER(Opts), C.POINTER(BatchInfo)]),
     "bbcp_propagate_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(Opts), C.POINTER(BatchInfo)]),

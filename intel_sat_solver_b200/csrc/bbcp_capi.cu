@@ -80,7 +80,14 @@ struct bbcp_handle {
     uint64_t bitmap_words = 0;
     uint64_t device_db_bytes = 0;
 
-    DevBuf d_flag, d_raw_off, d_len, d_out, d_off, d_impl, d_cube_lits, d_cube_off, d_overflow, d_big, d_deep, d_chunks, d_misc, d_lbits, d_ltrail, d_tiles;
+    // results of a batch: two sets, so that the read-back of one chunk can overlap the next chunk's kernels
+    // (bbcp_probe_lits_to_host); every other entry point uses set 0
+    struct ResultSet { DevBuf flag, off, impl; } rs[2];
+    int rb = 0;
+    uint64_t off_base = 0;       // added to the offsets a batch writes (chunked calls)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[16] = {}, ev_out[2] = {};
+    DevBuf d_raw_off, d_len, d_out, d_cube_lits, d_cube_off, d_overflow, d_big, d_deep, d_chunks, d_misc, d_lbits, d_ltrail, d_tiles;
     uint32_t misc_parity = 0;
     bool last_off32 = false;
     unsigned long long *h_misc = nullptr;   // pinned, mapped
@@ -226,7 +233,11 @@ bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
     free_b += h->d_lbits.bytes + h->d_ltrail.bytes;
     h->d_lbits.release();
     h->d_ltrail.release();
-    uint64_t slabs = std::min<uint64_t>((uint64_t)h->sm_count * 2, (free_b / 4) / std::max<size_t>(per_slab, 1));
+    // one slab per resident CTA of k_big; more CTAs = more giant probes in flight (each is a serial chain of
+    // breadth-first levels), bounded by a quarter of the free memory
+    uint64_t per_sm = 8;
+    if (const char *e = getenv("BBCP_BIG_SLABS_PER_SM")) per_sm = std::max(1, atoi(e));
+    uint64_t slabs = std::min<uint64_t>((uint64_t)h->sm_count * per_sm, (free_b / 4) / std::max<size_t>(per_slab, 1));
     slabs = std::max<uint64_t>(slabs, 1);
     if (!h->d_lbits.reserve(slabs * dbv.nvars_words16 * 4, true) || !h->d_ltrail.reserve(slabs * ((size_t)dbv.max_var + 1) * 4)) return false;
     h->big_slabs = (uint32_t)slabs;
@@ -256,7 +267,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     h->have_batch = false;
 
     const size_t n1 = (size_t)n + 1;
-    if (!h->d_flag.reserve(n1) || !h->d_raw_off.reserve(n1 * 8) || !h->d_len.reserve(n1 * 4 + 64) || !h->d_off.reserve(n1 * 8) ||
+    if (!h->rs[h->rb].flag.reserve(n1) || !h->d_raw_off.reserve(n1 * 8) || !h->d_len.reserve(n1 * 4 + 64) || !h->rs[h->rb].off.reserve(n1 * 8) ||
         !h->d_overflow.reserve(n1 * 4) || !h->d_big.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_tiles.reserve(((size_t)h->sg_blocks + 4) * 8))
         return h->fail(BBCP_ERR_ALLOC, "device allocation failed (batch buffers)");
 
@@ -281,7 +292,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.cube_off = d_off;
     b.first = first;
     b.n = n;
-    b.flag = h->d_flag.as<uint8_t>();
+    b.flag = h->rs[h->rb].flag.as<uint8_t>();
     b.raw_off = h->d_raw_off.as<uint64_t>();
     b.len = h->d_len.as<uint32_t>();
     b.failed = h->failed_p();
@@ -289,7 +300,8 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.mid_list = h->d_overflow.as<uint32_t>();
     b.big_list = h->d_big.as<uint32_t>();
     b.deep_list = h->d_deep.as<uint32_t>();
-    b.off = h->d_off.p;
+    b.off = h->rs[h->rb].off.p;
+    b.off_base = h->off_base;
     b.tile_state = h->d_tiles.as<unsigned long long>();
     b.zero_words = MISC_WORDS64;
     b.opts = opts.flags;
@@ -316,11 +328,11 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     cudaEventRecord(h->ev[0], h->stream);
     for (int attempt = 0;; ++attempt) {
         // room for every self-implying probe (n) plus out_cap stored literals
-        if (!h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4) || (implied && !h->d_impl.reserve((n + out_cap + 4) * 4)) ||
+        if (!h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4) || (implied && !h->rs[h->rb].impl.reserve((n + out_cap + 4) * 4)) ||
             !h->d_chunks.reserve((out_cap / 2048 + out_cap / 16384 + 64) * 8))   // sets above 16384 literals, 2048 per chunk, rounded up per set
             return h->fail(BBCP_ERR_ALLOC, "device allocation failed (implied literals)");
         b.out_lits = h->d_out.as<int32_t>();
-        b.impl = h->d_impl.as<int32_t>();
+        b.impl = h->rs[h->rb].impl.as<int32_t>();
         b.chunk_list = h->d_chunks.as<uint2>();
         b.out_cap = out_cap;
         // counter block of this launch sequence (zeroed by the previous sequence's triage, or at creation)
@@ -362,7 +374,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         } else {
             // empty batch: nothing ran, but the next sequence still needs a zeroed counter block
             cudaMemsetAsync(b.zero_next, 0, MISC_WORDS64 * 8, h->stream);
-            cudaMemsetAsync(h->d_off.p, 0, 8, h->stream);
+            cudaMemsetAsync(h->rs[h->rb].off.p, 0, 8, h->stream);
         }
         if (!zero_copy) cudaMemcpyAsync(h->h_misc, misc, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
         cudaEventRecord(h->ev[2], h->stream);
@@ -426,7 +438,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         if (attempt == 7) return h->fail(BBCP_ERR_ALLOC, "implied-literal buffer keeps overflowing");
     }
     if (!implied || n == 0) {
-        if (!implied) cudaMemsetAsync(h->d_off.p, 0, n1 * 8, h->stream);
+        if (!implied) cudaMemsetAsync(h->rs[h->rb].off.p, 0, n1 * 8, h->stream);
         if (do_merge) {
             // flags-only or empty batch: no compaction kernel to ride in, the merge is its own launch
             cudaEventRecord(h->ev_merge[0], h->stream);
@@ -507,11 +519,15 @@ void bbcp_release(bbcp_handle *h)
         cudaStreamSynchronize(h->stream);
         bbcp_peer_detach(h);
         for (auto &e : h->ev_merge) if (e) cudaEventDestroy(e);
-        for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_bitmaps, &h->d_peer_tab, &h->d_flag, &h->d_raw_off, &h->d_len,
-                          &h->d_out, &h->d_off, &h->d_impl, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_big, &h->d_deep, &h->d_chunks, &h->d_misc, &h->d_lbits,
+        for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_bitmaps, &h->d_peer_tab, &h->rs[0].flag, &h->rs[0].off, &h->rs[0].impl, &h->rs[1].flag, &h->rs[1].off, &h->rs[1].impl, &h->d_raw_off, &h->d_len,
+                          &h->d_out, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_big, &h->d_deep, &h->d_chunks, &h->d_misc, &h->d_lbits,
                           &h->d_ltrail, &h->d_tiles, &h->d_mid_slab})
             b->release();
         if (h->h_misc) cudaFreeHost(h->h_misc);
+        for (auto &e : h->ev_in) if (e) cudaEventDestroy(e);
+        for (auto &e : h->ev_out) if (e) cudaEventDestroy(e);
+        if (h->s_in) cudaStreamDestroy(h->s_in);
+        if (h->s_out) cudaStreamDestroy(h->s_out);
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
         if (h->stream) cudaStreamDestroy(h->stream);
     }
@@ -727,6 +743,82 @@ int bbcp_probe_lits(bbcp_handle *h, const int32_t *lits, uint64_t n, const bbcp_
     return run_batch(h, h->d_cube_lits.as<int32_t>(), nullptr, 0, n, opts, info);
 }
 
+int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, const bbcp_opts *uopts, uint8_t *flag_out, void *off_out,
+                            int32_t *impl_out, uint64_t impl_cap, bbcp_batch_info *info)
+{
+    int rc = need_final(h);
+    if (rc) return rc;
+    if ((!lits && n) || !flag_out || !off_out || (!impl_out && impl_cap)) return h->fail(BBCP_ERR_ARG, "bbcp_probe_lits_to_host: null buffer");
+    cudaSetDevice(h->device);
+    bbcp_opts opts;
+    memset(&opts, 0, sizeof(opts));
+    opts.flags = BBCP_OPT_IMPLIED;
+    if (uopts) opts = *uopts;
+    opts.flags |= BBCP_OPT_IMPLIED;
+    opts.flags &= ~(uint32_t)(BBCP_OPT_MERGE | BBCP_OPT_RENDEZVOUS);
+    const bool off32 = (opts.flags & BBCP_OPT_OFF32) != 0;
+    const size_t osz = off32 ? 4 : 8;
+    // chunks: whole compaction tiles, at most 16 of them, not smaller than 512 K probes (every chunk pays the fixed
+    // ~40 us of a batch; the chunks' kernel time line must stay shorter than the read-back it hides behind)
+    uint64_t nchunks = std::min<uint64_t>(16, std::max<uint64_t>(1, n / (512 * 1024)));
+    if (const char *e = getenv("BBCP_CHUNKS")) nchunks = std::min<uint64_t>(16, std::max<uint64_t>(1, (uint64_t)atoi(e)));
+    uint64_t csize = ((n + nchunks - 1) / nchunks + SG_TILE - 1) / SG_TILE * SG_TILE;
+    if (csize == 0) csize = SG_TILE;
+    nchunks = std::max<uint64_t>(1, (n + csize - 1) / csize);
+    if (!h->s_in) {
+        if (!h->cuda_ok(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking), "cudaStreamCreate") ||
+            !h->cuda_ok(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking), "cudaStreamCreate")) return BBCP_ERR_CUDA;
+        for (auto &e : h->ev_in) if (!h->cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return BBCP_ERR_CUDA;
+        for (auto &e : h->ev_out) if (!h->cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return BBCP_ERR_CUDA;
+    }
+    if (!h->d_cube_lits.reserve(std::max<uint64_t>(n, 4) * 4)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (probe list)");
+    // all input chunks go out at once on their own stream; each batch waits for its chunk only
+    for (uint64_t k = 0; k < nchunks; ++k) {
+        const uint64_t lo = k * csize, cnt = std::min(csize, n - lo);
+        cudaMemcpyAsync(h->d_cube_lits.as<int32_t>() + lo, lits + lo, cnt * 4, cudaMemcpyHostToDevice, h->s_in);
+        cudaEventRecord(h->ev_in[k], h->s_in);
+    }
+    bbcp_batch_info tot;
+    memset(&tot, 0, sizeof(tot));
+    uint64_t base = 0;
+    int ret = BBCP_OK;
+    for (uint64_t k = 0; k < nchunks && ret == BBCP_OK; ++k) {
+        const uint64_t lo = k * csize, cnt = std::min(csize, n - lo);
+        h->rb = (int)(k & 1);
+        h->off_base = base;
+        if (k >= 2) cudaStreamWaitEvent(h->stream, h->ev_out[k & 1], 0);   // this result set is still being read back
+        cudaStreamWaitEvent(h->stream, h->ev_in[k], 0);
+        bbcp_batch_info bi;
+        ret = run_batch(h, h->d_cube_lits.as<int32_t>() + lo, nullptr, 0, cnt, &opts, &bi);
+        if (ret != BBCP_OK) break;
+        if (base + bi.n_implied > impl_cap) { ret = h->fail(BBCP_ERR_ARG, "bbcp_probe_lits_to_host: implied-literal buffer too small"); break; }
+        // the batch is complete (run_batch synchronises): its results leave on the output stream while the next
+        // chunk computes into the other result set
+        cudaMemcpyAsync(flag_out + lo, h->rs[h->rb].flag.p, cnt, cudaMemcpyDeviceToHost, h->s_out);
+        cudaMemcpyAsync(static_cast<char *>(off_out) + lo * osz, h->rs[h->rb].off.p, cnt * osz, cudaMemcpyDeviceToHost, h->s_out);
+        if (bi.n_implied) cudaMemcpyAsync(impl_out + base, h->rs[h->rb].impl.p, bi.n_implied * 4, cudaMemcpyDeviceToHost, h->s_out);
+        cudaEventRecord(h->ev_out[k & 1], h->s_out);
+        base += bi.n_implied;
+        tot.n += bi.n; tot.n_implied += bi.n_implied; tot.n_ok += bi.n_ok; tot.n_conflict += bi.n_conflict; tot.n_skipped += bi.n_skipped;
+        tot.n_large += bi.n_large; tot.n_mid += bi.n_mid; tot.props_all += bi.props_all; tot.props_ref += bi.props_ref; tot.slots += bi.slots;
+        tot.clause_fetches += bi.clause_fetches; tot.kernel_bytes += bi.kernel_bytes; tot.triage_bytes += bi.triage_bytes; tot.n_deep += bi.n_deep;
+        tot.kernel_ms += bi.kernel_ms; tot.total_ms += bi.total_ms; tot.launches += bi.launches; tot.triage_ms += bi.triage_ms;
+        tot.deep_ms += bi.deep_ms; tot.block_ms += bi.block_ms; tot.mid_ms += bi.mid_ms; tot.compact_ms += bi.compact_ms; tot.tier1_ms += bi.tier1_ms;
+    }
+    h->rb = 0;
+    h->off_base = 0;
+    h->have_batch = false;   // the results are in the caller's buffers, not in one device-side batch
+    const bool ok = h->cuda_ok(cudaStreamSynchronize(h->s_out), "result read-back") && h->cuda_ok(cudaStreamSynchronize(h->s_in), "probe upload");
+    if (ret != BBCP_OK) return ret;
+    if (!ok) return BBCP_ERR_CUDA;
+    if (off32) {
+        if (base > 0xffffffffull) return h->fail(BBCP_ERR_ARG, "BBCP_OPT_OFF32: more than 2^32-1 implied literals");
+        static_cast<uint32_t *>(off_out)[n] = (uint32_t)base;
+    } else static_cast<uint64_t *>(off_out)[n] = base;
+    if (info) *info = tot;
+    return BBCP_OK;
+}
+
 int bbcp_probe_range(bbcp_handle *h, uint64_t first, uint64_t last, const bbcp_opts *opts, bbcp_batch_info *info)
 {
     int rc = need_final(h);
@@ -747,7 +839,7 @@ int bbcp_fetch_flags(bbcp_handle *h, uint8_t *flag)
 {
     if (!h || !h->have_batch) return h ? h->fail(BBCP_ERR_STATE, "no batch results") : BBCP_ERR_ARG;
     cudaSetDevice(h->device);
-    if (h->last_n && !h->cuda_ok(cudaMemcpyAsync(flag, h->d_flag.p, h->last_n, cudaMemcpyDeviceToHost, h->stream), "fetch flags")) return BBCP_ERR_CUDA;
+    if (h->last_n && !h->cuda_ok(cudaMemcpyAsync(flag, h->rs[h->rb].flag.p, h->last_n, cudaMemcpyDeviceToHost, h->stream), "fetch flags")) return BBCP_ERR_CUDA;
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "fetch flags") ? BBCP_OK : BBCP_ERR_CUDA;
 }
 
@@ -756,8 +848,8 @@ int bbcp_fetch_implied32(bbcp_handle *h, uint32_t *impl_off, int32_t *impl_lits)
     if (!h || !h->have_batch) return h ? h->fail(BBCP_ERR_STATE, "no batch results") : BBCP_ERR_ARG;
     if (!h->last_off32) return h->fail(BBCP_ERR_STATE, "the last batch was not run with BBCP_OPT_OFF32");
     cudaSetDevice(h->device);
-    if (!h->cuda_ok(cudaMemcpyAsync(impl_off, h->d_off.p, (h->last_n + 1) * 4, cudaMemcpyDeviceToHost, h->stream), "fetch offsets")) return BBCP_ERR_CUDA;
-    if (h->last_n_implied && !h->cuda_ok(cudaMemcpyAsync(impl_lits, h->d_impl.p, h->last_n_implied * 4, cudaMemcpyDeviceToHost, h->stream), "fetch implied")) return BBCP_ERR_CUDA;
+    if (!h->cuda_ok(cudaMemcpyAsync(impl_off, h->rs[h->rb].off.p, (h->last_n + 1) * 4, cudaMemcpyDeviceToHost, h->stream), "fetch offsets")) return BBCP_ERR_CUDA;
+    if (h->last_n_implied && !h->cuda_ok(cudaMemcpyAsync(impl_lits, h->rs[h->rb].impl.p, h->last_n_implied * 4, cudaMemcpyDeviceToHost, h->stream), "fetch implied")) return BBCP_ERR_CUDA;
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "fetch implied") ? BBCP_OK : BBCP_ERR_CUDA;
 }
 
@@ -766,8 +858,8 @@ int bbcp_fetch_implied(bbcp_handle *h, uint64_t *impl_off, int32_t *impl_lits)
     if (!h || !h->have_batch) return h ? h->fail(BBCP_ERR_STATE, "no batch results") : BBCP_ERR_ARG;
     if (h->last_off32) return h->fail(BBCP_ERR_STATE, "the last batch was run with BBCP_OPT_OFF32: use bbcp_fetch_implied32");
     cudaSetDevice(h->device);
-    if (!h->cuda_ok(cudaMemcpyAsync(impl_off, h->d_off.p, (h->last_n + 1) * 8, cudaMemcpyDeviceToHost, h->stream), "fetch offsets")) return BBCP_ERR_CUDA;
-    if (h->last_n_implied && !h->cuda_ok(cudaMemcpyAsync(impl_lits, h->d_impl.p, h->last_n_implied * 4, cudaMemcpyDeviceToHost, h->stream), "fetch implied")) return BBCP_ERR_CUDA;
+    if (!h->cuda_ok(cudaMemcpyAsync(impl_off, h->rs[h->rb].off.p, (h->last_n + 1) * 8, cudaMemcpyDeviceToHost, h->stream), "fetch offsets")) return BBCP_ERR_CUDA;
+    if (h->last_n_implied && !h->cuda_ok(cudaMemcpyAsync(impl_lits, h->rs[h->rb].impl.p, h->last_n_implied * 4, cudaMemcpyDeviceToHost, h->stream), "fetch implied")) return BBCP_ERR_CUDA;
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "fetch implied") ? BBCP_OK : BBCP_ERR_CUDA;
 }
 
@@ -794,9 +886,9 @@ int bbcp_clear_bitmaps(bbcp_handle *h)
 
 void *bbcp_device_failed_bitmap(bbcp_handle *h) { return h ? h->failed_p() : nullptr; }
 void *bbcp_device_unit_bitmap(bbcp_handle *h) { return h ? h->unit_p() : nullptr; }
-void *bbcp_device_flags(bbcp_handle *h) { return h && h->have_batch ? h->d_flag.p : nullptr; }
-void *bbcp_device_impl_off(bbcp_handle *h) { return h && h->have_batch ? h->d_off.p : nullptr; }
-void *bbcp_device_impl_lits(bbcp_handle *h) { return h && h->have_batch ? h->d_impl.p : nullptr; }
+void *bbcp_device_flags(bbcp_handle *h) { return h && h->have_batch ? h->rs[h->rb].flag.p : nullptr; }
+void *bbcp_device_impl_off(bbcp_handle *h) { return h && h->have_batch ? h->rs[h->rb].off.p : nullptr; }
+void *bbcp_device_impl_lits(bbcp_handle *h) { return h && h->have_batch ? h->rs[h->rb].impl.p : nullptr; }
 void *bbcp_stream(bbcp_handle *h) { return h ? (void *)h->stream : nullptr; }
 int bbcp_sync(bbcp_handle *h)
 {

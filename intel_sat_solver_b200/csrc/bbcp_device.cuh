@@ -61,6 +61,7 @@ struct BatchView {
     uint32_t *chunk_count;
     // result compaction (k_scan_gather): canonical CSR offsets + literals
     void *off;                  // [n+1] u64, or u32 with OPT_OFF32
+    unsigned long long off_base;   // added to every offset written (chunked batches that share one literal array)
     int32_t *impl;              // implied literals in item order
     unsigned long long *tile_state;   // per-CTA segment sums of k_scan_gather
     uint32_t *tile_ticket;            // its grid barrier word (zero before the launch)
@@ -106,6 +107,6 @@ struct MergeArgs {
 void launch_merge(const MergeArgs &m, int sm_count, cudaStream_t s);
 constexpr int SMALL_THREADS = 128;  // first tier: SMALL_THREADS / W probes in flight per CTA (W lanes per probe)
 constexpr int MID2_THREADS = 256;   // second tier: MID2_THREADS / W probes per CTA, state in a global slab
-constexpr int BIG_THREADS = 512;   // third tier: 16 warps share one probe, state in a global slab
+constexpr int BIG_THREADS = 256;   // third tier: 8 warps share one probe, state in a global slab
 
 }  // namespace bbcp

@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
     for (int k = 0; k < SG_THREADS / 32; ++k) run += s_red[k];
     if (blockIdx.x == gridDim.x - 1 && lo >= hi && tid == 0) {
         // degenerate tail (n == 0, or n a multiple of seg with spare CTAs): the last CTA still owes off[n]
-        if (off32) ((uint32_t *)b.off)[n] = (uint32_t)run; else ((uint64_t *)b.off)[n] = run;
+        if (off32) ((uint32_t *)b.off)[n] = (uint32_t)(run + b.off_base); else ((uint64_t *)b.off)[n] = run + b.off_base;
         *b.total = run;
     }
 
@@ -755,11 +755,13 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
 #pragma unroll
         for (int j = 0; j < SG_ITEMS; ++j) {
             o[j] += wrun;
-            if ((uint32_t)(j * 32 + lane) < nvalid) { if (OFF32) ((uint32_t *)b.off)[wbase + j * 32] = (uint32_t)o[j]; else ((uint64_t *)b.off)[wbase + j * 32] = o[j]; }
+            if ((uint32_t)(j * 32 + lane) < nvalid) {
+                if (OFF32) ((uint32_t *)b.off)[wbase + j * 32] = (uint32_t)(o[j] + b.off_base); else ((uint64_t *)b.off)[wbase + j * 32] = o[j] + b.off_base;
+            }
         }
         run += agg;
         if (cbase + SG_TILE >= hi && hi == n && tid == 0) {   // the step that holds the last item: off[n], total
-            if (OFF32) ((uint32_t *)b.off)[n] = (uint32_t)run; else ((uint64_t *)b.off)[n] = run;
+            if (OFF32) ((uint32_t *)b.off)[n] = (uint32_t)(run + b.off_base); else ((uint64_t *)b.off)[n] = run + b.off_base;
             *b.total = run;
         }
         // literals
@@ -836,7 +838,7 @@ __global__ void __launch_bounds__(256) k_gather_long(const BatchView b)
     for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const uint2 e = b.chunk_list[c];
         const uint32_t len = b.len[e.x] & 0x7fffffffu;
-        const uint64_t o = off32 ? (uint64_t)((const uint32_t *)b.off)[e.x] : ((const uint64_t *)b.off)[e.x];
+        const uint64_t o = (off32 ? (uint64_t)((const uint32_t *)b.off)[e.x] : ((const uint64_t *)b.off)[e.x]) - (off32 ? (uint64_t)(uint32_t)b.off_base : b.off_base);
         const uint64_t src = b.raw_off[e.x] + (uint64_t)e.y * GATHER_CHUNK, d = o + (uint64_t)e.y * GATHER_CHUNK;
         const uint32_t m = min(GATHER_CHUNK, len - e.y * GATHER_CHUNK);
 #pragma unroll

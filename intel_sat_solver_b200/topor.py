@@ -166,6 +166,22 @@ class BatchedTopor:
     def ProbeAll(self, implied=True, fetch=True, **kw) -> BatchResult:
         return self.ProbeRange(0, 2 * self.max_var, implied=implied, fetch=fetch, **kw)
 
+    def ProbeLitsToHost(self, lits, impl_cap=None, flag_out=None, off_out=None, impl_out=None, **kw) -> BatchResult:
+        """Pipelined form of ProbeLits + fetch (bbcp_probe_lits_to_host): upload, kernels and read-back of successive
+        chunks overlap. Output arrays may be passed in (e.g. views of pinned memory); impl_cap = literals they hold."""
+        a = np.ascontiguousarray(lits, dtype=np.int32)
+        off32 = kw.get("off32", False)
+        n = a.size
+        flag_out = np.empty(n, dtype=np.uint8) if flag_out is None else flag_out
+        off_out = np.empty(n + 1, dtype=np.uint32 if off32 else np.uint64) if off_out is None else off_out
+        if impl_out is None:
+            impl_out = np.empty(max(int(impl_cap if impl_cap is not None else 4 * n + 1024), 1), dtype=np.int32)
+        info = BatchInfo()
+        o = self._opts(implied=True, **kw)
+        self._check(self._L.bbcp_probe_lits_to_host(self._h, a.ctypes.data if n else None, n, C.byref(o), flag_out.ctypes.data, off_out.ctypes.data,
+                                                    impl_out.ctypes.data, impl_out.size, C.byref(info)))
+        return BatchResult(info.as_dict(), flag_out[:n], off_out[: n + 1], impl_out[: info.n_implied])
+
     def PropagateBatch(self, cube_lits, cube_off, implied=True, fetch=True, **kw) -> BatchResult:
         lits = np.ascontiguousarray(cube_lits, dtype=np.int32)
         off = np.ascontiguousarray(cube_off, dtype=np.uint64)

@@ -274,3 +274,37 @@ def test_large_batch_scan_and_giant_sets():
                 assert res.flag[k] == 4 and sizes[k] == 0
         assert res.info["n_large"] > 0 and res.info["n_mid"] > 0
         assert int(res.impl_off[-1]) == res.info["n_implied"] == int(sizes.sum())
+
+
+def test_pipelined_host_call_matches_plain_call():
+    """bbcp_probe_lits_to_host (chunked, upload / kernels / read-back overlapped, two result sets) against
+    bbcp_probe_lits + fetch on an instance big enough for several chunks, and against the goldens on small ones."""
+    with tempfile.TemporaryDirectory() as d:
+        inst, _ = gpu_util.gen("comm", d, n=300000, m=1200000, comms=300, seed=11)
+        t, rc = engine_for(fileio.read_bcnf(inst))
+        assert rc == 0
+        n = 2 * t.max_var
+        rng = np.random.default_rng(5)
+        idx = rng.permutation(n)
+        lits = np.where(idx & 1, -(idx // 2 + 1), idx // 2 + 1).astype(np.int32)
+        ref = t.ProbeLits(lits)
+        for off32 in (False, True):
+            res = t.ProbeLitsToHost(lits, impl_cap=int(ref.info["n_implied"]), off32=off32)
+            assert res.info["n"] == n and res.info["launches"] > 3     # more than one chunk
+            assert np.array_equal(res.flag, ref.flag)
+            assert np.array_equal(res.impl_off.astype(np.uint64), ref.impl_off)
+            assert np.array_equal(res.impl_lits, ref.impl_lits)
+        # a buffer that is too small is refused
+        with pytest.raises(Exception):
+            t.ProbeLitsToHost(lits, impl_cap=int(ref.info["n_implied"]) - 1)
+        assert not t.IsError()
+    g = np.load(os.path.join(gpu_util.ROOT, "tests", "golden", "golden.npz"))
+    for name in ["fuzz_10", "regr_47"]:
+        t, _ = engine_for(g[f"{name}/words"])
+        n = 2 * t.max_var
+        idx = np.arange(n)
+        lits = np.where(idx & 1, -(idx // 2 + 1), idx // 2 + 1).astype(np.int32)
+        res = t.ProbeLitsToHost(lits)
+        gpu_util.assert_same_results(res, g[f"{name}/probe_flag"], g[f"{name}/probe_off"], g[f"{name}/probe_lits"], name)
+        empty = t.ProbeLitsToHost(np.zeros(0, dtype=np.int32))
+        assert empty.impl_off.tolist() == [0]
