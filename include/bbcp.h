@@ -156,6 +156,12 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
 int bbcp_propagate_batch_device(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint64_t ncubes,
                                 uint64_t nlits, const bbcp_opts *opts, bbcp_batch_info *info);
 
+/* failed-literal probing to a fixpoint ("next" row N2 of the survey): probe all literals, add the negations of the
+ * failed literals as unit clauses, re-finalize (level-0 propagation + database simplification), repeat until a
+ * pass finds none (max_rounds == 0: no limit). Returns BBCP_OK, or BBCP_CONTRADICTORY if the units refute the
+ * instance. *rounds = passes run, *units = failed literals turned into units; bbcp_level0_lits has the result. */
+int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds, uint64_t *units);
+
 /* ---- results of the last batch, device -> caller buffers */
 int bbcp_fetch_flags(bbcp_handle *h, uint8_t *flag /* n */);
 int bbcp_fetch_implied(bbcp_handle *h, uint64_t *impl_off /* n+1 */, int32_t *impl_lits /* n_implied */);

@@ -130,6 +130,11 @@ public:
         if (r.rc == BBCP_OK && fetch) Fetch(r, implied);
         return r;
     }
+    // failed-literal probing with unit feedback to a fixpoint; BBCP_OK or BBCP_CONTRADICTORY
+    int ProbeToFixpoint(uint32_t maxRounds = 0, uint32_t *rounds = nullptr, uint64_t *units = nullptr)
+    {
+        return m_H ? bbcp_probe_to_fixpoint(m_H, maxRounds, rounds, units) : BBCP_ERR_ALLOC;
+    }
     // external literals whose depth-1 probe hit a conflict so far (ascending |var|, positive first)
     std::vector<int32_t> FailedLiterals()
     {

@@ -835,6 +835,49 @@ int bbcp_probe_all(bbcp_handle *h, const bbcp_opts *opts, bbcp_batch_info *info)
     return bbcp_probe_range(h, 0, 2ull * (uint64_t)h->db.max_var, opts, info);
 }
 
+// Failed-literal probing to a fixpoint: probe every literal, add the negation of every failed literal as a unit
+// clause, re-finalize (level-0 propagation + simplification of the database), repeat until a pass finds no new
+// failed literal. What the units would do inside the reference: each is an Assign at level 0 followed by BCP
+// (Topi.cc:1311-1333), and the satisfied clauses / false literals go away in SimplifyIfRequired
+// (TopiCompression.cc:509-640).
+int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds_out, uint64_t *units_out)
+{
+    if (rounds_out) *rounds_out = 0;
+    if (units_out) *units_out = 0;
+    if (!h) return BBCP_ERR_ARG;
+    if (h->status == BBCP_OK && !h->finalized) bbcp_finalize(h);
+    int rc = need_final(h);
+    if (rc) return rc;
+    uint64_t total_units = 0;
+    uint32_t round = 0;
+    std::vector<uint32_t> unit;
+    for (; max_rounds == 0 || round < max_rounds; ++round) {
+        bbcp_opts o;
+        memset(&o, 0, sizeof(o));   // flags and bitmaps only
+        if ((rc = bbcp_clear_bitmaps(h)) != BBCP_OK) return rc;
+        if ((rc = bbcp_probe_all(h, &o, nullptr)) != BBCP_OK) return rc;
+        unit.assign(bbcp_bitmap_words(h), 0);
+        if ((rc = bbcp_fetch_bitmaps(h, nullptr, unit.data())) != BBCP_OK) return rc;
+        uint64_t found = 0;
+        for (size_t w = 0; w < unit.size(); ++w)
+            for (uint32_t m = unit[w]; m; m &= m - 1) {
+                const uint32_t il = (uint32_t)(w * 32) + (uint32_t)__builtin_ctz(m);
+                const int32_t ext[2] = {(il & 1) ? -(int32_t)(il >> 1) : (int32_t)(il >> 1), 0};
+                h->db.add_words(ext, 2);
+                ++found;
+            }
+        if (rounds_out) *rounds_out = round + 1;
+        if (!found) break;
+        total_units += found;
+        if (units_out) *units_out = total_units;
+        h->finalized = false;
+        h->prepared = false;
+        rc = bbcp_finalize(h);
+        if (rc != BBCP_OK) return rc;   // BBCP_CONTRADICTORY: x and not-x both failed, or the units propagate to a conflict
+    }
+    return BBCP_OK;
+}
+
 int bbcp_fetch_flags(bbcp_handle *h, uint8_t *flag)
 {
     if (!h || !h->have_batch) return h ? h->fail(BBCP_ERR_STATE, "no batch results") : BBCP_ERR_ARG;

@@ -192,6 +192,13 @@ class BatchedTopor:
         self._check(self._L.bbcp_propagate_batch(self._h, lits.ctypes.data, off.ctypes.data, off.size - 1, C.byref(o), C.byref(info)))
         return self._fetch(info, implied, fetch, kw.get("off32", False))
 
+    def ProbeToFixpoint(self, max_rounds: int = 0) -> dict:
+        """Failed-literal probing with unit feedback until a pass finds no new failed literal (bbcp_probe_to_fixpoint).
+        Returns {"status": 0 | 1 (contradictory), "rounds": passes run, "units": failed literals turned into units}."""
+        rounds, units = C.c_uint32(0), C.c_uint64(0)
+        rc = self._check(self._L.bbcp_probe_to_fixpoint(self._h, int(max_rounds), C.byref(rounds), C.byref(units)))
+        return {"status": rc, "rounds": rounds.value, "units": units.value}
+
     def Bitmaps(self) -> tuple[np.ndarray, np.ndarray]:
         n = self._L.bbcp_bitmap_words(self._h)
         failed, unit = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)

@@ -288,9 +288,10 @@ def test_pipelined_host_call_matches_plain_call():
         idx = rng.permutation(n)
         lits = np.where(idx & 1, -(idx // 2 + 1), idx // 2 + 1).astype(np.int32)
         ref = t.ProbeLits(lits)
+        os.environ["BBCP_CHUNKS"] = "5"    # (the default keeps chunks above 512 K probes; force several here)
         for off32 in (False, True):
             res = t.ProbeLitsToHost(lits, impl_cap=int(ref.info["n_implied"]), off32=off32)
-            assert res.info["n"] == n and res.info["launches"] > 3     # more than one chunk
+            assert res.info["n"] == n and res.info["launches"] >= 15     # five chunks
             assert np.array_equal(res.flag, ref.flag)
             assert np.array_equal(res.impl_off.astype(np.uint64), ref.impl_off)
             assert np.array_equal(res.impl_lits, ref.impl_lits)
@@ -298,6 +299,7 @@ def test_pipelined_host_call_matches_plain_call():
         with pytest.raises(Exception):
             t.ProbeLitsToHost(lits, impl_cap=int(ref.info["n_implied"]) - 1)
         assert not t.IsError()
+        del os.environ["BBCP_CHUNKS"]
     g = np.load(os.path.join(gpu_util.ROOT, "tests", "golden", "golden.npz"))
     for name in ["fuzz_10", "regr_47"]:
         t, _ = engine_for(g[f"{name}/words"])
@@ -308,3 +310,43 @@ def test_pipelined_host_call_matches_plain_call():
         gpu_util.assert_same_results(res, g[f"{name}/probe_flag"], g[f"{name}/probe_off"], g[f"{name}/probe_lits"], name)
         empty = t.ProbeLitsToHost(np.zeros(0, dtype=np.int32))
         assert empty.impl_off.tolist() == [0]
+
+
+def test_probe_to_fixpoint_matches_checker_rounds(golden):
+    """Unit-feedback rounds (survey 'next' row N2): probe all, add the negations of the failed literals as units,
+    re-finalize, repeat. The same loop driven through the CPU checker gives the same number of rounds, the same
+    number of units and the same final level-0 assignment (or the same refutation)."""
+    from oracle_lib import Oracle
+    seen_multi = False
+    for name in ["fuzz_10", "fuzz_5", "fuzz_3", "fuzz_7", "regr_47", "regr_72", "regr_20"]:
+        words = golden[f"{name}/words"]
+        t, rc = engine_for(words)
+        assert rc == 0
+        got = t.ProbeToFixpoint()
+        # checker loop
+        w = words.copy()
+        rounds = units = 0
+        status = 0
+        while True:
+            o = Oracle(w)
+            if o.status:
+                status = 1
+                break
+            flag, _, _, _ = o.run()
+            rounds += 1
+            idx = np.nonzero(flag == 1)[0]
+            if idx.size == 0:
+                level0 = o.level0()
+                break
+            units += idx.size
+            neg = np.where(idx & 1, (idx // 2 + 1), -(idx // 2 + 1)).astype(np.int32)    # negation of the failed literal
+            w = np.concatenate([w, np.stack([neg, np.zeros_like(neg)], axis=1).ravel()])
+        assert got["status"] == status, name
+        assert got["units"] == units, name
+        if status == 0:
+            assert got["rounds"] == rounds, name
+            assert np.array_equal(t.Level0(), level0), name
+            seen_multi |= rounds > 1
+        else:
+            assert t.Solve([]) == TToporReturnVal.RET_UNSAT
+    assert seen_multi
