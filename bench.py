@@ -295,13 +295,13 @@ def ours_arm(args, rank, local_rank, world):
         avg = lambda k: sum(stats[k]) / max(len(stats[k]), 1) / 1e3
         tri, dee, com, blk = avg("triage_ms"), avg("deep_ms"), avg("compact_ms"), avg("block_ms")
         # bytes model of DESIGN.md section 4, per launch: triage; propagation (engine counters); compaction =
-        # 4 B size read twice (segment sums, then offsets) + 8 B offset + 4 B literal written per item here
+        # 4 B size read + 8 B offset + 4 B literal written per item here (+ the tile sums, negligible)
         # (every implied set of this workload is the probe's own literal, regenerated, so nothing is read back)
         prop_bytes = stats["kernel_bytes"] - stats["triage_bytes"]
-        compact_bytes = n_local * (4 + 4 + 8) + int(n_implied) * 4
+        compact_bytes = n_local * (4 + 8) + int(n_implied) * 4
         cands = [("k_triage (8 probes per thread, streaming)", stats["triage_bytes"], tri),
                  ("k_deep (warp-per-probe propagate, shared-memory state)", prop_bytes, dee + blk),
-                 ("k_scan_gather (cooperative single-pass scan + gather)", compact_bytes, com)]
+                 ("k_scan_gather (single-pass scan + gather on tile sums)", compact_bytes, com)]
         # the dominant kernel of the step = the one with the longest device time
         kname, kbytes, t1 = max(cands, key=lambda c: c[2])
         achieved = kbytes / t1 / 1e9

@@ -268,7 +268,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
 
     const size_t n1 = (size_t)n + 1;
     if (!h->rs[h->rb].flag.reserve(n1) || !h->d_raw_off.reserve(n1 * 8) || !h->d_len.reserve(n1 * 4 + 64) || !h->rs[h->rb].off.reserve(n1 * 8) ||
-        !h->d_overflow.reserve(n1 * 4) || !h->d_big.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_tiles.reserve(((size_t)h->sg_blocks + 4) * 8))
+        !h->d_overflow.reserve(n1 * 4) || !h->d_big.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_tiles.reserve((n / SG_TILE + 4) * 8))
         return h->fail(BBCP_ERR_ALLOC, "device allocation failed (batch buffers)");
 
     // lanes per probe (bbcp_propagate.cuh): a full warp. Narrower groups were measured and rejected, see DESIGN.md
@@ -302,7 +302,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.deep_list = h->d_deep.as<uint32_t>();
     b.off = h->rs[h->rb].off.p;
     b.off_base = h->off_base;
-    b.tile_state = h->d_tiles.as<unsigned long long>();
+    b.tile_sum = h->d_tiles.as<unsigned long long>();
     b.zero_words = MISC_WORDS64;
     b.opts = opts.flags;
 
@@ -367,7 +367,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             if (kevents) cudaEventRecord(h->ev[5], h->stream);
             bi.launches += 2;
             if (implied) {
-                if (!launch_scan_gather(b, 0, h->sg_blocks, false, in_batch, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
+                if (!launch_scan_gather(b, 0, h->sg_blocks, false, in_batch, h->stream)) return h->fail(BBCP_ERR_CUDA, "launch of the compaction kernel failed");
                 if (!dbg_check(h, "k_scan_gather (first sequence)")) return BBCP_ERR_CUDA;
                 ++bi.launches;
             }
@@ -414,7 +414,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             cudaEventRecord(h->ev[6], h->stream);
             bi.launches += 2;
             if (implied) {
-                if (!launch_scan_gather(b, 1, h->sg_blocks, true, in_batch, h->stream)) return h->fail(BBCP_ERR_CUDA, "cooperative launch of the compaction kernel failed");
+                if (!launch_scan_gather(b, 1, h->sg_blocks, true, in_batch, h->stream)) return h->fail(BBCP_ERR_CUDA, "launch of the compaction kernel failed");
                 if (!dbg_check(h, "k_scan_gather / k_gather_long (second sequence)")) return BBCP_ERR_CUDA;
                 bi.launches += 2;
             }

@@ -63,8 +63,8 @@ struct BatchView {
     void *off;                  // [n+1] u64, or u32 with OPT_OFF32
     unsigned long long off_base;   // added to every offset written (chunked batches that share one literal array)
     int32_t *impl;              // implied literals in item order
-    unsigned long long *tile_state;   // per-CTA segment sums of k_scan_gather
-    uint32_t *tile_ticket;            // its grid barrier word (zero before the launch)
+    unsigned long long *tile_sum;     // [ceil(n / 2048)] sum of the set sizes of each 2048-item tile (k_triage stores, propagate kernels add)
+    uint32_t *tile_ticket;            // +1: finished-CTA count of k_scan_gather
     unsigned long long *total;  // off[n]
     unsigned long long *host_report;  // mapped pinned host copy of the counter block, written by k_scan_gather (or nullptr)
     unsigned long long *zero_next;    // the counter block of the NEXT launch sequence, zeroed by k_triage

@@ -72,7 +72,10 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
             }
         }
     }
-    if (lane == 0) { b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off; }
+    if (lane == 0) {
+        b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
+        if (len) atomicAdd(&b.tile_sum[item / SG_TILE], (unsigned long long)len);
+    }
     wc.n_ok += flag == FLAG_OK;
     wc.n_conf += flag == FLAG_CONFLICT;
     G::sync();
@@ -153,10 +156,11 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
                 }
             }
         }
-        uint32_t deepmask = 0;
+        uint32_t deepmask = 0, selfs = 0;
 #pragma unroll
         for (int k = 0; k < TRIAGE_ITEMS; ++k) {
             const uint32_t x = q[k];
+            selfs += (x >> 8) & 1u;
             n_ok += (x >> 8) & 1u;
             n_ref += (x >> 9) & 1u;
             n_skip += (x & 0xffu) >= FLAG_TRIVIAL_L0 && (x & 0xffu) <= FLAG_UNMAPPED;
@@ -174,6 +178,15 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
 #pragma unroll
             for (int k = 0; k < TRIAGE_ITEMS; ++k)
                 if (base + k < n) { b.flag[base + k] = (uint8_t)q[k]; b.len[base + k] = (q[k] & TQ_SELF) ? selflen : 0u; }
+        }
+        // the tile's sum of set sizes so far (one literal per self-implying probe): stored, not added, so the array needs
+        // no clearing between batches; the propagate kernels add the sizes of the sets they store
+        {
+            const uint32_t wsum = __reduce_add_sync(FULL, selfs);
+            if (lane_id() == 0 && wsum) atomicAdd(&s_cnt[3], wsum);
+            __syncthreads();
+            if (threadIdx.x == 0) { b.tile_sum[wb / SG_TILE] = selflen ? (unsigned long long)s_cnt[3] : 0ull; s_cnt[3] = 0; }
+            __syncthreads();
         }
         // queue the deep items (the warp reserves one run of the list)
         if (__any_sync(FULL, deepmask != 0)) {
@@ -337,6 +350,7 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
         }
         if (lane == 0) {
             b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
+            if (len) atomicAdd(&b.tile_sum[item / SG_TILE], (unsigned long long)len);
             if (flag != FLAG_OVERFLOW) atomicAdd(&b.counters[C_MID], 1ull);
         }
         wc.n_ok += flag == FLAG_OK;
@@ -522,6 +536,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
         }
         if (threadIdx.x == 0) {
             b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
+            if (len) atomicAdd(&b.tile_sum[item / SG_TILE], (unsigned long long)len);
             atomicAdd(&b.counters[C_LARGE], 1ull);
             wc.n_ok += flag == FLAG_OK;
             wc.n_conf += flag == FLAG_CONFLICT;
@@ -626,12 +641,13 @@ __device__ __forceinline__ int32_t item_self_lit(const BatchView &b, uint64_t it
     return (idx & 1) ? -pv : pv;
 }
 
-// Cooperative launch (all CTAs co-resident). The items are cut into one contiguous segment per CTA.
-// Phase 1: every CTA sums the set sizes of its segment and publishes the sum; grid barrier. Phase 2: every CTA
-// adds up the sums of the segments before its own (<= a few hundred values), then walks its segment again
-// (from L2 now), 2048 items per step in a warp-striped arrangement -- lane l of warp w owns items
-// w*256 + j*32 + l, j = 0..7, so every load and store of a warp is one contiguous 128/256-byte run -- turns
-// sizes into offsets with warp shuffles, writes the offsets and moves the literals.
+// The items are cut into one contiguous segment of whole 2048-item tiles per CTA. The sum of the set sizes of
+// every tile is already known when this kernel starts (k_triage stores it, the propagate kernels add to it), so a
+// CTA gets the offset of its first item by adding up the tile sums before its segment (a few hundred to a few
+// thousand 8-byte loads spread over 256 threads) -- no pass over the sizes, no grid barrier, no look-back chain.
+// It then walks its segment, 2048 items per step in a warp-striped arrangement -- lane l of warp w owns items
+// w*256 + j*32 + l, j = 0..7, so every load and store of a warp is one contiguous 128/256-byte run -- turns sizes
+// into offsets with warp shuffles, writes the offsets and moves the literals.
 template <bool OFF32>
 __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, const int pass, const uint64_t seg, const MergeArgs mg)
 {
@@ -652,41 +668,17 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
     int32_t *__restrict__ dst = b.impl;
     const uint64_t lo = min((unsigned long long)blockIdx.x * seg, (unsigned long long)n), hi = min((unsigned long long)(lo + seg), (unsigned long long)n);
 
-    // ---- phase 1: segment sum
-    unsigned long long sum = 0;
-    {
-        // lo is a multiple of 2048 and the buffer is 256-byte aligned: 16-byte loads, four sizes each
-        const uint32_t cnt = (uint32_t)(hi - lo);
-        const uint4 *p4 = reinterpret_cast<const uint4 *>(b.len + lo);
-        for (uint32_t i = tid; i < cnt / 4; i += SG_THREADS) {
-            const uint4 v = p4[i];
-            sum += (unsigned long long)(v.x & 0x7fffffffu) + (v.y & 0x7fffffffu) + (v.z & 0x7fffffffu) + (v.w & 0x7fffffffu);
-        }
-        for (uint32_t i = (cnt & ~3u) + tid; i < cnt; i += SG_THREADS) sum += b.len[lo + i] & 0x7fffffffu;
-    }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(FULL, sum, d);
-    if (lane == 0) s_red[warp] = sum;
-    __syncthreads();
-    volatile unsigned long long *part = b.tile_state;   // [gridDim.x] segment sums, then the barrier word
-    if (tid == 0) {
-        unsigned long long t = 0;
-#pragma unroll
-        for (int k = 0; k < SG_THREADS / 32; ++k) t += s_red[k];
-        part[blockIdx.x] = t;
-        __threadfence();
-        atomicAdd(b.tile_ticket, 1u);
-        while (*(volatile uint32_t *)b.tile_ticket < gridDim.x) {}
-        __threadfence();
-    }
-    __syncthreads();
-
-    // ---- phase 2: my prefix = sum of the segments before mine
+    // my prefix = the sizes of all items before my segment = sum of the 2048-item tile sums before it. The tile sums
+    // were initialised by k_triage (one store per tile) and grown by the propagate kernels (one atomicAdd per stored
+    // set), so no pass over the sizes and no grid barrier is needed here.
     unsigned long long pre = 0;
-    for (uint32_t k = tid; k < blockIdx.x; k += SG_THREADS) pre += part[k];
+    {
+        const volatile unsigned long long *ts = b.tile_sum;
+        const uint32_t tiles_before = (uint32_t)(lo / SG_TILE);
+        for (uint32_t k = tid; k < tiles_before; k += SG_THREADS) pre += ts[k];
+    }
 #pragma unroll
     for (int d = 16; d; d >>= 1) pre += __shfl_xor_sync(FULL, pre, d);
-    __syncthreads();
     if (lane == 0) s_red[warp] = pre;
     __syncthreads();
     unsigned long long run = 0;   // offset of the first item of the current step
@@ -913,24 +905,20 @@ int scan_gather_max_blocks(int sm_count)
 {
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_gather<false>, SG_THREADS, 0);
-    return std::max(1, std::min(nb, 4)) * sm_count;
+    return std::max(1, nb) * sm_count * 2;   // no CTA waits for another one: the grid may exceed what is resident
 }
 
 bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s)
 {
-    // one contiguous segment of whole 2048-item steps per CTA
+    // one contiguous segment of whole 2048-item tiles per CTA
     uint64_t blocks = std::min<uint64_t>(std::max<uint64_t>((b.n + SG_TILE - 1) / SG_TILE, 1), (uint64_t)max_blocks);
     uint64_t seg = ((b.n + blocks - 1) / blocks + SG_TILE - 1) / SG_TILE * SG_TILE;
     if (seg == 0) seg = SG_TILE;
     blocks = std::max<uint64_t>((b.n + seg - 1) / seg, 1);
-    BatchView bv = b;
-    MergeArgs m = mg;
-    int p = pass;
-    void *args[] = {&bv, &p, &seg, &m};
-    const void *fn = (b.opts & OPT_OFF32) ? (const void *)k_scan_gather<true> : (const void *)k_scan_gather<false>;
-    if (cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(SG_THREADS), args, 0, s) != cudaSuccess) return false;
+    if (b.opts & OPT_OFF32) k_scan_gather<true><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
+    else k_scan_gather<false><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
     if (giant_sets_possible) k_gather_long<<<max_blocks, 256, 0, s>>>(b);
-    return true;
+    return cudaPeekAtLastError() == cudaSuccess;
 }
 
 void launch_merge(const MergeArgs &m, int sm_count, cudaStream_t s)
