@@ -277,7 +277,8 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     if (cap > 8192) cap = 8192;
     while (small_smem_bytes(cap, width) > 200 * 1024 && cap > 32) cap >>= 1;
     uint32_t cap_mid = opts.mid_trail ? pow2_at_least(opts.mid_trail) : 8192;
-    if (cap_mid > 16384) cap_mid = 16384;
+    if (!opts.mid_trail) if (const char *e = getenv("BBCP_MID_TRAIL")) cap_mid = pow2_at_least((uint32_t)atoi(e));
+    if (cap_mid > 32768) cap_mid = 32768;   // k_sort_sets sorts a whole set in shared memory (4 bytes per literal)
     const bool implied = (opts.flags & BBCP_OPT_IMPLIED) != 0;
     const bool off32 = (opts.flags & BBCP_OPT_OFF32) != 0;
     const bool want_kernel_times = (opts.flags & BBCP_OPT_KERNEL_TIMES) != 0 || !(h->lean & 2);
