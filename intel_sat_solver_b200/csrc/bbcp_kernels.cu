@@ -812,14 +812,18 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
     // reads it after the stream synchronisation it does anyway (no copy-engine round trip, and no fence: the
     // kernel has completed by then)
     if (b.host_report) {
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            s_pos = atomicAdd(b.tile_ticket + 1, 1u);
+        __syncthreads();   // this CTA's stores (offsets, total) are issued; warp 0 alone counts the CTA in, the rest leaves
+        if (warp == 0) {
+            unsigned last = 0;
+            if (lane == 0) {
+                __threadfence();
+                last = atomicAdd(b.tile_ticket + 1, 1u) == gridDim.x - 1;
+            }
+            if (__shfl_sync(FULL, last, 0)) {
+                __threadfence();
+                for (uint32_t i = lane; i < b.zero_words; i += 32) b.host_report[i] = ((volatile unsigned long long *)b.counters)[i];
+            }
         }
-        __syncthreads();
-        if (s_pos == gridDim.x - 1)
-            for (uint32_t i = tid; i < b.zero_words; i += SG_THREADS) b.host_report[i] = ((volatile unsigned long long *)b.counters)[i];
     }
 }
 
