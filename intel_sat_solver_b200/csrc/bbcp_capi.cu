@@ -25,7 +25,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         bytes = 0;
-        size_t want = need + need / 4 + 256;
+        size_t want = need + std::min<size_t>(need / 4, (size_t)1 << 30) + 256;   // head-room for the next batch, at most 1 GiB
         if (cudaMalloc(&p, want) != cudaSuccess) {
             cudaGetLastError();
             want = need;
@@ -95,6 +95,7 @@ struct bbcp_handle {
     int lean = 3;                           // bit 0: counters reach the host through mapped memory; bit 1: no per-kernel events
     uint64_t out_cap_hint = 0;   // stored literals the last batch needed (sizes the next batch's buffer)
     uint32_t big_slabs = 0;
+    uint32_t slab_budget_per_sm = 8;   // resident k_big CTAs per SM the slabs are sized for (lowered when memory runs short)
     DevBuf d_mid_slab;           // second tier: per-warp hash + trail
     uint32_t mid_slab_cap = 0;   // trail capacity the slab is laid out (and zeroed) for
     uint64_t mid_slab_groups = 0;
@@ -235,7 +236,7 @@ bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
     h->d_ltrail.release();
     // one slab per resident CTA of k_big; more CTAs = more giant probes in flight (each is a serial chain of
     // breadth-first levels), bounded by a quarter of the free memory
-    uint64_t per_sm = 8;
+    uint64_t per_sm = h->slab_budget_per_sm;
     if (const char *e = getenv("BBCP_BIG_SLABS_PER_SM")) per_sm = std::max(1, atoi(e));
     uint64_t slabs = std::min<uint64_t>((uint64_t)h->sm_count * per_sm, (free_b / 4) / std::max<size_t>(per_slab, 1));
     slabs = std::max<uint64_t>(slabs, 1);
@@ -329,7 +330,14 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     cudaEventRecord(h->ev[0], h->stream);
     for (int attempt = 0;; ++attempt) {
         // room for every self-implying probe (n) plus out_cap stored literals
-        if (!h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4) || (implied && !h->rs[h->rb].impl.reserve((n + out_cap + 4) * 4)) ||
+        auto pool_ok = [&]() { return h->d_out.reserve(std::max<uint64_t>(out_cap, 4) * 4) && (!implied || h->rs[h->rb].impl.reserve((n + out_cap + 4) * 4)); };
+        if (!pool_ok() && h->d_lbits.p) {
+            // the third tier's slabs were sized when memory was plentiful: give most of them back and try again
+            h->d_lbits.release();
+            h->d_ltrail.release();
+            h->slab_budget_per_sm = 1;
+        }
+        if (!pool_ok() ||
             !h->d_chunks.reserve((out_cap / 2048 + out_cap / 16384 + 64) * 8))   // sets above 16384 literals, 2048 per chunk, rounded up per set
             return h->fail(BBCP_ERR_ALLOC, "device allocation failed (implied literals)");
         b.out_lits = h->d_out.as<int32_t>();
