@@ -162,6 +162,15 @@ int bbcp_propagate_batch_device(bbcp_handle *h, const int32_t *d_lits, const uin
  * instance. *rounds = passes run, *units = failed literals turned into units; bbcp_level0_lits has the result. */
 int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds, uint64_t *units);
 
+/* products of the last all-literal pass with implied sets (bbcp_probe_all, or bbcp_probe_range with even bounds),
+ * computed on the device ("next" row N4; not in the reference, defined on the per-probe implied sets the reference
+ * would produce): necessary literals -- x implied by +v and by -v, so x is a unit -- as a bitmap over internal
+ * literals (bbcp_bitmap_words() words, may be NULL), and equivalences -- +v implies x and -v implies not-x, so
+ * v == x -- as pairs (v, x) of external literals in no particular order. *n_equiv is the number found, which may
+ * exceed equiv_cap (then only equiv_cap pairs were stored). */
+int bbcp_probe_products(bbcp_handle *h, uint32_t *necessary, uint64_t *n_necessary, int32_t *equiv /* 2 * equiv_cap */, uint64_t equiv_cap,
+                        uint64_t *n_equiv);
+
 /* ---- results of the last batch, device -> caller buffers */
 int bbcp_fetch_flags(bbcp_handle *h, uint8_t *flag /* n */);
 int bbcp_fetch_implied(bbcp_handle *h, uint64_t *impl_off /* n+1 */, int32_t *impl_lits /* n_implied */);

@@ -101,7 +101,9 @@ struct bbcp_handle {
     uint64_t mid_slab_groups = 0;
     uint32_t slab_version = 0;   // db_version the slabs were sized for
 
-    uint64_t last_n = 0, last_n_implied = 0;
+    uint64_t last_n = 0, last_n_implied = 0, last_first = 0;
+    bool last_universe = false, last_implied = false;
+    DevBuf d_products;
     bool have_batch = false;
     uint64_t total_props = 0;
 
@@ -493,6 +495,9 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     bi.tier1_ms = triage_ms + deep_ms;
     bi.kernel_ms = triage_ms + deep_ms + block_ms;
     h->last_n = n;
+    h->last_first = first;
+    h->last_universe = !d_lits && !d_off;
+    h->last_implied = implied;
     h->last_n_implied = bi.n_implied;
     h->have_batch = true;
     h->total_props += bi.props_ref;
@@ -530,7 +535,7 @@ void bbcp_release(bbcp_handle *h)
         for (auto &e : h->ev_merge) if (e) cudaEventDestroy(e);
         for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_bitmaps, &h->d_peer_tab, &h->rs[0].flag, &h->rs[0].off, &h->rs[0].impl, &h->rs[1].flag, &h->rs[1].off, &h->rs[1].impl, &h->d_raw_off, &h->d_len,
                           &h->d_out, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_big, &h->d_deep, &h->d_chunks, &h->d_misc, &h->d_lbits,
-                          &h->d_ltrail, &h->d_tiles, &h->d_mid_slab})
+                          &h->d_ltrail, &h->d_tiles, &h->d_mid_slab, &h->d_products})
             b->release();
         if (h->h_misc) cudaFreeHost(h->h_misc);
         for (auto &e : h->ev_in) if (e) cudaEventDestroy(e);
@@ -884,6 +889,39 @@ int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds
         rc = bbcp_finalize(h);
         if (rc != BBCP_OK) return rc;   // BBCP_CONTRADICTORY: x and not-x both failed, or the units propagate to a conflict
     }
+    return BBCP_OK;
+}
+
+// Products of the last all-literal pass (survey "next" row N4), computed on the device from its implied sets.
+int bbcp_probe_products(bbcp_handle *h, uint32_t *necessary, uint64_t *n_necessary, int32_t *equiv, uint64_t equiv_cap, uint64_t *n_equiv)
+{
+    if (n_necessary) *n_necessary = 0;
+    if (n_equiv) *n_equiv = 0;
+    if (!h || !h->have_batch) return h ? h->fail(BBCP_ERR_STATE, "no batch results") : BBCP_ERR_ARG;
+    if (!h->last_universe || !h->last_implied || (h->last_first & 1) || (h->last_n & 1))
+        return h->fail(BBCP_ERR_STATE, "bbcp_probe_products needs the results of bbcp_probe_all / bbcp_probe_range (even bounds) with implied sets");
+    if (equiv_cap && !equiv) return h->fail(BBCP_ERR_ARG, "bbcp_probe_products: null pair buffer");
+    cudaSetDevice(h->device);
+    const uint64_t words = h->bitmap_words;
+    const size_t bytes = 16 + words * 4 + equiv_cap * 8;
+    if (!h->d_products.reserve(bytes)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (probing products)");
+    cudaMemsetAsync(h->d_products.p, 0, 16 + words * 4, h->stream);
+    unsigned long long *counts = h->d_products.as<unsigned long long>();
+    uint32_t *d_nec = reinterpret_cast<uint32_t *>(counts + 2);
+    int32_t *d_eq = reinterpret_cast<int32_t *>(d_nec + words);
+    launch_products(h->last_off32, h->rs[h->rb].flag.as<uint8_t>(), h->rs[h->rb].off.p, h->rs[h->rb].impl.as<int32_t>(), h->last_n / 2, h->last_first / 2,
+                    d_nec, d_eq, equiv_cap, counts, h->sm_count, h->stream);
+    unsigned long long hc[2] = {0, 0};
+    cudaMemcpyAsync(hc, counts, 16, cudaMemcpyDeviceToHost, h->stream);
+    if (necessary) cudaMemcpyAsync(necessary, d_nec, words * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "probing products")) return BBCP_ERR_CUDA;
+    const uint64_t ne = std::min<uint64_t>(hc[1], equiv_cap);
+    if (ne) {
+        cudaMemcpyAsync(equiv, d_eq, ne * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "probing products")) return BBCP_ERR_CUDA;
+    }
+    if (n_necessary) *n_necessary = hc[0];
+    if (n_equiv) *n_equiv = hc[1];   // may exceed equiv_cap: call again with a larger buffer
     return BBCP_OK;
 }
 

@@ -97,6 +97,8 @@ int small_blocks_per_sm(uint32_t trail_cap, int width);
 struct MergeArgs;
 bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s);
 int scan_gather_max_blocks(int sm_count);
+void launch_products(bool off32, const uint8_t *flag, const void *off, const int32_t *impl, uint64_t npairs, uint64_t var_base, uint32_t *necessary, int32_t *equiv,
+                     unsigned long long equiv_cap, unsigned long long *counts, int sm_count, cudaStream_t s);
 struct MergeArgs {
     uint32_t *const *peer_base;   // [world] every rank's [failed | unit | control] block (own entry = own memory)
     int rank, world;              // world <= 1: nothing to merge

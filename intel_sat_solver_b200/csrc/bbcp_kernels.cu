@@ -845,6 +845,54 @@ __global__ void __launch_bounds__(256) k_gather_long(const BatchView b)
     }
 }
 
+// ---------------------------------------------------------------- probing products (survey "next" row N4)
+// From the implied sets of one all-literal pass (item 2k = +v, item 2k+1 = -v, both sorted by variable):
+//   necessary literal  x in impl(+v) and x in impl(-v): x holds whichever way v is decided, so x is a unit;
+//   equivalence        x in impl(+v) and not-x in impl(-v), x != v: v -> x and not-v -> not-x, so v == x.
+// One warp per variable: the lanes walk the shorter set and binary-search the longer one.
+template <bool OFF32>
+__global__ void __launch_bounds__(256) k_products(const uint8_t *__restrict__ flag, const void *__restrict__ off_, const int32_t *__restrict__ impl,
+                                                   const uint64_t npairs, const uint64_t var_base, uint32_t *__restrict__ necessary, int32_t *__restrict__ equiv,
+                                                   const unsigned long long equiv_cap, unsigned long long *__restrict__ counts)
+{
+    const uint64_t warp = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * 256) >> 5;
+    const int lane = lane_id();
+    for (uint64_t v = warp; v < npairs; v += nwarps) {
+        if (flag[2 * v] != FLAG_OK || flag[2 * v + 1] != FLAG_OK) continue;
+        uint64_t o0, o1, o2;
+        if (OFF32) { const uint32_t *o = (const uint32_t *)off_; o0 = o[2 * v]; o1 = o[2 * v + 1]; o2 = o[2 * v + 2]; }
+        else { const uint64_t *o = (const uint64_t *)off_; o0 = o[2 * v]; o1 = o[2 * v + 1]; o2 = o[2 * v + 2]; }
+        const int32_t *A = impl + o0, *B = impl + o1;
+        uint64_t na = o1 - o0, nb = o2 - o1;
+        const int32_t var = (int32_t)(var_base + v + 1);   // the variable this pair of probes belongs to
+        const bool swap = na > nb;
+        if (swap) { const int32_t *t = A; A = B; B = t; const uint64_t tn = na; na = nb; nb = tn; }
+        for (uint64_t i = lane; i < na; i += 32) {
+            const int32_t x = A[i];
+            const int32_t ax = x < 0 ? -x : x;
+            uint64_t lo = 0, hi = nb;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                const int32_t y = B[mid];
+                if ((y < 0 ? -y : y) < ax) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= nb) continue;
+            const int32_t y = B[lo];
+            if ((y < 0 ? -y : y) != ax) continue;
+            if (y == x) {
+                const uint32_t il = 2u * (uint32_t)ax + (x < 0);
+                if (!(atomicOr(&necessary[il >> 5], 1u << (il & 31)) & (1u << (il & 31)))) atomicAdd(&counts[0], 1ull);
+            } else {
+                // opposite signs. x_pos = the literal implied by +v (A and B may have been swapped)
+                const int32_t x_pos = swap ? y : x;
+                if (ax == var) continue;                 // v itself: +v in impl(+v), -v in impl(-v)
+                const unsigned long long e = atomicAdd(&counts[1], 1ull);
+                if (e < equiv_cap) { equiv[2 * e] = var; equiv[2 * e + 1] = x_pos; }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 static uint32_t ilog2(uint32_t x) { uint32_t l = 0; while ((1u << l) < x) ++l; return l; }
@@ -930,6 +978,14 @@ void launch_merge(const MergeArgs &m, int sm_count, cudaStream_t s)
     const uint64_t total = (m.wp / 4) * 2 * (uint64_t)std::max(m.world - 1, 0);
     const int blocks = (int)std::min<uint64_t>(std::max<uint64_t>((total + 255) / 256, 1), (uint64_t)sm_count * 2);
     k_merge<<<blocks, 256, 0, s>>>(m);
+}
+
+void launch_products(bool off32, const uint8_t *flag, const void *off, const int32_t *impl, uint64_t npairs, uint64_t var_base, uint32_t *necessary, int32_t *equiv,
+                     unsigned long long equiv_cap, unsigned long long *counts, int sm_count, cudaStream_t s)
+{
+    const int blocks = (int)std::min<uint64_t>(std::max<uint64_t>((npairs + 7) / 8, 1), (uint64_t)sm_count * 8);
+    if (off32) k_products<true><<<blocks, 256, 0, s>>>(flag, off, impl, npairs, var_base, necessary, equiv, equiv_cap, counts);
+    else k_products<false><<<blocks, 256, 0, s>>>(flag, off, impl, npairs, var_base, necessary, equiv, equiv_cap, counts);
 }
 
 }  // namespace bbcp

@@ -199,6 +199,24 @@ class BatchedTopor:
         rc = self._check(self._L.bbcp_probe_to_fixpoint(self._h, int(max_rounds), C.byref(rounds), C.byref(units)))
         return {"status": rc, "rounds": rounds.value, "units": units.value}
 
+    def ProbeProducts(self, equiv_cap: int = 1 << 20) -> tuple[np.ndarray, np.ndarray]:
+        """Products of the last ProbeAll / even-bounded ProbeRange with implied sets: (necessary literals, ascending
+        |var|; equivalence pairs (v, x) as an (m, 2) array, sorted). Computed on the device (bbcp_probe_products)."""
+        words = self._L.bbcp_bitmap_words(self._h)
+        nec = np.zeros(words, dtype=np.uint32)
+        n_nec, n_eq = C.c_uint64(0), C.c_uint64(0)
+        while True:
+            eq = np.zeros((max(equiv_cap, 1), 2), dtype=np.int32)
+            self._check(self._L.bbcp_probe_products(self._h, nec.ctypes.data, C.byref(n_nec), eq.ctypes.data, equiv_cap, C.byref(n_eq)))
+            if n_eq.value <= equiv_cap:
+                break
+            equiv_cap = int(n_eq.value)
+        il = np.nonzero(np.unpackbits(nec.view(np.uint8), bitorder="little"))[0]
+        lits = np.where(il & 1, -(il >> 1), il >> 1).astype(np.int32)
+        eq = eq[: n_eq.value]
+        eq = eq[np.lexsort((eq[:, 1], eq[:, 0]))] if eq.size else eq
+        return lits, eq
+
     def Bitmaps(self) -> tuple[np.ndarray, np.ndarray]:
         n = self._L.bbcp_bitmap_words(self._h)
         failed, unit = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)

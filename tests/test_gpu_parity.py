@@ -350,3 +350,31 @@ def test_probe_to_fixpoint_matches_checker_rounds(golden):
         else:
             assert t.Solve([]) == TToporReturnVal.RET_UNSAT
     assert seen_multi
+
+
+def test_probe_products_match_the_golden_implied_sets(golden):
+    """Necessary literals and equivalences (survey 'next' row N4) computed on the device from the pass's implied sets
+    equal the same products derived on the CPU from the REFERENCE's golden implied sets."""
+    total_nec = total_eq = 0
+    for name in ["fuzz_10", "fuzz_5", "fuzz_3", "fuzz_7", "regr_47", "regr_72", "regr_20", "hand_long", "ddtbug_32499"]:
+        g = lambda k: golden[f"{name}/{k}"]
+        flag, off, lits = g("probe_flag"), g("probe_off"), g("probe_lits")
+        nec, eq = set(), set()
+        for v in range(flag.size // 2):
+            if flag[2 * v] != 0 or flag[2 * v + 1] != 0:
+                continue
+            a = set(lits[int(off[2 * v]):int(off[2 * v + 1])].tolist())
+            b = set(lits[int(off[2 * v + 1]):int(off[2 * v + 2])].tolist())
+            nec |= a & b
+            eq |= {(v + 1, x) for x in a if -x in b and abs(x) != v + 1}
+        t, rc = engine_for(g("words"))
+        for kw in (dict(), dict(off32=True)):
+            t.ProbeAll(fetch=False, **kw)
+            got_nec, got_eq = t.ProbeProducts(equiv_cap=4)     # small buffer: the call grows it
+            assert sorted(got_nec.tolist(), key=lambda l: (abs(l), l < 0)) == sorted(nec, key=lambda l: (abs(l), l < 0)), name
+            assert {tuple(p) for p in got_eq.tolist()} == eq and len(got_eq) == len(eq), name
+        total_nec += len(nec)
+        total_eq += len(eq)
+        t.ProbeLits(np.asarray([1], dtype=np.int32))
+        assert t.lib.bbcp_probe_products(t.handle, None, None, None, 0, None) == -4      # not an all-literal pass
+    assert total_nec > 0 and total_eq > 0
