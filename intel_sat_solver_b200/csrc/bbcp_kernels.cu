@@ -594,19 +594,25 @@ __device__ __forceinline__ uint4 ld_remote(const uint4 *p)
     return v;
 }
 
+// element i of the pull (0 <= i < merge_total): 16 bytes of a peer's slice of the FAILED bitmap; the unit bitmap is its
+// image under "negate the literal" = swap the two bits of every variable, so it is derived here instead of being pulled
+__device__ __forceinline__ uint32_t swap_polarity(uint32_t f) { return ((f & 0x55555555u) << 1) | ((f & 0xaaaaaaaau) >> 1); }
+
+__device__ __forceinline__ uint64_t merge_total(const MergeArgs &m) { return (m.wp / 4) * (uint64_t)(m.world - 1); }
+
 __device__ __forceinline__ void merge_pull(const MergeArgs &m, uint64_t gtid, uint64_t gsize)
 {
-    uint32_t *mine = m.peer_base[m.rank];
     const uint64_t wp4 = m.wp / 4, s4 = m.stride / 4;           // both multiples of 4 words
-    const uint64_t per_peer = 2 * wp4, total = per_peer * (uint64_t)(m.world - 1);
+    const uint64_t total = merge_total(m);
+    uint4 *mine = reinterpret_cast<uint4 *>(m.peer_base[m.rank]);
     for (uint64_t i = gtid; i < total; i += gsize) {
-        const int pi = (int)(i / per_peer);
-        const uint64_t r = i - (uint64_t)pi * per_peer;
-        const uint64_t which = r >= wp4 ? 1 : 0;
+        const int pi = (int)(i / wp4);
         const int p = pi + (pi >= m.rank);
-        const uint64_t v = (uint64_t)p * wp4 + (r - which * wp4);   // vector index inside one bitmap
-        if (v >= s4) continue;                                      // the last rank's slice may be short
-        reinterpret_cast<uint4 *>(mine)[which * s4 + v] = ld_remote(reinterpret_cast<const uint4 *>(m.peer_base[p]) + which * s4 + v);
+        const uint64_t v = (uint64_t)p * wp4 + (i - (uint64_t)pi * wp4);   // vector index inside the bitmap
+        if (v >= s4) continue;                                             // the last rank's slice may be short
+        const uint4 f = ld_remote(reinterpret_cast<const uint4 *>(m.peer_base[p]) + v);
+        mine[v] = f;
+        mine[s4 + v] = make_uint4(swap_polarity(f.x), swap_polarity(f.y), swap_polarity(f.z), swap_polarity(f.w));
     }
 }
 
@@ -648,7 +654,7 @@ __device__ __forceinline__ int32_t item_self_lit(const BatchView &b, uint64_t it
 // It then walks its segment, 2048 items per step in a warp-striped arrangement -- lane l of warp w owns items
 // w*256 + j*32 + l, j = 0..7, so every load and store of a warp is one contiguous 128/256-byte run -- turns sizes
 // into offsets with warp shuffles, writes the offsets and moves the literals.
-template <bool OFF32>
+template <bool OFF32, bool MERGE>
 __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, const int pass, const uint64_t seg, const MergeArgs mg)
 {
     // first pass of a batch: if some probes still wait for the CTA-per-probe tiers the sizes are not final
@@ -656,7 +662,8 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
     if (pass == 0 && *(volatile uint32_t *)b.mid_count != 0) return;
     // the bitmaps are final (every propagate kernel of the batch is done): start sending this rank's slice to the
     // peers now -- unless the implied-literal pool overflowed and the whole batch is about to be re-run
-    const bool merging = mg.world > 1 && *(volatile unsigned long long *)b.out_cursor <= b.out_cap;
+    // (MERGE is a template parameter so that the single-GPU kernel does not carry the merge's registers)
+    const bool merging = MERGE && mg.world > 1 && *(volatile unsigned long long *)b.out_cursor <= b.out_cap;
     if (merging && blockIdx.x == 0 && threadIdx.x == 0) merge_signal(mg);
     __shared__ unsigned long long s_warp[SG_THREADS / 32], s_red[SG_THREADS / 32];
     __shared__ uint32_t s_nbig, s_pos;
@@ -803,6 +810,8 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
     }
     // merge: by now the peers' flags have had a whole compaction to arrive; copy their slices
     if (merging) {
+        // (measured and dropped: issuing the remote loads early and holding the values to the end -- +16 registers, one
+        // CTA less per SM, no gain; letting only the last-dispatched CTAs pull -- slower as well)
         __syncthreads();
         if (tid == 0) s_pos = merge_wait(mg);
         __syncthreads();
@@ -956,26 +965,35 @@ void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int 
 int scan_gather_max_blocks(int sm_count)
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_gather<false>, SG_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_gather<false, false>, SG_THREADS, 0);
     return std::max(1, nb) * sm_count * 2;   // no CTA waits for another one: the grid may exceed what is resident
 }
 
 bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s)
 {
     // one contiguous segment of whole 2048-item tiles per CTA
-    uint64_t blocks = std::min<uint64_t>(std::max<uint64_t>((b.n + SG_TILE - 1) / SG_TILE, 1), (uint64_t)max_blocks);
+    // (with the merge inside, every CTA ends with a wait + a remote-load round trip: keep the grid to ONE resident wave,
+    // max_blocks is twice that)
+    const bool merge = mg.world > 1;
+    const uint64_t limit = merge ? std::max(max_blocks / 2, 1) : max_blocks;
+    uint64_t blocks = std::min<uint64_t>(std::max<uint64_t>((b.n + SG_TILE - 1) / SG_TILE, 1), limit);
     uint64_t seg = ((b.n + blocks - 1) / blocks + SG_TILE - 1) / SG_TILE * SG_TILE;
     if (seg == 0) seg = SG_TILE;
     blocks = std::max<uint64_t>((b.n + seg - 1) / seg, 1);
-    if (b.opts & OPT_OFF32) k_scan_gather<true><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
-    else k_scan_gather<false><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
+    if (b.opts & OPT_OFF32) {
+        if (merge) k_scan_gather<true, true><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
+        else k_scan_gather<true, false><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
+    } else {
+        if (merge) k_scan_gather<false, true><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
+        else k_scan_gather<false, false><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
+    }
     if (giant_sets_possible) k_gather_long<<<max_blocks, 256, 0, s>>>(b);
     return cudaPeekAtLastError() == cudaSuccess;
 }
 
 void launch_merge(const MergeArgs &m, int sm_count, cudaStream_t s)
 {
-    const uint64_t total = (m.wp / 4) * 2 * (uint64_t)std::max(m.world - 1, 0);
+    const uint64_t total = (m.wp / 4) * (uint64_t)std::max(m.world - 1, 0);
     const int blocks = (int)std::min<uint64_t>(std::max<uint64_t>((total + 255) / 256, 1), (uint64_t)sm_count * 2);
     k_merge<<<blocks, 256, 0, s>>>(m);
 }
