@@ -181,6 +181,7 @@ struct GmemState {
     }
     __device__ __forceinline__ uint32_t tget(uint32_t i) const { return __ldcg(&trail[i]); }
     __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t) { __stcg(&trail[i], lit); }
+    template <class G> __device__ __forceinline__ void wipe() {}   // cannot overflow: the trail holds every variable
 };
 
 // per-group work counters, kept in registers (uniform over the group) and flushed once
@@ -210,6 +211,7 @@ struct GroupTail {
     __device__ __forceinline__ uint32_t get() const { return tail; }
     __device__ __forceinline__ bool aborted() const { return false; }
     template <class G> __device__ __forceinline__ void latch_conflict() {}
+    template <class G> __device__ __forceinline__ void drop() { tail = 0; }   // the state was wiped: nothing is on the trail
     // Commit one round of candidate implications (one candidate per lane, 0 = none). Group-converged.
     // Returns 0 ok, 1 conflict, 2 state overflow.
     template <class G, class S>
@@ -236,6 +238,7 @@ struct BlockTail {
     __device__ __forceinline__ uint32_t get() const { return *(volatile uint32_t *)&ctl[0]; }
     __device__ __forceinline__ bool aborted() const { return (*(volatile uint32_t *)&ctl[1] | *(volatile uint32_t *)&ctl[2]) != 0; }
     template <class G> __device__ __forceinline__ void latch_conflict() { if (G::lane() == 0) ctl[1] = 1; }
+    template <class G> __device__ __forceinline__ void drop() {}   // (the dense third-tier state cannot overflow)
     template <class G, class S>
     __device__ __forceinline__ int commit(S &st, uint32_t cand)
     {
@@ -433,6 +436,13 @@ __device__ int load_cube(const DbView &db, S &st, const int32_t *lits, uint32_t 
             if (r == 2) overflow = true;
         }
         G::sync();
+    }
+    const bool decided = G::any(unmapped) || G::any(false_l0);
+    if (decided && overflow) {
+        // the cube is decided without propagation, but the commit that overflowed left table entries that are not on
+        // the trail: the caller's trail-driven clean-up would miss them and they would leak into the next probe
+        st.template wipe<G>();
+        tl.template drop<G>();
     }
     if (G::any(unmapped)) return FLAG_UNMAPPED;
     if (G::any(false_l0)) return FLAG_FALSE_L0;

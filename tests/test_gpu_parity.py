@@ -378,3 +378,31 @@ def test_probe_products_match_the_golden_implied_sets(golden):
         t.ProbeLits(np.asarray([1], dtype=np.int32))
         assert t.lib.bbcp_probe_products(t.handle, None, None, None, 0, None) == -4      # not an all-literal pass
     assert total_nec > 0 and total_eq > 0
+
+
+def test_decided_cubes_that_overflow_the_state_leave_it_clean(golden):
+    """A cube longer than the tier's trail capacity that is ALSO decided without propagation (it names an unmapped
+    variable / a literal false at level 0) must not leave table entries behind for the probes the same warp runs
+    next: interleave many such cubes with every depth-1 probe and compare the probes with the goldens."""
+    for name in ["fuzz_10", "fuzz_5"]:
+        g = lambda k: golden[f"{name}/{k}"]
+        t, _ = engine_for(g("words"))
+        n = 2 * t.max_var
+        free = [v for v in range(1, t.max_var + 1) if g("probe_flag")[2 * (v - 1)] in (0, 1)]
+        assert len(free) > 100
+        poison = [l * (1 if i % 3 else -1) for i, l in enumerate(free[:100])] + [t.max_var + 7]     # 100 literals + an unmapped variable
+        cubes = []
+        for i in range(n):
+            v = i // 2 + 1
+            cubes.append([v if i % 2 == 0 else -v])
+            if i % 4 == 0:
+                cubes.append(poison)
+        lits, off = fileio.cubes_to_csr(cubes)
+        res = t.PropagateBatch(lits, off, small_trail=32, mid_trail=32)
+        probe_idx = [k for k, c in enumerate(cubes) if len(c) == 1]
+        assert all(res.flag[k] == 4 for k, c in enumerate(cubes) if len(c) > 1)
+        assert np.array_equal(res.flag[probe_idx], g("probe_flag")), name
+        sizes = np.diff(res.impl_off)[probe_idx]
+        assert np.array_equal(sizes, np.diff(g("probe_off"))), name
+        got = np.concatenate([res.implied(k) for k in probe_idx]) if probe_idx else np.zeros(0, np.int32)
+        assert np.array_equal(got, g("probe_lits")), name
