@@ -70,7 +70,7 @@ typedef struct {
     uint64_t n;                /* probes / cubes in the batch */
     uint64_t n_implied;        /* total implied literals (length of impl_lits) */
     uint64_t n_ok, n_conflict, n_skipped; /* flag 0 / flag 1 / flags 2,3,4 */
-    uint64_t n_large;          /* probes that ran in the third tier (CTA per probe, state in a global slab) */
+    uint64_t n_large;          /* probes that ran in the third tier (one CTA per probe, dense state in a global slab) */
     uint64_t props_all;        /* literals dequeued and propagated (every trail literal of every probe) */
     uint64_t props_ref;        /* of those, literals whose negation has a non-empty row: the reference's
                                   m_Implications convention (TopiBcp.cc:193-198) */
@@ -84,10 +84,10 @@ typedef struct {
     uint32_t launches;         /* kernels of this engine launched by the call (library scan kernels not counted) */
     float tier1_ms;            /* triage_ms + deep_ms */
     float triage_ms;           /* device time of k_triage (last attempt) */
-    float deep_ms;             /* device time of k_deep, the warp-per-probe propagate kernel (last attempt) */
-    float block_ms;            /* device time of the two CTA-per-probe tiers (last attempt) */
-    float mid_ms;              /* of which the shared-memory one */
-    uint64_t n_mid;            /* probes that ran in the second tier (CTA per probe, state in shared memory) */
+    float deep_ms;             /* device time of k_deep, the first tier: warp per probe, state in shared memory (last attempt) */
+    float block_ms;            /* device time of the second and third tiers + the sorting of second-tier sets (last attempt) */
+    float mid_ms;              /* of which the second tier (k_deep2) */
+    uint64_t n_mid;            /* probes that ran in the second tier (warp per probe, hash + trail in a global slab) */
     float compact_ms;          /* device time of k_scan_gather (+ k_gather_long), last sequence */
     float merge_ms;            /* device time of the in-batch bitmap all-gather (BBCP_OPT_MERGE), incl. waiting for peers */
 } bbcp_batch_info;

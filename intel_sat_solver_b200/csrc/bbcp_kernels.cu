@@ -1,11 +1,14 @@
 // bbcp_kernels.cu -- batched BCP to fixpoint on sm_100a. Hand-written CUDA; no tensor cores (there is no
-// dense contraction on this path), the bound is HBM/L2 gather bandwidth and load latency.
+// dense contraction on this path); what bounds the kernels is dependent-load latency (propagation) and launch /
+// first-load latency (the streaming kernels), see DESIGN.md section 4 and profiles/r01.
 //
 // What one probe/cube does here replaces one NewDecLevel/Assign/BCP()/Backtrack(0) round of the reference
 // (TopiBcp.cc:103-410, TopiAsg.cc:46-139, TopiBacktrack.cc:18-53):
 //   * the database is immutable and shared by all probes; the per-probe state is a sparse assignment
-//     (open-addressed hash set of true literals) and a trail, both in shared memory (first tier), or a dense
-//     2-bit-per-variable assignment and a trail in a per-warp global slab (second tier, any size);
+//     (open-addressed hash set of true literals) and a trail -- in shared memory (first tier, k_deep), in a
+//     per-warp slab in global memory (second tier, k_deep2) -- or a dense 2-bit-per-variable assignment and a
+//     full-length trail in a per-CTA slab (third tier, k_big, any size); the propagation core itself is in
+//     bbcp_propagate.cuh;
 //   * the trail is also the propagation queue; it is consumed breadth-first, 32 literals per step, one
 //     literal per lane for the row-header gather, then the union of the 32 rows is flattened and scanned
 //     32 eight-byte slots at a time (coalesced within a row);
@@ -21,9 +24,12 @@
 //     the hash set (atomicCAS) is the linearisation point that detects x / not-x conflicts;
 //   * while exactly one literal is assigned, only binary clauses can become unit, so the first step of a
 //     depth-1 probe reads the binary part of its row only ("length pruning"); a probe whose literal has no
-//     binary clause ends right there. That triage is its own streaming kernel (k_triage: one probe per
-//     thread, one byte of per-literal facts read, flag + set size written, no atomics on the common path);
-//     only the probes that can propagate are queued for the warp-per-probe kernel (k_deep).
+//     binary clause ends right there. That triage is its own streaming kernel (k_triage: eight probes per
+//     thread, one byte of per-literal facts each, a table look-up, flag + set size written, one atomic per
+//     warp only where probes are queued); only the probes that can propagate are queued for k_deep;
+//   * k_scan_gather turns the set sizes into CSR offsets and moves every set to its canonical place in one
+//     pass (the per-tile sums it needs are produced on the way by k_triage and the propagate kernels), and
+//     carries the multi-GPU merge of the bitmaps when peers are attached.
 // A conflict ends the probe (NewContradiction's same-level branch, TopiBcp.cc:141-158); only the flag is
 // part of the contract for conflicting probes.
 #include "bbcp_device.cuh"
