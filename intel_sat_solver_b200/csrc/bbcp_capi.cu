@@ -373,12 +373,15 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             launch_triage(b, dbv, h->sm_count, h->stream);
             if (!dbg_check(h, "k_triage")) return BBCP_ERR_CUDA;
             if (kevents) cudaEventRecord(h->ev[4], h->stream);
-            launch_small(dbv, b, cap, width, bps * h->sm_count, h->stream);
+            // (programmatic dependent launch only when no event sits between the kernels, and switchable for diagnosis)
+            static const bool pdl_on = getenv("BBCP_NO_PDL") == nullptr;
+            const bool pdl = pdl_on && !kevents;
+            launch_small(dbv, b, cap, width, bps * h->sm_count, h->stream, pdl);
             if (!dbg_check(h, "k_deep")) return BBCP_ERR_CUDA;
             if (kevents) cudaEventRecord(h->ev[5], h->stream);
             bi.launches += 2;
             if (implied) {
-                if (!launch_scan_gather(b, 0, h->sg_blocks, false, in_batch, h->stream)) return h->fail(BBCP_ERR_CUDA, "launch of the compaction kernel failed");
+                if (!launch_scan_gather(b, 0, h->sg_blocks, false, in_batch, h->stream, pdl)) return h->fail(BBCP_ERR_CUDA, "launch of the compaction kernel failed");
                 if (!dbg_check(h, "k_scan_gather (first sequence)")) return BBCP_ERR_CUDA;
                 ++bi.launches;
             }
@@ -425,7 +428,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             cudaEventRecord(h->ev[6], h->stream);
             bi.launches += 2;
             if (implied) {
-                if (!launch_scan_gather(b, 1, h->sg_blocks, true, in_batch, h->stream)) return h->fail(BBCP_ERR_CUDA, "launch of the compaction kernel failed");
+                if (!launch_scan_gather(b, 1, h->sg_blocks, true, in_batch, h->stream, false)) return h->fail(BBCP_ERR_CUDA, "launch of the compaction kernel failed");
                 if (!dbg_check(h, "k_scan_gather / k_gather_long (second sequence)")) return BBCP_ERR_CUDA;
                 bi.launches += 2;
             }

@@ -85,7 +85,7 @@ struct LargeState {
 };
 
 void launch_triage(const BatchView &b, const DbView &db, int sm_count, cudaStream_t s);
-void launch_small(const DbView &db, const BatchView &b, uint32_t trail_cap, int width, int blocks, cudaStream_t s);
+void launch_small(const DbView &db, const BatchView &b, uint32_t trail_cap, int width, int blocks, cudaStream_t s, bool pdl);
 void launch_mid(const DbView &db, const BatchView &b, uint32_t *slab, uint32_t cap, int width, int blocks, cudaStream_t s);
 void launch_sort_sets(const BatchView &b, uint32_t cap, int sm_count, cudaStream_t s);
 size_t mid_slab_words_per_group(uint32_t cap);
@@ -95,7 +95,7 @@ constexpr uint32_t SG_TILE = 2048;   // items per step of the compaction kernel
 size_t small_smem_bytes(uint32_t trail_cap, int width);
 int small_blocks_per_sm(uint32_t trail_cap, int width);
 struct MergeArgs;
-bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s);
+bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s, bool pdl);
 int scan_gather_max_blocks(int sm_count);
 void launch_products(bool off32, const uint8_t *flag, const void *off, const int32_t *impl, uint64_t npairs, uint64_t var_base, uint32_t *necessary, int32_t *equiv,
                      unsigned long long equiv_cap, unsigned long long *counts, int sm_count, cudaStream_t s);

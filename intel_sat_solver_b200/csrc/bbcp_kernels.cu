@@ -43,6 +43,13 @@ namespace {
 
 __device__ __forceinline__ uint32_t lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 
+// Programmatic dependent launch (sm_90+): the three kernels of a batch's first sequence are launched with
+// programmatic stream serialization, so the CTAs of the next kernel are scheduled while the previous one drains.
+// pdl_wait() = "everything the previous kernel of the stream wrote is visible from here on" (a no-op when the
+// kernel was launched the ordinary way); pdl_trigger() = "the next kernel may be scheduled now".
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // ---------------------------------------------------------------- first tier: shared-memory state
 // Result of one probe of the first tier: flag, implied set (sorted in shared memory, written to the pool as
 // external literals) or hand-over to the second tier.
@@ -103,6 +110,7 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
 {
     __shared__ unsigned int s_cnt[4];  // ok, skipped, props_ref
     __shared__ uint16_t s_lut[32];
+    pdl_trigger();   // k_deep's CTAs may take their places; they wait for this grid to complete before they read anything
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x < 32) {
@@ -245,6 +253,8 @@ k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t
     extern __shared__ uint32_t smem[];
     constexpr int GROUPS = SMALL_THREADS / W;
     const int lane = G::lane(), grp = threadIdx.x / W;
+    pdl_wait();
+    pdl_trigger();
     const uint32_t ndeep = *b.deep_count;
     if ((uint64_t)blockIdx.x * GROUPS >= ndeep) return;
     const uint32_t hs = 1u << log_hs;
@@ -663,8 +673,8 @@ __device__ __forceinline__ int32_t item_self_lit(const BatchView &b, uint64_t it
 template <bool OFF32, bool MERGE>
 __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, const int pass, const uint64_t seg, const MergeArgs mg)
 {
-    // first pass of a batch: if some probes still wait for the CTA-per-probe tiers the sizes are not final
-    // (uniform over the grid, so nobody is left waiting at the barrier)
+    pdl_wait();
+    // first pass of a batch: if some probes still wait for the later tiers the sizes are not final
     if (pass == 0 && *(volatile uint32_t *)b.mid_count != 0) return;
     // the bitmaps are final (every propagate kernel of the batch is done): start sending this rank's slice to the
     // peers now -- unless the implied-literal pool overflowed and the whole batch is about to be re-run
@@ -934,11 +944,29 @@ void launch_triage(const BatchView &b, const DbView &db, int sm_count, cudaStrea
     else k_triage<TM_UNIVERSE><<<blocks, 256, 0, s>>>(db, b);
 }
 
-void launch_small(const DbView &db, const BatchView &b, uint32_t cap, int width, int blocks, cudaStream_t s)
+// launch with programmatic stream serialization: the kernel may be scheduled before its predecessor in the stream has
+// drained; it calls pdl_wait() before it touches anything the predecessor wrote
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+void launch_small(const DbView &db, const BatchView &b, uint32_t cap, int width, int blocks, cudaStream_t s, bool pdl)
 {
     const size_t smem = small_smem_bytes(cap, width);
     const uint32_t lh = ilog2(2 * cap);
-    k_deep<32><<<blocks, SMALL_THREADS, smem, s>>>(db, b, lh, cap);
+    launch_pdl(k_deep<32>, dim3(blocks), dim3(SMALL_THREADS), smem, s, pdl, db, b, lh, cap);
 }
 
 size_t mid_slab_words_per_group(uint32_t cap) { return (size_t)2 * cap + cap; }
@@ -975,7 +1003,7 @@ int scan_gather_max_blocks(int sm_count)
     return std::max(1, nb) * sm_count;
 }
 
-bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s)
+bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s, bool pdl)
 {
     // one contiguous segment of whole 2048-item tiles per CTA
     // one resident wave (max_blocks): measured 4 % faster than two waves of one-tile CTAs on one GPU, and with the merge
@@ -986,12 +1014,13 @@ bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant
     uint64_t seg = ((b.n + blocks - 1) / blocks + SG_TILE - 1) / SG_TILE * SG_TILE;
     if (seg == 0) seg = SG_TILE;
     blocks = std::max<uint64_t>((b.n + seg - 1) / seg, 1);
+    const dim3 g((unsigned)blocks), t(SG_THREADS);
     if (b.opts & OPT_OFF32) {
-        if (merge) k_scan_gather<true, true><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
-        else k_scan_gather<true, false><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
+        if (merge) launch_pdl(k_scan_gather<true, true>, g, t, 0, s, pdl, b, pass, seg, mg);
+        else launch_pdl(k_scan_gather<true, false>, g, t, 0, s, pdl, b, pass, seg, mg);
     } else {
-        if (merge) k_scan_gather<false, true><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
-        else k_scan_gather<false, false><<<(unsigned)blocks, SG_THREADS, 0, s>>>(b, pass, seg, mg);
+        if (merge) launch_pdl(k_scan_gather<false, true>, g, t, 0, s, pdl, b, pass, seg, mg);
+        else launch_pdl(k_scan_gather<false, false>, g, t, 0, s, pdl, b, pass, seg, mg);
     }
     if (giant_sets_possible) k_gather_long<<<max_blocks, 256, 0, s>>>(b);
     return cudaPeekAtLastError() == cudaSuccess;
