@@ -160,3 +160,40 @@ def test_product_does_not_reference_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in src.lower(), fn
+
+
+def test_normaliser_on_seeded_random_clause_streams():
+    """300 small random clause streams with duplicate literals, tautologies, unit clauses, repeated clauses and the
+    occasional empty clause: the host database (intake result-equivalent to AddUserClause, Topi.cc:377-653) agrees
+    with the independent Python model on status, counts and every row."""
+    rng = np.random.default_rng(20260101)
+    n_contra = n_rows = 0
+    for trial in range(300):
+        nv = int(rng.integers(3, 12))
+        words = []
+        for _ in range(int(rng.integers(1, 25))):
+            k = int(rng.choice([1, 2, 2, 2, 3, 3, 3, 4, 5, 6])) if rng.random() < 0.995 else 0
+            lits = [int(rng.integers(1, nv + 1)) * (1 if rng.random() < 0.5 else -1) for _ in range(k)]
+            if lits and rng.random() < 0.15:
+                lits.append(lits[0])            # duplicate literal
+            if lits and rng.random() < 0.08:
+                lits.append(-lits[-1])          # tautology
+            words += lits + [0]
+        words = np.asarray(words, dtype=np.int32)
+        kept, mapped, unit_val, contradictory = py_normalise(words)
+        t = BatchedTopor()
+        t.AddClauses(words)
+        rc = t.HostPrepare()
+        assert (rc == 1) == contradictory, (trial, words.tolist())
+        if contradictory:
+            n_contra += 1
+            continue
+        info = t.DbInfo()
+        max_var = int(np.abs(words).max()) if words.size and np.abs(words).max() > 0 else 0
+        assert info["n_mapped_vars"] == len(mapped) and info["n_level0"] == len(unit_val), (trial, words.tolist())
+        assert info["n_tern"] == sum(len(c) == 3 for c in kept) and info["n_long"] == sum(len(c) > 3 for c in kept)
+        assert info["n_bin"] == len({frozenset(c) for c in kept if len(c) == 2})
+        if max_var:
+            check_rows(t, kept, max_var)
+            n_rows += 1
+    assert n_contra > 10 and n_rows > 100
