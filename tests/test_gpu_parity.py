@@ -406,3 +406,51 @@ def test_decided_cubes_that_overflow_the_state_leave_it_clean(golden):
         assert np.array_equal(sizes, np.diff(g("probe_off"))), name
         got = np.concatenate([res.implied(k) for k in probe_idx]) if probe_idx else np.zeros(0, np.int32)
         assert np.array_equal(got, g("probe_lits")), name
+
+
+def test_seeded_random_instances_against_checker():
+    """60 seeded random instances (20-80 variables, clause lengths 1-7, duplicate literals, tautologies, units that
+    propagate at level 0, sometimes refuted at level 0): every probe and 40 random cubes each (depth 1-10, with
+    repeated, contradictory, level-0 and unmapped literals) against the CPU checker, default and tiny state budgets."""
+    from oracle_lib import Oracle
+    rng = np.random.default_rng(424242)
+    n_items = n_conf = n_unsat = 0
+    for trial in range(60):
+        nv = int(rng.integers(20, 81))
+        words = []
+        for _ in range(int(rng.integers(nv, 4 * nv))):
+            k = int(rng.choice([1, 2, 2, 2, 2, 3, 3, 3, 4, 5, 7], p=[.02, .2, .1, .1, .08, .15, .1, .1, .08, .05, .02]))
+            lits = [int(rng.integers(1, nv + 1)) * (1 if rng.random() < 0.5 else -1) for _ in range(k)]
+            if rng.random() < 0.05:
+                lits.append(lits[0])
+            if rng.random() < 0.03:
+                lits.append(-lits[0])
+            words += lits + [0]
+        words = np.asarray(words, dtype=np.int32)
+        o = Oracle(words)
+        t, rc = engine_for(words)
+        assert rc == o.status, trial
+        if rc:
+            n_unsat += 1
+            continue
+        assert np.array_equal(t.Level0(), o.level0()), trial
+        flag, _, off, lits = o.run()
+        cubes = []
+        for _ in range(40):
+            d = int(rng.integers(1, 11))
+            c = [int(rng.integers(1, nv + 4)) * (1 if rng.random() < 0.5 else -1) for _ in range(d)]
+            if rng.random() < 0.2:
+                c.append(c[0])
+            if rng.random() < 0.1:
+                c.append(-c[0])
+            cubes.append(c)
+        cl, co = fileio.cubes_to_csr(cubes)
+        cflag, _, coff, clits = o.run(cl, co)
+        for kw in (dict(), dict(small_trail=32, mid_trail=32)):
+            res = t.ProbeAll(**kw)
+            gpu_util.assert_same_results(res, flag, off, lits, f"trial {trial} probes {kw}")
+            res = t.PropagateBatch(cl, co, **kw)
+            gpu_util.assert_same_results(res, cflag, coff, clits, f"trial {trial} cubes {kw}")
+        n_items += flag.size + cflag.size
+        n_conf += int((flag == 1).sum() + (cflag == 1).sum())
+    assert n_items > 3000 and n_conf > 300 and n_unsat > 5
