@@ -10,14 +10,19 @@ the implied-literal set come back, plus the failed-literal / unit bitmaps.
 Workload (config.workload): C2 of SURVEY.md 8d -- random 3-SAT, 1,000,000 variables, clause/variable ratio 4.2,
 seed 1 (tools/cnfgen.c), probe all 2,000,000 literals on one B200. With N GPUs the run is a WEAK-scaling one:
 N x 1M variables / N x 4.2M clauses, the database replicated on every GPU, the probe universe cut into N
-contiguous literal ranges (one per rank, aligned to failed-literal-bitmap words), and one NCCL all-gather of
-the bitmap slices on the stream right behind the kernels.
+contiguous literal ranges (one per rank, aligned to failed-literal-bitmap words), and the all-gather of the bitmap
+slices done by the engine itself over NVLink peer memory inside the batch's last kernel (BBCP_OPT_MERGE; the CUDA
+IPC handles are exchanged once through torch.distributed); a device-side rendezvous aligns the ranks before
+each timed batch.
 
-Keys: value = probes/s with everything resident in HBM (device-timed, CUDA events on the launching stream, max
-over ranks); e2e = the same metric through the C ABI with HOST buffers (pinned probe list H2D, flags + implied
-sets D2H inside the timed region); roofline = the first-tier propagate kernel against the measured HBM copy
-bandwidth; cpu_baseline = the reference's own CTopi::BCP() (oracle/_ref/ref_bcp; the C port if the harness did
-not travel) on the box's host cores, one process per core over probe shards, timed in this same run.
+Keys: value = probes/s with everything resident in HBM (device-timed, CUDA events on the engine's stream from the
+first kernel to the end of the last one incl. the merge, max over ranks); e2e = the same metric through ONE C-ABI
+call with HOST buffers (bbcp_probe_lits_to_host: pinned 4-byte probe list in; flags, u32 CSR offsets and implied
+literals out; upload / kernels / read-back of successive chunks overlapped); roofline = the kernel of the step with
+the longest device time (per-kernel events in a separate pass) on the bytes model of DESIGN.md section 4, against
+the measured HBM copy bandwidth; cpu_baseline = the reference's own CTopi::BCP() (oracle/_ref/ref_bcp; the C port
+if the harness did not travel) on the box's host cores, one process per core over probe shards, timed in this
+same run.
 """
 import argparse
 import ctypes as C
