@@ -2,7 +2,9 @@
 #include "bbcp_db.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace bbcp {
 
@@ -106,28 +108,64 @@ bool HostDb::simplify_level0()
     return true;
 }
 
+namespace {
+
+unsigned host_threads(size_t work_words)
+{
+    unsigned t = std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("BBCP_HOST_THREADS")) t = (unsigned)std::atoi(e);   // (explicit: also for small inputs)
+    else if (work_words < (1u << 20)) return 1;   // small databases: not worth the thread start-up
+    t = std::min(std::max(t, 1u), 32u);
+    while (t & (t - 1)) t &= t - 1;   // a power of two: ownership below is a mask test
+    return t;
+}
+
+template <class F>
+void parallel(unsigned T, F f)
+{
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(f, t);
+    f(0u);
+    for (auto &x : th) x.join();
+}
+
+}  // namespace
+
+// Flattening, multi-threaded by OWNER-COMPUTES: thread t owns the literals l with (l / 256) % T == t (blocks of 256
+// literals dealt round-robin, so that the hot low-numbered variables of a power-law instance are spread). Every thread
+// streams the whole clause list (sequential reads, cheap) and touches only the counters, cursors and rows of its own
+// literals (the random accesses, a T-th of them each, with no atomics -- locked increments were measured to be slower
+// than one thread, they serialise the cache misses). Entries land in every row in clause order, exactly as with one
+// thread, so the database does not depend on the thread count. Only the arena is filled by clause chunk.
 std::string HostDb::build_rows()
 {
     const size_t nl = 2 * ((size_t)max_var + 1);
     hdr.assign(nl, RowHdr{0, 0, 0, 0});
     n_bin = n_tern = n_long = n_long_lits = 0;
+    const unsigned T = host_threads(cls.size());
+    const uint32_t own_mask = T - 1;
+    auto owns = [own_mask](unsigned t, uint32_t l) { return ((l >> 8) & own_mask) == t; };
 
-    // pass 1: occurrences per literal
+    // pass 1: occurrences per literal (owner-computes) + the global clause counts (thread 0)
     std::vector<uint32_t> bcount(nl + 1, 0);
     uint64_t arena_words = 4;  // unit 0 is never a valid clause reference
-    for (size_t r = 0; r < cls.size();) {
-        const uint32_t len = cls[r];
-        const uint32_t *c = &cls[r + 1];
-        if (len == 2) { ++bcount[c[0]]; ++bcount[c[1]]; }
-        else if (len == 3) { ++hdr[c[0]].ntern; ++hdr[c[1]].ntern; ++hdr[c[2]].ntern; ++n_tern; }
-        else {
-            for (uint32_t i = 0; i < len; ++i) ++hdr[c[i]].nlong;
-            ++n_long;
-            n_long_lits += len;
-            arena_words += (1 + (uint64_t)len + 3) & ~3ull;
+    parallel(T, [&](unsigned t) {
+        for (size_t r = 0; r < cls.size();) {
+            const uint32_t len = cls[r];
+            const uint32_t *c = &cls[r + 1];
+            if (len == 2) {
+                if (owns(t, c[0])) ++bcount[c[0]];
+                if (owns(t, c[1])) ++bcount[c[1]];
+            } else if (len == 3) {
+                for (int i = 0; i < 3; ++i) if (owns(t, c[i])) ++hdr[c[i]].ntern;
+                if (t == 0) ++n_tern;
+            } else {
+                for (uint32_t i = 0; i < len; ++i) if (owns(t, c[i])) ++hdr[c[i]].nlong;
+                if (t == 0) { ++n_long; n_long_lits += len; arena_words += (1 + (uint64_t)len + 3) & ~3ull; }
+            }
+            r += 1 + len;
         }
-        r += 1 + len;
-    }
+    });
     if (arena_words / 4 >= 0xffffffffull) return "clause arena exceeds the 32-bit clause index";
 
     // binary rows: gather, sort, unique -- a duplicate binary clause is kept once
@@ -135,28 +173,33 @@ std::string HostDb::build_rows()
     std::vector<uint64_t> boff(nl + 1, 0);
     for (size_t l = 0; l < nl; ++l) boff[l + 1] = boff[l] + bcount[l];
     std::vector<uint32_t> bins(boff[nl]);
-    {
-        std::vector<uint64_t> pos(boff.begin(), boff.end() - 1);
+    std::vector<uint64_t> c_bins(T, 0);
+    std::vector<uint64_t> pos(boff.begin(), boff.end() - 1);   // shared, every entry written by its owner only
+    parallel(T, [&](unsigned t) {
         for (size_t r = 0; r < cls.size();) {
             const uint32_t len = cls[r];
             if (len == 2) {
                 const uint32_t a = cls[r + 1], b = cls[r + 2];
-                bins[pos[a]++] = b;
-                bins[pos[b]++] = a;
+                if (owns(t, a)) bins[pos[a]++] = b;
+                if (owns(t, b)) bins[pos[b]++] = a;
             }
             r += 1 + len;
         }
-    }
-    uint64_t total_bins = 0;
-    for (size_t l = 0; l < nl; ++l) {
-        uint32_t *b = bins.data() + boff[l], *e = bins.data() + boff[l + 1];
-        if (e - b > 1) {
-            std::sort(b, e);
-            e = std::unique(b, e);
+        uint64_t tot = 0;
+        for (size_t l = 0; l < nl; ++l) {
+            if (!owns(t, (uint32_t)l)) { l |= 255; continue; }   // skip the rest of a block that is not mine
+            uint32_t *b = bins.data() + boff[l], *e = bins.data() + boff[l + 1];
+            if (e - b > 1) {
+                std::sort(b, e);
+                e = std::unique(b, e);
+            }
+            hdr[l].nbin = (uint32_t)(e - b);
+            tot += hdr[l].nbin;
         }
-        hdr[l].nbin = (uint32_t)(e - b);
-        total_bins += hdr[l].nbin;
-    }
+        c_bins[t] = tot;
+    });
+    uint64_t total_bins = 0;
+    for (unsigned t = 0; t < T; ++t) total_bins += c_bins[t];
     n_bin = total_bins / 2;
 
     // row extents
@@ -170,39 +213,42 @@ std::string HostDb::build_rows()
     slots.assign(nslots, Slot{0, 0});
     arena.assign(arena_words, 0);
 
-    // fill: binary part
-    for (size_t l = 0; l < nl; ++l) {
-        const uint32_t *b = bins.data() + boff[l];
-        Slot *row = slots.data() + hdr[l].start;
-        for (uint32_t i = 0; i < hdr[l].nbin; ++i) {
-            if (i & 1) row[i / 2].y = b[i]; else row[i / 2].x = b[i];
+    // clause references: the arena position of every long clause follows from the clause order alone
+    // fill (owner-computes): binary part, then the ternary and long slots of the owned rows; thread 0 also copies the
+    // long clauses into the arena
+    std::vector<uint32_t> tpos(nl), lpos(nl);   // shared, every entry written by its owner only
+    parallel(T, [&](unsigned t) {
+        for (size_t l = 0; l < nl; ++l) {
+            if (!owns(t, (uint32_t)l)) { l |= 255; continue; }
+            const uint32_t *b = bins.data() + boff[l];
+            Slot *row = slots.data() + hdr[l].start;
+            for (uint32_t i = 0; i < hdr[l].nbin; ++i) {
+                if (i & 1) row[i / 2].y = b[i]; else row[i / 2].x = b[i];
+            }
+            tpos[l] = hdr[l].start + (hdr[l].nbin + 1) / 2;
+            lpos[l] = tpos[l] + hdr[l].ntern;
         }
-    }
-    bins.clear();
-    bins.shrink_to_fit();
-    // fill: ternary and long parts
-    std::vector<uint32_t> tpos(nl), lpos(nl);
-    for (size_t l = 0; l < nl; ++l) {
-        tpos[l] = hdr[l].start + (hdr[l].nbin + 1) / 2;
-        lpos[l] = tpos[l] + hdr[l].ntern;
-    }
-    uint64_t aw = 4;
-    for (size_t r = 0; r < cls.size();) {
-        const uint32_t len = cls[r];
-        const uint32_t *c = &cls[r + 1];
-        if (len == 3) {
-            slots[tpos[c[0]]++] = Slot{c[1], c[2]};
-            slots[tpos[c[1]]++] = Slot{c[0], c[2]};
-            slots[tpos[c[2]]++] = Slot{c[0], c[1]};
-        } else if (len > 3) {
-            const uint32_t cref = (uint32_t)(aw / 4);
-            arena[aw] = len;
-            std::memcpy(&arena[aw + 1], c, (size_t)len * 4);
-            for (uint32_t i = 0; i < len; ++i) slots[lpos[c[i]]++] = Slot{c[(i + 1) % len], cref};
-            aw += (1 + (uint64_t)len + 3) & ~3ull;
+        uint64_t aw = 4;
+        for (size_t r = 0; r < cls.size();) {
+            const uint32_t len = cls[r];
+            const uint32_t *c = &cls[r + 1];
+            if (len == 3) {
+                if (owns(t, c[0])) slots[tpos[c[0]]++] = Slot{c[1], c[2]};
+                if (owns(t, c[1])) slots[tpos[c[1]]++] = Slot{c[0], c[2]};
+                if (owns(t, c[2])) slots[tpos[c[2]]++] = Slot{c[0], c[1]};
+            } else if (len > 3) {
+                const uint32_t cref = (uint32_t)(aw / 4);
+                if (t == 0) {
+                    arena[aw] = len;
+                    std::memcpy(&arena[aw + 1], c, (size_t)len * 4);
+                }
+                for (uint32_t i = 0; i < len; ++i)
+                    if (owns(t, c[i])) slots[lpos[c[i]]++] = Slot{c[(i + 1) % len], cref};
+                aw += (1 + (uint64_t)len + 3) & ~3ull;
+            }
+            r += 1 + len;
         }
-        r += 1 + len;
-    }
+    });
     return "";
 }
 

@@ -197,3 +197,22 @@ def test_normaliser_on_seeded_random_clause_streams():
             check_rows(t, kept, max_var)
             n_rows += 1
     assert n_contra > 10 and n_rows > 100
+
+
+def test_row_build_does_not_depend_on_the_thread_count(golden):
+    """The multi-threaded flattening (owner-computes by literal block) produces the same database, entry for entry
+    and in the same order, as one thread."""
+    import subprocess, sys, json
+    prog = (
+        "import sys, json, numpy as np; sys.path.insert(0, %r); "
+        "from intel_sat_solver_b200 import BatchedTopor; g = np.load(%r); out = {}\n"
+        "for name in ['fuzz_10', 'fuzz_3', 'regr_66', 'hand_long']:\n"
+        "    t = BatchedTopor(); t.AddClauses(g[name + '/words']); t.HostPrepare(); mv = t.max_var\n"
+        "    out[name] = [t.HostRow(l).tolist() for l in range(2, 2 * mv + 2)]\n"
+        "print(json.dumps(out))" % (ROOT, os.path.join(ROOT, "tests", "golden", "golden.npz")))
+    rows = {}
+    for th in ("1", "4", "8"):
+        env = dict(os.environ, BBCP_HOST_THREADS=th)
+        rows[th] = json.loads(subprocess.run([sys.executable, "-c", prog], check=True, capture_output=True, text=True, env=env).stdout)
+    assert rows["1"] == rows["4"] == rows["8"]
+    assert sum(len(r) for r in rows["1"]["fuzz_10"]) > 10000
