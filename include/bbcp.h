@@ -54,6 +54,8 @@ enum {
                                   unit bitmaps (bbcp_merge_bitmaps) runs as the last kernel of the batch, no host round trip */
     BBCP_OPT_RENDEZVOUS = 32u, /* bbcp_probe_range with peers attached: wait on the device for every peer before the batch
                                   starts (aligns the ranks' device clocks; every rank must pass the same flags) */
+    BBCP_OPT_NO_REUSE = 64u,   /* diagnostic: all-literal batches propagate every probe from scratch (no adoption of the
+                                  finished probes' results, DESIGN.md "closure reuse"); results are identical */
     BBCP_OPT_OFF32 = 4u        /* produce impl_off as uint32 (fetch with bbcp_fetch_implied32): halves the offset
                                   read-back; the batch fails with BBCP_ERR_ARG if it implies >= 2^32 literals */
 };
@@ -90,6 +92,13 @@ typedef struct {
     uint64_t n_mid;            /* probes that ran in the second tier (warp per probe, hash + trail in a global slab) */
     float compact_ms;          /* device time of k_scan_gather (+ k_gather_long), last sequence */
     float merge_ms;            /* device time of the in-batch bitmap all-gather (BBCP_OPT_MERGE), incl. waiting for peers */
+    /* closure reuse (all-literal batches): finished probes whose implied set was adopted by a later probe, the literals
+     * read back that way, and probes decided by a finished probe's conflict / tier overflow */
+    uint64_t adopted, adopt_lits, inherited;
+    /* the reference's other two counters on this path: Assign calls (m_Assignments, TopiAsg.cc:49: every literal put on
+     * a trail, decisions included) and BCP() calls (m_BCPs, TopiBcp.cc:176: one per decision level opened, i.e. per
+     * probe, and per cube literal that was still unassigned when its turn came -- see DESIGN.md on what is exact) */
+    uint64_t assignments, bcps;
 } bbcp_batch_info;
 
 typedef struct {
@@ -127,6 +136,11 @@ uint64_t bbcp_level0_lits(const bbcp_handle *h, int32_t *out, uint64_t cap);
 /* row of internal literal ilit (= 2*var + neg) as built on the host: copies up to cap words of
  * [nbin, ntern, nlong, bins..., tern pairs..., long (blocker, clause lits...)...]; returns words needed */
 uint64_t bbcp_host_row(const bbcp_handle *h, uint32_t ilit, uint32_t *out, uint64_t cap);
+
+/* the probe schedule of the prepared database (DESIGN.md "closure reuse"): every internal literal 2..2*max_var+1,
+ * sorted so that q comes before p whenever the binary clause (not-p or q) exists and p, q are not equivalent; empty (0)
+ * for a database without binary clauses. Copies up to cap entries, returns the count. Host only. */
+uint64_t bbcp_host_order(bbcp_handle *h, uint32_t *out, uint64_t cap);
 
 /* ---- status: CTopor::IsError / GetStatusExplanation (Topor.hpp:111-114) */
 int bbcp_status(const bbcp_handle *h);

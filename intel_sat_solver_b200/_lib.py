@@ -19,7 +19,8 @@ class BatchInfo(C.Structure):
                 ("triage_bytes", C.c_uint64), ("n_deep", C.c_uint64),
                 ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("tier1_ms", C.c_float),
                 ("triage_ms", C.c_float), ("deep_ms", C.c_float), ("block_ms", C.c_float), ("mid_ms", C.c_float), ("n_mid", C.c_uint64),
-                ("compact_ms", C.c_float), ("merge_ms", C.c_float)]
+                ("compact_ms", C.c_float), ("merge_ms", C.c_float),
+                ("adopted", C.c_uint64), ("adopt_lits", C.c_uint64), ("inherited", C.c_uint64), ("assignments", C.c_uint64), ("bcps", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -46,6 +47,7 @@ _SIGS = {
     "bbcp_get_db_info": (C.c_int, [C.c_void_p, C.POINTER(DbInfo)]),
     "bbcp_level0_lits": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "bbcp_host_row": (C.c_uint64, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "bbcp_host_order": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "bbcp_status": (C.c_int, [C.c_void_p]),
     "bbcp_error_string": (C.c_char_p, [C.c_void_p]),
     "bbcp_propagate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Opts), C.POINTER(BatchInfo)]),

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -18,8 +19,9 @@ namespace {
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
-    // grow-only; contents are not preserved
-    bool reserve(size_t need, bool zero = false)
+    // grow-only; contents are not preserved. zero: the new allocation is cleared ON `zs` (the stream the kernels that
+    // rely on the zeroes run on -- the handle's stream is non-blocking, so the legacy stream would not order with it)
+    bool reserve(size_t need, bool zero = false, cudaStream_t zs = nullptr)
     {
         if (need <= bytes && p) return true;
         if (p) cudaFree(p);
@@ -32,7 +34,7 @@ struct DevBuf {
             if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
         }
         bytes = want;
-        if (zero) cudaMemset(p, 0, bytes);
+        if (zero) cudaMemsetAsync(p, 0, bytes, zs);
         return true;
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
@@ -65,7 +67,8 @@ struct bbcp_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
-    DevBuf d_hdr, d_slots, d_arena, d_litinfo;
+    DevBuf d_hdr, d_slots, d_arena, d_litinfo, d_order;
+    uint32_t order_n = 0;   // entries of the probe schedule on the device (0: none)
     // ONE allocation shared with peer GPUs (CUDA IPC): [failed: bm_stride words][unit: bm_stride words]
     // [arrival flags: one u32 per rank][push-done counter], see bbcp_merge_bitmaps
     DevBuf d_bitmaps;
@@ -99,7 +102,7 @@ struct bbcp_handle {
     DevBuf d_mid_slab;           // second tier: per-warp hash + trail
     uint32_t mid_slab_cap = 0;   // trail capacity the slab is laid out (and zeroed) for
     uint64_t mid_slab_groups = 0;
-    uint32_t slab_version = 0;   // db_version the slabs were sized for
+    int32_t slab_max_var = -1;   // variable range the third-tier slabs are laid out for
 
     uint64_t last_n = 0, last_n_implied = 0, last_first = 0;
     bool last_universe = false, last_implied = false;
@@ -147,7 +150,7 @@ bool ensure_device(bbcp_handle *h)
     if (!h->cuda_ok(cudaHostAlloc(&h->h_misc, MISC_WORDS64 * 8, cudaHostAllocMapped), "cudaHostAlloc")) return false;
     if (!h->cuda_ok(cudaHostGetDevicePointer(&h->d_hmisc, h->h_misc, 0), "cudaHostGetDevicePointer")) return false;
     h->lean = getenv("BBCP_LEAN") ? atoi(getenv("BBCP_LEAN")) : 3;
-    if (!h->d_misc.reserve(2 * MISC_WORDS64 * 8, true)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (counters)"); return false; }
+    if (!h->d_misc.reserve(2 * MISC_WORDS64 * 8, true, h->stream)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (counters)"); return false; }
     if (!h->cuda_ok(cudaDeviceSynchronize(), "counter init")) return false;
     h->device_ready = true;
     return true;
@@ -160,7 +163,7 @@ bool upload(bbcp_handle *h, DevBuf &b, const void *src, size_t bytes)
     return true;
 }
 
-bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo)
+bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo, bool with_order)
 {
     HostDb &db = h->db;
     // per-literal facts for the triage: level-0 value and mappedness of the variable, and what the row of
@@ -180,6 +183,16 @@ bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo)
     if (!upload(h, h->d_slots, db.slots.data(), db.slots.size() * sizeof(Slot))) return false;
     if (!upload(h, h->d_arena, db.arena.data(), db.arena.size() * 4)) return false;
     if (!upload(h, h->d_litinfo, litinfo.data(), litinfo.size())) return false;
+    // probe schedule for closure reuse (only databases with binary clauses have one)
+    static const bool no_order = getenv("BBCP_NO_ORDER") != nullptr;
+    h->order_n = 0;
+    if (with_order && !no_order) {
+        db.build_order();
+        if (!db.order.empty()) {
+            if (!upload(h, h->d_order, db.order.data(), db.order.size() * 4)) return false;
+            h->order_n = (uint32_t)db.order.size();
+        }
+    }
     h->bitmap_words = (2 * ((uint64_t)db.max_var + 1) + 31) / 32;
     const uint64_t stride = (h->bitmap_words + 3) & ~3ull;
     if (stride != h->bm_stride || !h->d_bitmaps.p) {
@@ -194,7 +207,7 @@ bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo)
         cudaMemsetAsync(h->d_bitmaps.p, 0, 2 * stride * 4, h->stream);   // keep the arrival flags: they are monotonic epochs
     }
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "upload sync")) return false;
-    h->device_db_bytes = db.hdr.size() * sizeof(RowHdr) + db.slots.size() * sizeof(Slot) + db.arena.size() * 4 + litinfo.size() + 2 * h->bitmap_words * 4;
+    h->device_db_bytes = db.hdr.size() * sizeof(RowHdr) + db.slots.size() * sizeof(Slot) + db.arena.size() * 4 + litinfo.size() + 2 * h->bitmap_words * 4 + (size_t)h->order_n * 4;
     return true;
 }
 
@@ -229,7 +242,7 @@ uint32_t pow2_at_least(uint32_t x) { uint32_t p = 32; while (p < x) p <<= 1; ret
 // third-tier slabs: one dense assignment + trail per resident CTA, sized for the whole variable range
 bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
 {
-    if (h->d_lbits.p && h->slab_version == h->db_version + 1) return true;
+    if (h->d_lbits.p && h->slab_max_var == dbv.max_var) return true;   // keyed on what sizes the slabs, not on the database version
     const size_t per_slab = (size_t)dbv.nvars_words16 * 4 + ((size_t)dbv.max_var + 1) * 4;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
@@ -242,9 +255,10 @@ bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
     if (const char *e = getenv("BBCP_BIG_SLABS_PER_SM")) per_sm = std::max(1, atoi(e));
     uint64_t slabs = std::min<uint64_t>((uint64_t)h->sm_count * per_sm, (free_b / 4) / std::max<size_t>(per_slab, 1));
     slabs = std::max<uint64_t>(slabs, 1);
-    if (!h->d_lbits.reserve(slabs * dbv.nvars_words16 * 4, true) || !h->d_ltrail.reserve(slabs * ((size_t)dbv.max_var + 1) * 4)) return false;
+    h->slab_max_var = -1;
+    if (!h->d_lbits.reserve(slabs * dbv.nvars_words16 * 4, true, h->stream) || !h->d_ltrail.reserve(slabs * ((size_t)dbv.max_var + 1) * 4)) return false;
     h->big_slabs = (uint32_t)slabs;
-    h->slab_version = h->db_version + 1;
+    h->slab_max_var = dbv.max_var;
     return true;
 }
 
@@ -309,6 +323,12 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.tile_sum = h->d_tiles.as<unsigned long long>();
     b.zero_words = MISC_WORDS64;
     b.opts = opts.flags;
+    // closure reuse: all-literal batches only (item i is the probe of internal literal first + i + 2)
+    static const bool no_reuse = getenv("BBCP_NO_REUSE") != nullptr;
+    if (!d_lits && !d_off && !no_reuse && !(opts.flags & BBCP_OPT_NO_REUSE)) {
+        b.reuse = 1;
+        if (h->order_n) { b.order = h->d_order.as<uint32_t>(); b.order_n = h->order_n; }
+    }
 
     const int bps = small_blocks_per_sm(cap, width);
     if (bps <= 0) return h->fail(BBCP_ERR_CUDA, "propagate kernel does not fit (shared memory)");
@@ -337,6 +357,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
             // the third tier's slabs were sized when memory was plentiful: give most of them back and try again
             h->d_lbits.release();
             h->d_ltrail.release();
+            h->slab_max_var = -1;
             h->slab_budget_per_sm = 1;
         }
         if (!pool_ok() ||
@@ -481,6 +502,9 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     bi.n_conflict = h->h_misc[C_CONFLICT];
     bi.n_skipped = h->h_misc[C_SKIPPED];
     bi.n_deep = h_u32[5];
+    bi.adopted = h->h_misc[C_ADOPTED];
+    bi.adopt_lits = h->h_misc[C_ADOPT_LITS];
+    bi.inherited = h->h_misc[C_INHERITED];
     // bytes model: triage = 1 B of literal facts + 1 B flag + 4 B size per item (+ 4 B literal for
     // probe lists, + 16 B offsets more for cubes); propagation = row headers, row slots, clause units, stored
     // implied literals (kernel counters) + the per-item record (flag, size, position) of the queued items;
@@ -538,7 +562,7 @@ void bbcp_release(bbcp_handle *h)
         for (auto &e : h->ev_merge) if (e) cudaEventDestroy(e);
         for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_bitmaps, &h->d_peer_tab, &h->rs[0].flag, &h->rs[0].off, &h->rs[0].impl, &h->rs[1].flag, &h->rs[1].off, &h->rs[1].impl, &h->d_raw_off, &h->d_len,
                           &h->d_out, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_big, &h->d_deep, &h->d_chunks, &h->d_misc, &h->d_lbits,
-                          &h->d_ltrail, &h->d_tiles, &h->d_mid_slab, &h->d_products})
+                          &h->d_ltrail, &h->d_tiles, &h->d_mid_slab, &h->d_products, &h->d_order})
             b->release();
         if (h->h_misc) cudaFreeHost(h->h_misc);
         for (auto &e : h->ev_in) if (e) cudaEventDestroy(e);
@@ -569,16 +593,23 @@ static int intake_guard(bbcp_handle *h)
     return BBCP_OK;
 }
 
+// internal literals are 2*var+neg in 32 bits with bit 31 reserved (TRAIL_CLOSED, placeholder values): variables stop
+// below 2^30. The reference reports STATUS_INDEX_TOO_NARROW for what its index type cannot hold (TopiConflictAnalysis.cc:67-71)
+static inline bool lit_in_range(int32_t l) { return l > -(1 << 30) && l < (1 << 30); }
+static const char *const LIT_RANGE_MSG = "literal out of range (|literal| must be below 2^30)";
+
 int bbcp_add(bbcp_handle *h, int32_t lit)
 {
     int rc = intake_guard(h);
     if (rc) return rc;
-    if (lit == INT32_MIN) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, "literal out of range");
+    if (!lit_in_range(lit)) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, LIT_RANGE_MSG);
+    try {
     h->db.pending.push_back(lit);
     if (lit == 0) {
         h->db.add_words(h->db.pending.data(), h->db.pending.size());
         h->db.pending.clear();
     }
+    } catch (const std::bad_alloc &) { return h->fail(BBCP_ERR_ALLOC, "host allocation failed (clause intake)"); }
     return BBCP_OK;
 }
 
@@ -588,12 +619,14 @@ int bbcp_add_clause(bbcp_handle *h, const int32_t *lits, size_t n)
     if (rc) return rc;
     size_t m = 0;
     while (m < n && lits[m] != 0) {
-        if (lits[m] == INT32_MIN) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, "literal out of range");
+        if (!lit_in_range(lits[m])) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, LIT_RANGE_MSG);
         ++m;
     }
-    h->db.add_words(lits, m);
-    const int32_t z = 0;
-    h->db.add_words(&z, 1);
+    try {
+        h->db.add_words(lits, m);
+        const int32_t z = 0;
+        h->db.add_words(&z, 1);
+    } catch (const std::bad_alloc &) { return h->fail(BBCP_ERR_ALLOC, "host allocation failed (clause intake)"); }
     return BBCP_OK;
 }
 
@@ -602,12 +635,29 @@ int bbcp_add_clauses(bbcp_handle *h, const int32_t *words, uint64_t nwords)
     int rc = intake_guard(h);
     if (rc) return rc;
     if (nwords && words[nwords - 1] != 0) return h->fail(BBCP_ERR_ARG, "clause stream must end with 0");
-    for (uint64_t i = 0; i < nwords; ++i) if (words[i] == INT32_MIN) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, "literal out of range");
-    h->db.add_words(words, nwords);
+    for (uint64_t i = 0; i < nwords; ++i) if (!lit_in_range(words[i])) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, LIT_RANGE_MSG);
+    try { h->db.add_words(words, nwords); }
+    catch (const std::bad_alloc &) { return h->fail(BBCP_ERR_ALLOC, "host allocation failed (clause intake)"); }
     return BBCP_OK;
 }
 
+static int host_prepare_impl(bbcp_handle *h);
+static int finalize_impl(bbcp_handle *h);
+
+// no exception crosses the C ABI: a host allocation failure becomes BBCP_ERR_ALLOC (the reference's STATUS_ALLOC_FAILED)
 int bbcp_host_prepare(bbcp_handle *h)
+{
+    try { return host_prepare_impl(h); }
+    catch (const std::bad_alloc &) { return h->fail(BBCP_ERR_ALLOC, "host allocation failed (database build)"); }
+}
+
+int bbcp_finalize(bbcp_handle *h)
+{
+    try { return finalize_impl(h); }
+    catch (const std::bad_alloc &) { return h->fail(BBCP_ERR_ALLOC, "host allocation failed (database build)"); }
+}
+
+static int host_prepare_impl(bbcp_handle *h)
 {
     if (!h) return BBCP_ERR_ARG;
     if (h->status < 0) return h->status;
@@ -620,7 +670,7 @@ int bbcp_host_prepare(bbcp_handle *h)
     return BBCP_OK;
 }
 
-int bbcp_finalize(bbcp_handle *h)
+static int finalize_impl(bbcp_handle *h)
 {
     if (!h) return BBCP_ERR_ARG;
     if (h->status < 0) return h->status;
@@ -630,7 +680,7 @@ int bbcp_finalize(bbcp_handle *h)
     h->solved = false;
     if (!ensure_device(h)) return h->status;
     cudaSetDevice(h->device);
-    int rc = bbcp_host_prepare(h);
+    int rc = host_prepare_impl(h);
     if (rc == BBCP_CONTRADICTORY) { h->finalized = true; ++h->db_version; return rc; }
     if (rc) return rc;
     HostDb &db = h->db;
@@ -639,7 +689,7 @@ int bbcp_finalize(bbcp_handle *h)
         // database (Topi.cc:1137-1160 runs BCP() at level 0 before anything else)
         std::vector<uint8_t> mapped_only(db.varinfo);
         for (auto &v : mapped_only) v &= 4;
-        if (!upload_db(h, mapped_only)) return h->status;
+        if (!upload_db(h, mapped_only, false)) return h->status;
         std::vector<int32_t> cube(db.units.size());
         for (size_t i = 0; i < cube.size(); ++i) cube[i] = (db.units[i] & 1) ? -(int32_t)(db.units[i] >> 1) : (int32_t)(db.units[i] >> 1);
         const uint64_t off[2] = {0, cube.size()};
@@ -664,7 +714,7 @@ int bbcp_finalize(bbcp_handle *h)
         if (!e.empty()) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, e);
         h->total_props = 0;
     }
-    if (!upload_db(h, db.varinfo)) return h->status;
+    if (!upload_db(h, db.varinfo, true)) return h->status;
     h->finalized = true;
     h->have_batch = false;
     ++h->db_version;
@@ -719,6 +769,14 @@ uint64_t bbcp_host_row(const bbcp_handle *h, uint32_t ilit, uint32_t *out, uint6
     }
     for (size_t i = 0; i < w.size() && i < cap; ++i) out[i] = w[i];
     return w.size();
+}
+
+uint64_t bbcp_host_order(bbcp_handle *h, uint32_t *out, uint64_t cap)
+{
+    if (!h || !h->prepared) return 0;
+    try { h->db.build_order(); } catch (const std::bad_alloc &) { h->fail(BBCP_ERR_ALLOC, "host allocation failed (probe schedule)"); return 0; }
+    for (size_t i = 0; i < h->db.order.size() && i < cap; ++i) out[i] = h->db.order[i];
+    return h->db.order.size();
 }
 
 int bbcp_status(const bbcp_handle *h) { return h ? h->status : BBCP_ERR_ARG; }

@@ -252,6 +252,68 @@ std::string HostDb::build_rows()
     return "";
 }
 
+void HostDb::build_order()
+{
+    order.clear();
+    max_height = 0;
+    if (n_bin == 0 || hdr.size() < 4) return;
+    const size_t nl = hdr.size();
+    // successors of p = the binary partners in the row scanned when p becomes true (the row of not-p)
+    auto nsucc = [&](uint32_t p) { return hdr[p ^ 1u].nbin; };
+    auto succ = [&](uint32_t p, uint32_t j) {
+        const Slot &s = slots[hdr[p ^ 1u].start + j / 2];
+        return (j & 1) ? s.y : s.x;
+    };
+    std::vector<uint32_t> index(nl, 0), low(nl, 0), it(nl, 0), height(nl, 0);
+    std::vector<uint8_t> onstack(nl, 0);
+    std::vector<uint32_t> stack, call;
+    uint32_t counter = 0;
+    for (uint32_t root = 2; root < nl; ++root) {
+        if (index[root] || nsucc(root) == 0) continue;   // literals without successors are complete at height 0
+        index[root] = low[root] = ++counter;
+        stack.push_back(root);
+        onstack[root] = 1;
+        call.push_back(root);
+        while (!call.empty()) {
+            const uint32_t p = call.back();
+            if (it[p] < nsucc(p)) {
+                const uint32_t q = succ(p, it[p]++);
+                if (nsucc(q) == 0) continue;
+                if (!index[q]) {
+                    index[q] = low[q] = ++counter;
+                    stack.push_back(q);
+                    onstack[q] = 1;
+                    call.push_back(q);
+                } else if (onstack[q]) low[p] = std::min(low[p], index[q]);
+                continue;
+            }
+            call.pop_back();
+            if (!call.empty()) low[call.back()] = std::min(low[call.back()], low[p]);
+            if (low[p] != index[p]) continue;
+            // p closes a component: its members are the stack entries from p upwards; every successor outside of it
+            // is complete, so the component's height is known now
+            size_t base = stack.size();
+            while (stack[--base] != p) {}
+            uint32_t h = 0;
+            for (size_t k = base; k < stack.size(); ++k) {
+                const uint32_t m = stack[k];
+                for (uint32_t j = 0, n = nsucc(m); j < n; ++j) {
+                    const uint32_t q = succ(m, j);
+                    if (!onstack[q]) h = std::max(h, height[q] + 1);
+                }
+            }
+            for (size_t k = base; k < stack.size(); ++k) { height[stack[k]] = h; onstack[stack[k]] = 0; }
+            stack.resize(base);
+            max_height = std::max(max_height, h);
+        }
+    }
+    std::vector<uint64_t> start((size_t)max_height + 2, 0);
+    for (size_t l = 2; l < nl; ++l) ++start[height[l] + 1];
+    for (size_t h = 0; h <= max_height; ++h) start[h + 1] += start[h];
+    order.resize(nl - 2);
+    for (size_t l = 2; l < nl; ++l) order[start[height[l]]++] = (uint32_t)l;
+}
+
 uint64_t HostDb::n_mapped() const
 {
     uint64_t n = 0;

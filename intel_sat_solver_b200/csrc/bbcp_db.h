@@ -31,6 +31,11 @@ struct HostDb {
     std::vector<uint32_t> arena;      // 4-word aligned clauses [size, lits..., 0 pad]
     uint64_t n_bin = 0, n_tern = 0, n_long = 0, n_long_lits = 0;
 
+    // ---- after build_order(): the internal literals 2..2*(max_var+1)-1 sorted by their height in the binary
+    // implication graph (children first). Empty when the database has no binary clause.
+    std::vector<uint32_t> order;
+    uint32_t max_height = 0;
+
     void add_words(const int32_t *w, uint64_t n);
     // AddUserClause semantics over the whole raw stream; fills varinfo (mapped + direct units), cls, units
     void normalise();
@@ -39,6 +44,12 @@ struct HostDb {
     bool simplify_level0();
     // flatten cls into hdr/slots/arena. Returns an error string ("" = ok)
     std::string build_rows();
+    // Probe schedule for closure reuse (bbcp_propagate.cuh, expand_closures): p -> q is an edge when the binary clause
+    // (not-p or q) exists, so closure(q) is a subset of closure(p). Strongly connected components (equivalent literals)
+    // are found with an iterative Tarjan pass, which completes them in reverse topological order, so the height of a
+    // component (1 + the largest height among its successors) is known the moment it completes. Literals are then
+    // counting-sorted by height. Needs build_rows().
+    void build_order();
     uint64_t n_mapped() const;
     uint64_t n_level0() const;
 };

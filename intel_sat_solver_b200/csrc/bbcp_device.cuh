@@ -30,7 +30,7 @@ struct DbView {
 constexpr uint8_t LI_TRUE_L0 = 1, LI_FALSE_L0 = 2, LI_MAPPED = 4, LI_HAS_BIN = 8, LI_NONEMPTY = 16;
 constexpr uint32_t LEN_SELF = 0x80000000u;   // len[] flag: the implied set is the item's own literal (not stored)
 
-enum Counter { C_PROPS_ALL = 0, C_PROPS_REF, C_SLOTS, C_CLAUSE_FETCH, C_BYTES, C_LARGE, C_MID, C_OK, C_CONFLICT, C_SKIPPED, C_N };
+enum Counter { C_PROPS_ALL = 0, C_PROPS_REF, C_SLOTS, C_CLAUSE_FETCH, C_BYTES, C_LARGE, C_MID, C_OK, C_CONFLICT, C_SKIPPED, C_ADOPTED, C_ADOPT_LITS, C_INHERITED, C_N };
 
 struct BatchView {
     // input: cubes (external literals, CSR); or, when cube_off == nullptr, a list of probe literals
@@ -70,13 +70,23 @@ struct BatchView {
     unsigned long long *zero_next;    // the counter block of the NEXT launch sequence, zeroed by k_triage
     uint32_t zero_words;
     uint32_t opts;
+    // closure reuse (universe batches only): order[] = every internal literal sorted by its height in the binary
+    // implication graph, children first (HostDb::build_order); the first tier takes its probes in that order, and a probe
+    // that reaches a literal whose own probe has finished adopts that result (expand_closures). nullptr: triage queue order.
+    const uint32_t *order;
+    uint32_t order_n;
+    uint32_t reuse;             // 1: item i of this batch is the probe of internal literal first + i + 2 and may be looked up
 };
 
 constexpr uint32_t OPT_IMPLIED = 1u;
 constexpr uint32_t OPT_NO_LEN_PRUNE = 2u;
 constexpr uint32_t OPT_OFF32 = 4u;
 constexpr uint8_t FLAG_OK = 0, FLAG_CONFLICT = 1, FLAG_TRIVIAL_L0 = 2, FLAG_FALSE_L0 = 3, FLAG_UNMAPPED = 4;
-constexpr uint8_t FLAG_OVERFLOW = 250;      // internal: re-run in the global-state tier
+constexpr uint8_t FLAG_OVERFLOW = 250;      // internal: outgrew the first tier, queued for the second (global hash state)
+constexpr uint8_t FLAG_OVERFLOW2 = 249;     // internal: outgrew the second tier, queued for the third (dense state)
+constexpr uint8_t FLAG_QUEUED = 255;        // internal: written by the triage for items that wait for the first tier
+constexpr uint32_t TRAIL_CLOSED = 0x80000000u;  // trail entry mark: the literal came in with a finished closure, so every
+                                                // binary clause of its row is already satisfied (only longer clauses are re-examined)
 constexpr uint8_t FLAG_OUT_OVERFLOW = 251;  // internal: implied-literal buffer full, re-run in a later launch
 
 struct LargeState {

@@ -64,7 +64,7 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
     unsigned long long off = 0;
     if (res == 2) {
         flag = FLAG_OVERFLOW;
-        if (lane == 0) b.mid_list[atomicAdd(b.mid_count, 1u)] = (uint32_t)item;
+        if (lane == 0) b.mid_list[atomicAdd(b.mid_count, 1u)] = (uint32_t)item;   // queued before the flag shows (expand_closures)
     } else if (res == 1) {
         flag = FLAG_CONFLICT;
         if (it.probe_lit && lane == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
@@ -73,22 +73,21 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
         if (b.opts & OPT_IMPLIED) {
             uint32_t n2 = 1;
             while (n2 < tail) n2 <<= 1;
-            for (uint32_t i = tail + lane; i < n2; i += G::width) st.trail[i] = 0xffffffffu;
+            for (uint32_t i = lane; i < n2; i += G::width) st.trail[i] = i < tail ? (st.trail[i] & ~TRAIL_CLOSED) : 0xffffffffu;
             G::sync();
             if (tail > 1) bitonic_sort<G>(st.trail, n2);
             off = out_alloc<G>(b, tail);
             if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
             else {
+                // the pool holds INTERNAL literals (ascending = ascending variable): other probes adopt the set as it is
+                // (expand_closures); k_scan_gather turns it into external literals on its way to the canonical place
                 len = tail;
-                for (uint32_t i = lane; i < tail; i += G::width) b.out_lits[off + i] = to_ext(st.trail[i]);
+                for (uint32_t i = lane; i < tail; i += G::width) b.out_lits[off + i] = (int32_t)st.trail[i];
                 wc.bytes += 4ull * tail;
             }
         }
     }
-    if (lane == 0) {
-        b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
-        if (len) atomicAdd(&b.tile_sum[item / SG_TILE], (unsigned long long)len);
-    }
+    publish_result<G>(b, item, flag, len, off);
     wc.n_ok += flag == FLAG_OK;
     wc.n_conf += flag == FLAG_CONFLICT;
     G::sync();
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
             uint32_t pos = 0;
             if (lane_id() == 0) pos = atomicAdd(b.deep_count, total);
             pos = __shfl_sync(FULL, pos, 0) + incl - cnt;
-            uint32_t m = deepmask;
+            uint32_t m = b.order ? 0u : deepmask;   // with a probe schedule (b.order) the first tier finds the queued items by their flag
             while (m) {
                 const int k = __ffs(m) - 1;
                 m &= m - 1;
@@ -270,23 +269,49 @@ k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t
 
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
     WorkCounters wc;
+    // work: the triage queue in queue order, or -- all-literal batches over a database with binary clauses -- the
+    // height-sorted schedule b.order, ORDER_CHUNK positions per ticket, of which the ones that name a queued item of
+    // this batch are taken (a sharded range sees only its own part of the schedule)
+    constexpr uint32_t ORDER_CHUNK = 8;
+    unsigned pending = 0;
+    uint32_t mine = 0;
     for (;;) {
-        unsigned t = 0;
-        if (lane == 0) t = atomicAdd(b.ticket, 1u);
-        t = G::shfl(t, 0);
-        if (t >= ndeep) break;
-        const uint64_t it_idx = b.deep_list[t];
-        BBCP_CHECK(it_idx < b.n, "deep_list[%u] = %llu of %llu (ndeep %u)\n", t, (unsigned long long)it_idx, (unsigned long long)b.n, ndeep);
+        uint64_t it_idx;
+        if (b.order) {
+            while (!pending) {
+                unsigned t = 0;
+                if (lane == 0) t = atomicAdd(b.ticket, ORDER_CHUNK);
+                t = G::shfl(t, 0);
+                if (t >= b.order_n) break;
+                bool ok = false;
+                if (lane < (int)ORDER_CHUNK && t + lane < b.order_n) {
+                    const uint64_t u = (uint64_t)__ldg(&b.order[t + lane]) - 2u;
+                    if (u >= b.first && u - b.first < b.n) { mine = (uint32_t)(u - b.first); ok = b.flag[mine] == FLAG_QUEUED; }
+                }
+                pending = G::ballot(ok);
+            }
+            if (!pending) break;
+            const int k = __ffs(pending) - 1;
+            pending &= pending - 1;
+            it_idx = G::shfl(mine, k);
+        } else {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(b.ticket, 1u);
+            t = G::shfl(t, 0);
+            if (t >= ndeep) break;
+            it_idx = b.deep_list[t];
+        }
+        BBCP_CHECK(it_idx < b.n, "queued item %llu of %llu (ndeep %u)\n", (unsigned long long)it_idx, (unsigned long long)b.n, ndeep);
         const Item it = get_item(b, it_idx);
         GroupTail tl{0};
         int f = it.probe_lit ? load_probe<G>(db, st, it.probe_lit, tl) : load_cube<G>(db, st, it.lits, it.n, tl);
         int res;
-        if (f == 0xff) res = propagate<G>(db, st, tl, prune, wc);
+        if (f == 0xff) res = propagate<G>(db, b, st, tl, prune, 1, wc);
         else if (f == FLAG_OVERFLOW) res = 2;
         else if (f == FLAG_CONFLICT) res = 1;
         else {
             st.template cleanup<G>(tl.tail);
-            if (lane == 0) { b.flag[it_idx] = (uint8_t)f; b.len[it_idx] = 0; b.raw_off[it_idx] = 0; }
+            publish_result<G>(b, it_idx, (uint8_t)f, 0, 0);
             ++wc.n_skip;
             G::sync();
             continue;
@@ -326,12 +351,13 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
         GroupTail tl{0};
         const int f = it.probe_lit ? load_probe<G>(db, st, it.probe_lit, tl) : load_cube<G>(db, st, it.lits, it.n, tl);
         int res;
-        if (f == 0xff) res = propagate<G>(db, st, tl, prune, wc);
+        if (f == 0xff) res = propagate<G>(db, b, st, tl, prune, 2, wc);
         else if (f == FLAG_OVERFLOW) res = 2;
         else if (f == FLAG_CONFLICT) res = 1;
         else {
             st.template cleanup<G>(tl.tail);
-            if (lane == 0) { b.flag[item] = (uint8_t)f; b.len[item] = 0; b.raw_off[item] = 0; atomicAdd(&b.counters[C_MID], 1ull); }
+            publish_result<G>(b, item, (uint8_t)f, 0, 0);
+            if (lane == 0) atomicAdd(&b.counters[C_MID], 1ull);
             ++wc.n_skip;
             G::sync();
             continue;
@@ -341,7 +367,7 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
         unsigned long long off = 0;
         const uint32_t tail = tl.tail;
         if (res == 2) {
-            flag = FLAG_OVERFLOW;
+            flag = FLAG_OVERFLOW2;
             if (lane == 0) b.big_list[atomicAdd(b.big_count, 1u)] = (uint32_t)item;
             st.template wipe<G>();   // some table entries have no trail entry
         } else {
@@ -355,7 +381,7 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
                     if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
                     else {
                         len = tail;
-                        for (uint32_t i = lane; i < tail; i += W) b.out_lits[off + i] = (int32_t)st.tget(i);   // internal literals, trail order
+                        for (uint32_t i = lane; i < tail; i += W) b.out_lits[off + i] = (int32_t)(st.tget(i) & ~TRAIL_CLOSED);   // internal literals, trail order
                         if (lane == 0) b.sort_list[atomicAdd(b.sort_count, 1u)] = (uint32_t)item;
                         wc.bytes += 4ull * tail;
                     }
@@ -364,11 +390,8 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
             G::sync();
             st.template cleanup<G>(tail);
         }
-        if (lane == 0) {
-            b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
-            if (len) atomicAdd(&b.tile_sum[item / SG_TILE], (unsigned long long)len);
-            if (flag != FLAG_OVERFLOW) atomicAdd(&b.counters[C_MID], 1ull);
-        }
+        publish_result<G>(b, item, flag, len, off);
+        if (lane == 0 && flag != FLAG_OVERFLOW2) atomicAdd(&b.counters[C_MID], 1ull);
         wc.n_ok += flag == FLAG_OK;
         wc.n_conf += flag == FLAG_CONFLICT;
         G::sync();
@@ -377,7 +400,7 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
 }
 
 // Sorts the implied sets the second tier left unsorted in the pool (ascending internal literal = ascending
-// variable) and rewrites them as external literals. One CTA per set, in shared memory.
+// variable). One CTA per set, in shared memory.
 constexpr int SORT_THREADS = 256;
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_sets(const BatchView b, const uint32_t cap)
 {
@@ -403,7 +426,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_sets(const BatchView b, c
                 __syncthreads();
             }
         }
-        for (uint32_t i = threadIdx.x; i < len; i += SORT_THREADS) set[i] = to_ext(s_keys[i]);
+        for (uint32_t i = threadIdx.x; i < len; i += SORT_THREADS) set[i] = (int32_t)s_keys[i];
         __syncthreads();
     }
 }
@@ -413,7 +436,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_sets(const BatchView b, c
 // a per-CTA slab in global memory) and walk each breadth-first level of the trail together (level-synchronous,
 // two barriers per level).
 template <class S>
-__device__ void block_propagate(const DbView &db, S &st, uint32_t *ctl, bool prune, WorkCounters &wc)
+__device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uint32_t *ctl, bool prune, WorkCounters &wc)
 {
     using G = Grp<32>;
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -428,8 +451,9 @@ __device__ void block_propagate(const DbView &db, S &st, uint32_t *ctl, bool pru
         const bool bins_only = prune && level_end == 1;
         for (uint32_t bse = head + warp * 32; bse < level_end; bse += nwarps * 32) {
             const uint32_t B = min(32u, level_end - bse);
-            const uint32_t p = lane < (int)B ? st.tget(bse + lane) : 0u;
-            if (process_batch<G>(db, st, tl, p, B, bins_only, wc)) break;
+            const uint32_t e = lane < (int)B ? st.tget(bse + lane) : 0u;
+            if (b.reuse && level_end > 1 && expand_closures<G>(b, st, tl, e, B, 3, wc)) break;
+            if (process_batch<G>(db, st, tl, e, B, bins_only, wc)) break;
         }
         head = level_end;
     }
@@ -473,7 +497,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
         }
         __syncthreads();
         const uint32_t f = ctl[3];
-        if (f == 0xff) block_propagate(db, gs, ctl, prune, wc);
+        if (f == 0xff) block_propagate(db, b, gs, ctl, prune, wc);
         __syncthreads();
         const uint32_t tail = min(ctl[0], gs.cap);
         const bool conflict = ctl[1] != 0 || f == FLAG_CONFLICT;
@@ -499,7 +523,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
                         len = tail;
                         uint32_t vmin = 0xffffffffu, vmax = 0;
                         for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
-                            const uint32_t var = gs.tget(i) >> 1;
+                            const uint32_t var = (gs.tget(i) & ~TRAIL_CLOSED) >> 1;
                             vmin = min(vmin, var);
                             vmax = max(vmax, var);
                         }
@@ -534,7 +558,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
                                 m &= m - 1;
                                 const uint32_t var = wi * 16u + (uint32_t)(bpos >> 1);
                                 const bool isneg = ((word >> bpos) & 3u) == 2u;
-                                b.out_lits[o++] = isneg ? -(int32_t)var : (int32_t)var;
+                                b.out_lits[o++] = (int32_t)(2u * var + (isneg ? 1u : 0u));   // internal literals, as every set in the pool
                             }
                             w += total;
                             __syncthreads();
@@ -547,12 +571,16 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
         __syncthreads();
         // leave the state empty for the next probe
         for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
-            const uint32_t var = gs.tget(i) >> 1;
+            const uint32_t var = (gs.tget(i) & ~TRAIL_CLOSED) >> 1;
             atomicAnd(&gs.bits[var >> 4], ~(3u << ((var & 15u) * 2u)));
         }
+        if (b.reuse) __threadfence();   // every thread: its part of the set is out (publish_result, CTA-wide)
+        __syncthreads();
         if (threadIdx.x == 0) {
-            b.flag[item] = flag; b.len[item] = len; b.raw_off[item] = off;
+            b.len[item] = len; b.raw_off[item] = off;
             if (len) atomicAdd(&b.tile_sum[item / SG_TILE], (unsigned long long)len);
+            if (b.reuse) __threadfence();
+            *(volatile uint8_t *)&b.flag[item] = flag;
             atomicAdd(&b.counters[C_LARGE], 1ull);
             wc.n_ok += flag == FLAG_OK;
             wc.n_conf += flag == FLAG_CONFLICT;
@@ -789,7 +817,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
             uint64_t src = 0;
             if (l) src = b.raw_off[item];
             if (l && l <= GATHER_WARP) {
-                for (uint32_t i = 0; i < l; ++i) dst[o[j] + i] = b.out_lits[src + i];
+                for (uint32_t i = 0; i < l; ++i) dst[o[j] + i] = to_ext((uint32_t)b.out_lits[src + i]);
             }
             unsigned med = __ballot_sync(FULL, l > GATHER_WARP && l <= GATHER_BLOCK);
             while (med) {
@@ -797,7 +825,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
                 med &= med - 1;
                 const uint32_t ll = __shfl_sync(FULL, l, k);
                 const uint64_t ss = __shfl_sync(FULL, src, k), dd = __shfl_sync(FULL, o[j], k);
-                for (uint32_t i = lane; i < ll; i += 32) dst[dd + i] = b.out_lits[ss + i];
+                for (uint32_t i = lane; i < ll; i += 32) dst[dd + i] = to_ext((uint32_t)b.out_lits[ss + i]);
             }
             if (l > GATHER_BLOCK) {
                 const uint32_t e = atomicAdd(&s_nbig, 1u);
@@ -820,7 +848,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
                 continue;
             }
             const uint64_t ss = b.raw_off[item], dd = s_bigdst[e];
-            for (uint32_t i = tid; i < l; i += SG_THREADS) dst[dd + i] = b.out_lits[ss + i];
+            for (uint32_t i = tid; i < l; i += SG_THREADS) dst[dd + i] = to_ext((uint32_t)b.out_lits[ss + i]);
         }
         if (nbig) __syncthreads();
     }
@@ -865,7 +893,7 @@ __global__ void __launch_bounds__(256) k_gather_long(const BatchView b)
 #pragma unroll
         for (uint32_t k = 0; k < GATHER_CHUNK / 256; ++k) {
             const uint32_t i = k * 256 + threadIdx.x;
-            if (i < m) b.impl[d + i] = b.out_lits[src + i];
+            if (i < m) b.impl[d + i] = to_ext((uint32_t)b.out_lits[src + i]);
         }
     }
 }

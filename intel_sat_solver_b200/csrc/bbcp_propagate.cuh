@@ -141,7 +141,7 @@ struct GhashState {
         const uint32_t hs = 1u << log_hs, mask = hs - 1u;
         if (tail * 8u >= hs) { wipe<G>(); return; }
         for (uint32_t i = G::lane(); i < tail; i += G::width) {
-            const uint32_t lit = __ldcg(&trail[i]);
+            const uint32_t lit = __ldcg(&trail[i]) & ~TRAIL_CLOSED;
             uint32_t s = h(lit >> 1);
             while (__ldcg(&hash[s]) != lit) s = (s + 1) & mask;
             __stcg(&trail[i], s);
@@ -186,8 +186,8 @@ struct GmemState {
 
 // per-group work counters, kept in registers (uniform over the group) and flushed once
 struct WorkCounters {
-    unsigned long long props_all = 0, props_ref = 0, slots = 0, fetches = 0, bytes = 0;
-    uint32_t n_ok = 0, n_conf = 0, n_skip = 0;
+    unsigned long long props_all = 0, props_ref = 0, slots = 0, fetches = 0, bytes = 0, adopt_lits = 0;
+    uint32_t n_ok = 0, n_conf = 0, n_skip = 0, adopted = 0, inherited = 0;
     template <class G> __device__ void flush(unsigned long long *c)
     {
         if (G::lane() == 0) {
@@ -199,6 +199,9 @@ struct WorkCounters {
             if (n_ok) atomicAdd(&c[C_OK], (unsigned long long)n_ok);
             if (n_conf) atomicAdd(&c[C_CONFLICT], (unsigned long long)n_conf);
             if (n_skip) atomicAdd(&c[C_SKIPPED], (unsigned long long)n_skip);
+            if (adopted) atomicAdd(&c[C_ADOPTED], (unsigned long long)adopted);
+            if (adopt_lits) atomicAdd(&c[C_ADOPT_LITS], adopt_lits);
+            if (inherited) atomicAdd(&c[C_INHERITED], (unsigned long long)inherited);
         }
     }
 };
@@ -213,21 +216,25 @@ struct GroupTail {
     template <class G> __device__ __forceinline__ void latch_conflict() {}
     template <class G> __device__ __forceinline__ void drop() { tail = 0; }   // the state was wiped: nothing is on the trail
     // Commit one round of candidate implications (one candidate per lane, 0 = none). Group-converged.
-    // Returns 0 ok, 1 conflict, 2 state overflow.
-    template <class G, class S>
+    // ADOPT: the candidates are the literals of a finished closure -- pairwise distinct (no duplicate search) and
+    // entered on the trail with the TRAIL_CLOSED mark. Returns 0 ok, 1 conflict, 2 state overflow.
+    template <class G, class S, bool ADOPT = false>
     __device__ __forceinline__ int commit(S &st, uint32_t cand)
     {
         const bool has = cand != 0;
-        // same literal implied by several clauses in this step: keep the lowest lane (deterministic trail order)
-        const unsigned same = G::match_any(has ? cand : (0x80000000u | (uint32_t)G::lane()));
-        const bool leader = has && (G::lane() == __ffs(same) - 1);
+        bool leader = has;
+        if (!ADOPT) {
+            // same literal implied by several clauses in this step: keep the lowest lane (deterministic trail order)
+            const unsigned same = G::match_any(has ? cand : (0x80000000u | (uint32_t)G::lane()));
+            leader = has && (G::lane() == __ffs(same) - 1);
+        }
         uint32_t slot = 0;
         const int r = leader ? st.insert(cand, slot) : 1;
         const bool any_conf = G::any(r == 2);
         const unsigned newm = G::ballot(leader && r == 0);
         const uint32_t nnew = __popc(newm);
         if (tail + nnew > st.cap) return 2;  // caller wipes the whole table: the new entries are not on the trail
-        if (leader && r == 0) st.tset(tail + __popc(newm & G::lt()), cand, slot);
+        if (leader && r == 0) st.tset(tail + __popc(newm & G::lt()), ADOPT ? (cand | TRAIL_CLOSED) : cand, slot);
         tail += nnew;
         return any_conf ? 1 : 0;
     }
@@ -239,12 +246,15 @@ struct BlockTail {
     __device__ __forceinline__ bool aborted() const { return (*(volatile uint32_t *)&ctl[1] | *(volatile uint32_t *)&ctl[2]) != 0; }
     template <class G> __device__ __forceinline__ void latch_conflict() { if (G::lane() == 0) ctl[1] = 1; }
     template <class G> __device__ __forceinline__ void drop() {}   // (the dense third-tier state cannot overflow)
-    template <class G, class S>
+    template <class G, class S, bool ADOPT = false>
     __device__ __forceinline__ int commit(S &st, uint32_t cand)
     {
         const bool has = cand != 0;
-        const unsigned same = G::match_any(has ? cand : (0x80000000u | (uint32_t)G::lane()));
-        const bool leader = has && (G::lane() == __ffs(same) - 1);
+        bool leader = has;
+        if (!ADOPT) {
+            const unsigned same = G::match_any(has ? cand : (0x80000000u | (uint32_t)G::lane()));
+            leader = has && (G::lane() == __ffs(same) - 1);
+        }
         uint32_t slot = 0;
         const int r = leader ? st.insert(cand, slot) : 1;   // duplicates across warps: only one insert returns 0
         const bool any_conf = G::any(r == 2);
@@ -256,7 +266,7 @@ struct BlockTail {
             if (G::lane() == 0) pos = atomicAdd(&ctl[0], nnew);
             pos = G::shfl(pos, 0);
             if (pos + nnew > st.cap) { if (G::lane() == 0) ctl[2] = 1; ret = 2; }
-            else if (leader && r == 0) st.tset(pos + __popc(newm & G::lt()), cand, slot);
+            else if (leader && r == 0) st.tset(pos + __popc(newm & G::lt()), ADOPT ? (cand | TRAIL_CLOSED) : cand, slot);
         }
         if (any_conf) { if (G::lane() == 0) ctl[1] = 1; if (!ret) ret = 1; }
         return ret;
@@ -301,14 +311,19 @@ __device__ __forceinline__ uint32_t visit_long(const DbView &db, const S &st, ui
 // One group scans the rows of up to W newly true literals (lane i holds literal p for i < B): one header
 // gather, then the union of the rows is flattened and walked W eight-byte slots at a time.
 // Returns 0 ok, 1 conflict, 2 overflow.
+// e = trail entries: the literal, | TRAIL_CLOSED when it came in with a finished closure (then its binary clauses are
+// known to be satisfied and only the ternary / long part of its row is walked).
 template <class G, class S, class T>
-__device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t p, uint32_t B, bool bins_only, WorkCounters &wc)
+__device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_t B, bool bins_only, WorkCounters &wc)
 {
     constexpr int W = G::width;
     const int lane = G::lane();
+    const uint32_t p = e & ~TRAIL_CLOSED;
     uint4 hd = make_uint4(0, 0, 0, 0);
     BBCP_CHECK(lane >= (int)B || (p >= 2 && p < 2u * ((uint32_t)db.max_var + 1)), "trail literal %u (B %u lane %d blk %d thr %d)\n", p, B, lane, blockIdx.x, threadIdx.x);
     if (lane < (int)B) hd = __ldg(&db.hdr[p ^ 1u]);
+    wc.props_ref += __popc(G::ballot((hd.y | hd.z | hd.w) != 0));
+    if (e & TRAIL_CLOSED) { hd.x += (hd.y + 1u) >> 1; hd.y = 0; }
     const uint32_t nb2 = (hd.y + 1u) >> 1;
     const uint32_t cnt = bins_only ? nb2 : nb2 + hd.z + hd.w;
     uint32_t incl = cnt;
@@ -320,7 +335,6 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t p, uint32_
     const uint32_t excl = incl - cnt;
     const uint32_t total = G::shfl(incl, W - 1);
     wc.props_all += B;
-    wc.props_ref += __popc(G::ballot((hd.y | hd.z | hd.w) != 0));
     wc.slots += total;
     wc.bytes += 16ull * B + 8ull * total;
 
@@ -392,21 +406,95 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t p, uint32_
     return 0;
 }
 
+// Closure reuse. The lanes hold newly true literals of this probe (`e`, lane < B). If the batch is an all-literal pass,
+// literal q is itself an item of the batch, and when its own probe has already finished its result is adopted:
+//   conflict    UP(F and q) derives a conflict, and q is implied here, so this probe conflicts too;
+//   overflow    q's set outgrew this tier (it waits in a later tier's queue), and this probe's set contains it: hand
+//               this probe on right away instead of propagating up to the capacity first;
+//   fixpoint    every literal of q's implied set is implied here as well: the set is read back from the result pool
+//               (internal literals, coalesced) and entered 32 literals per step, marked TRAIL_CLOSED -- the set is closed
+//               under the binary clauses, so when those literals are dequeued only their ternary / long rows are walked.
+// This adds literals of the fixpoint EARLIER than the row scans would find them, nothing else: every trail literal
+// still gets its row walked, so the fixpoint, the conflict answer and the sorted implied set are unchanged (unit
+// propagation is confluent). What it changes is the shape of the work: the breadth-first frontier of a probe is a few
+// literals wide (the kernels were instruction-issue-bound at ~3 literals per 32-lane step), adopted sets fill the lanes.
+// `tier`: 1 shared-memory state, 2 global hash, 3 dense. Returns 0 / 1 conflict / 2 overflow.
+__device__ __forceinline__ uint8_t ld_flag(const uint8_t *p) { return *(const volatile uint8_t *)p; }
+
+template <class G, class S, class T>
+__device__ int expand_closures(const BatchView &b, S &st, T &tl, uint32_t e, uint32_t B, int tier, WorkCounters &wc)
+{
+    const int lane = G::lane();
+    const uint64_t u = (uint64_t)(e & ~TRAIL_CLOSED) - 2u - b.first;      // item index of the literal's own probe
+    const bool want = lane < (int)B && !(e & TRAIL_CLOSED) && (e & ~TRAIL_CLOSED) >= 2u + b.first && u < b.n;
+    const uint8_t f = want ? ld_flag(&b.flag[u]) : (uint8_t)FLAG_QUEUED;
+    if (G::any(f == FLAG_CONFLICT)) { tl.template latch_conflict<G>(); ++wc.inherited; return 1; }
+    if (tier < 3 && G::any(f == FLAG_OVERFLOW2 || (tier == 1 && f == FLAG_OVERFLOW))) { ++wc.inherited; return 2; }
+    unsigned m = G::ballot(f == FLAG_OK);
+    if (!m || !(b.opts & OPT_IMPLIED)) return 0;
+    __threadfence();   // the set was published before the flag (publish_result)
+    uint32_t len = 0;
+    unsigned long long off = 0;
+    if (f == FLAG_OK) {
+        len = __ldcg(&b.len[u]);
+        if (len & LEN_SELF) len = 0;         // implies only itself
+        if (len > 1) off = __ldcg((const unsigned long long *)&b.raw_off[u]);
+    }
+    m = G::ballot(len > 1);
+    while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t n = G::shfl(len, k);
+        const unsigned long long src = G::shfl(off, k);
+        if (n > st.cap) return 2;
+        for (uint32_t i = 0; i < n; i += G::width) {
+            const uint32_t c = i + lane < n ? (uint32_t)__ldcg(&b.out_lits[src + i + lane]) : 0u;
+            const int r = tl.template commit<G, S, true>(st, c);
+            if (r) return r;
+        }
+        ++wc.adopted;
+        wc.adopt_lits += n;
+        wc.bytes += 4ull * n;
+        if (tl.aborted()) return 1;
+    }
+    return 0;
+}
+
 // Breadth-first unit propagation of trail[0..tail) to fixpoint by ONE group. Returns 0 fixpoint, 1 conflict, 2 overflow.
 template <class G, class S>
-__device__ int propagate(const DbView &db, S &st, GroupTail &tl, bool prune, WorkCounters &wc)
+__device__ int propagate(const DbView &db, const BatchView &b, S &st, GroupTail &tl, bool prune, int tier, WorkCounters &wc)
 {
     const int lane = G::lane();
     uint32_t head = 0;
     while (head < tl.tail) {
         const uint32_t B = min((uint32_t)G::width, tl.tail - head);
-        const uint32_t p = lane < (int)B ? st.tget(head + lane) : 0u;
+        const uint32_t e = lane < (int)B ? st.tget(head + lane) : 0u;
         // while a single literal is assigned only binary clauses can become unit
-        const int r = process_batch<G>(db, st, tl, p, B, prune && tl.tail == 1, wc);
+        const bool first_step = tl.tail == 1;
+        if (b.reuse && !first_step) {
+            const int r = expand_closures<G>(b, st, tl, e, B, tier, wc);
+            if (r) return r;
+        }
+        const int r = process_batch<G>(db, st, tl, e, B, prune && first_step, wc);
         if (r) return r;
         head += B;
     }
     return 0;
+}
+
+// A finished probe makes its result visible to the other probes of the launch (expand_closures): the set and its
+// position first, the flag last, each behind a fence.
+template <class G>
+__device__ __forceinline__ void publish_result(const BatchView &b, uint64_t item, uint8_t flag, uint32_t len, unsigned long long off)
+{
+    if (b.reuse) __threadfence();   // every lane: its part of the set is out
+    G::sync();
+    if (G::lane() == 0) {
+        b.len[item] = len; b.raw_off[item] = off;
+        if (len) atomicAdd(&b.tile_sum[item / SG_TILE], (unsigned long long)len);
+        if (b.reuse) __threadfence();
+        *(volatile uint8_t *)&b.flag[item] = flag;
+    }
 }
 
 // Load a cube into the (empty) state with the semantics of HandleAssumptions (Topi.cc:797-938).

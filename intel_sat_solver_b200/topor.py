@@ -24,6 +24,7 @@ OPT_OFF32 = 4
 OPT_KERNEL_TIMES = 8
 OPT_MERGE = 16
 OPT_RENDEZVOUS = 32
+OPT_NO_REUSE = 64
 
 
 class TToporReturnVal(enum.IntEnum):
@@ -130,10 +131,11 @@ class BatchedTopor:
 
     @staticmethod
     def _opts(implied=True, small_trail=0, out_capacity=0, no_len_prune=False, mid_trail=0, off32=False, kernel_times=False,
-              merge=0, rendezvous=False) -> Opts:
+              merge=0, rendezvous=False, no_reuse=False) -> Opts:
         """merge: 0, or the bitmap words owned by each rank (sharding.Shard.words_per_rank) to all-gather the slices in the batch"""
         return Opts((OPT_IMPLIED if implied else 0) | (OPT_NO_LEN_PRUNE if no_len_prune else 0) | (OPT_OFF32 if off32 else 0)
-                    | (OPT_KERNEL_TIMES if kernel_times else 0) | (OPT_MERGE if merge else 0) | (OPT_RENDEZVOUS if rendezvous else 0),
+                    | (OPT_KERNEL_TIMES if kernel_times else 0) | (OPT_MERGE if merge else 0) | (OPT_RENDEZVOUS if rendezvous else 0)
+                    | (OPT_NO_REUSE if no_reuse else 0),
                     small_trail, out_capacity, mid_trail, int(merge))
 
     def _fetch(self, info: BatchInfo, implied: bool, fetch: bool, off32: bool = False) -> BatchResult:
@@ -267,4 +269,12 @@ class BatchedTopor:
         n = self._L.bbcp_host_row(self._h, ilit, None, 0)
         out = np.zeros(max(n, 1), dtype=np.uint32)
         self._L.bbcp_host_row(self._h, ilit, out.ctypes.data, n)
+        return out[:n]
+
+    def HostOrder(self) -> np.ndarray:
+        """The probe schedule of the prepared database (children of the binary implication graph first); empty
+        when the database has no binary clause."""
+        n = self._L.bbcp_host_order(self._h, None, 0)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self._L.bbcp_host_order(self._h, out.ctypes.data, n)
         return out[:n]

@@ -54,3 +54,33 @@ def test_conflict_probes_count_their_input_only(golden):
     g = lambda k: golden[f"fuzz_10/{k}"]
     a = ab.abytes(g("words"), g("level0"), g("probe_flag"), g("probe_off"), g("probe_lits"))
     assert (a[g("probe_flag") == 1] == 4).all() and a[g("probe_flag") == 0].min() >= 16
+
+
+def test_c_tool_agrees_with_the_python_definition():
+    """oracle/abytes (the C form used by bench.py's workload blocks on the checker's sampled fixpoints) against
+    tests/abytes.py on instances with binaries, units, long clauses, conflicts and a strided sample over two shards."""
+    import json
+    import gpu_util
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, capture_output=True)
+    tool = os.path.join(ROOT, "oracle", "abytes")
+    port = os.path.join(ROOT, "oracle", "oracle_bcp")
+    with tempfile.TemporaryDirectory() as d:
+        for kind, kw, stride in (("aig", dict(frames=3, gates=400, inputs=30, latches=30, window=100, seed=2), 1),
+                                 ("plaw", dict(n=1500, m=6000, seed=5), 3), ("comm", dict(n=1500, m=6000, comms=5, seed=3), 2)):
+            inst, _ = gpu_util.gen(kind, d, **kw)
+            words = fileio.read_bcnf(inst)
+            outs = []
+            for sh in range(2):
+                out = os.path.join(d, f"{kind}{sh}.bres")
+                subprocess.run([port, inst, "--out", out, "--probe-all", "--shard", str(sh), "2", "--stride", str(stride)], check=True, capture_output=True)
+                outs.append(out)
+            got = json.loads(subprocess.run([tool, inst] + outs, check=True, capture_output=True, text=True).stdout)
+            o = Oracle(words)
+            exp = items = 0
+            for out in outs:
+                r = fileio.read_bres(out)
+                a = ab.abytes(words, o.level0(), r.flag, r.off, r.lits)
+                ran = r.flag != 255
+                exp += int(a[ran].sum())
+                items += int(ran.sum())
+            assert got["items"] == items and got["abytes_total"] == exp, kind

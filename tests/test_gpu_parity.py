@@ -68,7 +68,8 @@ def test_regression_corpus_totals(golden, golden_names):
 
 
 @pytest.mark.parametrize("kw", [dict(small_trail=32), dict(small_trail=32, mid_trail=32), dict(no_len_prune=True), dict(out_capacity=64),
-                                dict(small_trail=32, mid_trail=64, out_capacity=16)])
+                                dict(small_trail=32, mid_trail=64, out_capacity=16), dict(no_reuse=True), dict(no_reuse=True, small_trail=32, mid_trail=32),
+                                dict(no_len_prune=True, small_trail=32)])
 def test_option_variants_keep_results(golden, kw):
     """Tiny warp-private state (forces the CTA-per-probe shared-memory tier), tiny CTA state too (forces the
     global-slab tier), no length pruning, and an implied-literal buffer that overflows and regrows must all
@@ -128,6 +129,14 @@ def _synthetic_shape(kind, kw, cubekw, width):
         assert res2.info["n_mid"] >= res.info["n_mid"] and res3.info["n_large"] >= res2.info["n_large"]
         if kind in ("aig", "plaw"):
             assert res2.info["n_mid"] > 0 and res3.info["n_large"] > 0
+        # closure reuse (finished probes' results adopted by later probes) on and off: same bits
+        res4 = t.ProbeAll(no_reuse=True)
+        gpu_util.assert_same_results(res4, ref.flag, ref.off, ref.lits, kind + " no reuse")
+        assert res4.info["adopted"] == 0 and res4.info["inherited"] == 0
+        if kind == "aig":
+            assert res.info["adopted"] > 0 and res.info["adopt_lits"] > res.info["adopted"]
+        if kind == "plaw":
+            assert res.info["inherited"] > 0
 
 
 def test_probe_range_shards_compose(golden):

@@ -216,3 +216,66 @@ def test_row_build_does_not_depend_on_the_thread_count(golden):
         rows[th] = json.loads(subprocess.run([sys.executable, "-c", prog], check=True, capture_output=True, text=True, env=env).stdout)
     assert rows["1"] == rows["4"] == rows["8"]
     assert sum(len(r) for r in rows["1"]["fuzz_10"]) > 10000
+
+
+def _scc_ids(nl, succ):
+    """Tarjan, recursive-free reference (small inputs): component id per literal."""
+    import sys
+    index, low, comp, stack, on = {}, {}, {}, [], set()
+    counter = [0]
+    for root in range(2, nl):
+        if root in index:
+            continue
+        work = [(root, 0)]
+        index[root] = low[root] = counter[0]; counter[0] += 1; stack.append(root); on.add(root)
+        while work:
+            v, i = work.pop()
+            if i < len(succ[v]):
+                work.append((v, i + 1))
+                w = succ[v][i]
+                if w not in index:
+                    index[w] = low[w] = counter[0]; counter[0] += 1; stack.append(w); on.add(w)
+                    work.append((w, 0))
+                elif w in on:
+                    low[v] = min(low[v], index[w])
+            else:
+                if work:
+                    low[work[-1][0]] = min(low[work[-1][0]], low[v])
+                if low[v] == index[v]:
+                    while True:
+                        w = stack.pop(); on.discard(w); comp[w] = v
+                        if w == v:
+                            break
+    return comp
+
+
+@pytest.mark.parametrize("name", ["regr_20", "regr_47", "regr_66", "regr_72", "fuzz_3", "fuzz_10", "hand_long"])
+def test_probe_schedule_is_children_first(golden, name):
+    """bbcp_host_order: a permutation of all internal literals in which q precedes p whenever p -> q is a binary
+    implication and the two are not in one strongly connected component (equivalent literals share a height)."""
+    t = BatchedTopor()
+    t.AddClauses(golden[f"{name}/words"])
+    if t.HostPrepare() != 0:
+        pytest.skip("contradictory at intake")
+    nl = 2 * t.max_var + 2
+    order = t.HostOrder().tolist()
+    succ = {l: [] for l in range(nl)}
+    nbin = 0
+    for l in range(2, nl):
+        row = t.HostRow(l ^ 1).tolist()      # the row walked when l becomes true
+        succ[l] = row[3:3 + row[0]]
+        nbin += row[0]
+    if nbin == 0:
+        assert order == []
+        return
+    assert sorted(order) == list(range(2, nl))
+    pos = {l: i for i, l in enumerate(order)}
+    comp = _scc_ids(nl, succ)
+    edges = cross = 0
+    for p in range(2, nl):
+        for q in succ[p]:
+            edges += 1
+            if comp[p] != comp[q]:
+                cross += 1
+                assert pos[q] < pos[p], (p, q)
+    assert edges == nbin and cross > 0

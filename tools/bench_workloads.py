@@ -112,6 +112,7 @@ def main():
             "n_skipped": info["n_skipped"], "n_implied": info["n_implied"], "tiers": {"queued": info["n_deep"], "second": info["n_mid"], "third": info["n_large"]},
             "db": {k: dbi[k] for k in ("n_bin", "n_tern", "n_long", "row_slots", "device_bytes")}, "gen_s": round(t1 - t0, 1), "db_build_s": round(t2 - t1, 1),
             "kernel_ms": kern_ms, "gpu_launches": info["launches"],
+            "reuse": {k: info[k] for k in ("adopted", "adopt_lits", "inherited")}, "props_all": info["props_all"], "slots": info["slots"],
             "roofline": {"bound": "hbm", "kernel": "k_deep + k_deep2 + k_big (propagation)", "bytes_per_launch": prop_bytes, "kernel_ms": prop_ms,
                          "achieved": prop_bytes / max(prop_ms, 1e-9) / 1e6, "peak": peak, "unit": "GB/s", "frac": prop_bytes / max(prop_ms, 1e-9) / 1e6 / peak,
                          "note": "engine byte counters (row headers, slots, clause units, stored literals); served mostly from L2"},
