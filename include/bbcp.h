@@ -207,6 +207,10 @@ void *bbcp_device_impl_lits(bbcp_handle *h);
 void *bbcp_stream(bbcp_handle *h);
 /* blocks until the handle's stream is idle */
 int bbcp_sync(bbcp_handle *h);
+/* measurement aid: enqueue, on the handle's stream, a write of `bytes` (0 = 256 MiB, twice the L2) that evicts the L2
+ * before the next batch; returns at once. Because the next call's kernels queue up behind it, the host is done launching
+ * them before the device starts on them: the batch's device time does not depend on how fast the host issues launches. */
+int bbcp_l2_flush(bbcp_handle *h, uint64_t bytes);
 
 /* ---- multi-GPU: one handle per GPU (one process per GPU), the database replicated, the probe universe cut into
  *      contiguous ranges aligned to bitmap words: rank r probes the literals whose bits live in bitmap words

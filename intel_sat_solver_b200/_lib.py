@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbbcp.so")
+LIB_PATH = os.environ.get("BBCP_LIB") or os.path.join(_HERE, "libbbcp.so")   # BBCP_LIB: a diagnostic build (make checks)
 
 
 class Opts(C.Structure):
@@ -72,6 +72,7 @@ _SIGS = {
     "bbcp_device_impl_lits": (C.c_void_p, [C.c_void_p]),
     "bbcp_stream": (C.c_void_p, [C.c_void_p]),
     "bbcp_sync": (C.c_int, [C.c_void_p]),
+    "bbcp_l2_flush": (C.c_int, [C.c_void_p, C.c_uint64]),
     "bbcp_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bbcp_peer_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "bbcp_peer_detach": (C.c_int, [C.c_void_p]),

@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -16,40 +18,53 @@ using namespace bbcp;
 
 namespace {
 
+// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync), not from cudaMalloc: with peer
+// GPUs attached (CUDA IPC mappings of the bitmap block enable peer access between the contexts) a cudaMalloc / cudaFree
+// has to map / unmap the allocation in every peer context, which waits for the peers' running kernels -- and a peer
+// may at that moment be spinning in a merge kernel for THIS rank's flag (a batch that needs its second-tier slabs
+// for the first time, or a larger literal pool, allocates in the middle of the call). Pool memory is mapped on the
+// owning device only, so growing a buffer never involves a peer. Only the bitmap block itself, which IS exported over
+// IPC, is a cudaMalloc allocation (made in bbcp_finalize, before any peer can wait).
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
-    // grow-only; contents are not preserved. zero: the new allocation is cleared ON `zs` (the stream the kernels that
-    // rely on the zeroes run on -- the handle's stream is non-blocking, so the legacy stream would not order with it)
-    bool reserve(size_t need, bool zero = false, cudaStream_t zs = nullptr)
+    cudaStream_t s = nullptr;   // the handle's stream (set by ensure_device); allocation, zeroing and release are ordered on it
+    bool pooled = true;
+    // grow-only; contents are not preserved. zero: the new allocation is cleared (on the stream the kernels run on)
+    bool reserve(size_t need, bool zero = false)
     {
         if (need <= bytes && p) return true;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
+        release();
         size_t want = need + std::min<size_t>(need / 4, (size_t)1 << 30) + 256;   // head-room for the next batch, at most 1 GiB
-        if (cudaMalloc(&p, want) != cudaSuccess) {
+        if (cudaMallocAsync(&p, want, s) != cudaSuccess) {
             cudaGetLastError();
             want = need;
-            if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+            if (cudaMallocAsync(&p, want, s) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
         }
         bytes = want;
-        if (zero) cudaMemsetAsync(p, 0, bytes, zs);
+        if (zero) cudaMemsetAsync(p, 0, bytes, s);
+        // the buffer is also used from the copy streams of bbcp_probe_lits_to_host: make it valid everywhere now
+        // (allocations are rare: buffers only grow)
+        if (cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); return false; }
         return true;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release()
+    {
+        if (p) { if (pooled) cudaFreeAsync(p, s); else cudaFree(p); }
+        p = nullptr;
+        bytes = 0;
+    }
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
-// misc device words (u64): [0..C_N) counters, cursor, six u32 {ticket[3], mid_count, big_count, deep_count},
-// total (a copy of off[n])
-constexpr int MERGE_CTRL_WORDS = 128;   // after the two bitmaps: [0..63] arrival flag per rank, [64] push-done counter, [65] error
+// misc device words (u64): [0..C_N) counters, cursor, a block of u32 words (U32_* below), total (a copy of off[n])
 constexpr int MISC_CURSOR = C_N;
-constexpr int MISC_U32 = C_N + 1;       // as u32 index from 2*MISC_U32: +0..2 tickets, +3 mid_count, +4 big_count, +5 deep_count
-                                        // +6 chunk_count of the giant-set gather, +7 grid barrier of the scan, +8 its finished-CTA count,
-                                        // +10 sort_count (second-tier sets waiting for k_sort_sets)
-constexpr int MISC_TOTAL = C_N + 7;
-constexpr int MISC_WORDS64 = C_N + 8;
+constexpr int MISC_U32 = C_N + 1;       // u32 words start at u32 index 2*MISC_U32
+enum { U32_TICKET = 0 /* ..3: one dynamic scheduler per tier */, U32_MID_COUNT = 4, U32_BIG_COUNT = 5, U32_DEEP_COUNT = 6, U32_CHUNK_COUNT = 7,
+       U32_TILE_TICKET = 8, U32_SG_FINISHED = 9 /* finished CTAs of k_scan_gather = "the report was written" */, U32_SORT_COUNT = 10,
+       U32_HUGE_COUNT = 11, U32_N = 12 };
+constexpr int MISC_TOTAL = MISC_U32 + U32_N / 2;
+constexpr int MISC_WORDS64 = MISC_TOTAL + 1;
 // two counter blocks used alternately: the triage kernel of one launch sequence zeroes the block of the next one
 
 }  // namespace
@@ -78,7 +93,8 @@ struct bbcp_handle {
     int peer_rank = -1, peer_world = 0;
     std::vector<void *> peer_base;          // mapped base of every rank's d_bitmaps (own entry = own pointer)
     DevBuf d_peer_tab;                      // the same table on the device
-    uint32_t merge_epoch = 0;
+    uint32_t merge_epoch = 0, drained_epoch = 0;
+    uint32_t merge_timeout_ms = 20000;      // BBCP_MERGE_TIMEOUT_MS: how long a merging kernel waits for a peer (ranks may be seconds apart on skewed shards)
     cudaEvent_t ev_merge[2] = {nullptr, nullptr};
     uint64_t bitmap_words = 0;
     uint64_t device_db_bytes = 0;
@@ -90,7 +106,7 @@ struct bbcp_handle {
     uint64_t off_base = 0;       // added to the offsets a batch writes (chunked calls)
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[16] = {}, ev_out[2] = {};
-    DevBuf d_raw_off, d_len, d_out, d_cube_lits, d_cube_off, d_overflow, d_big, d_deep, d_chunks, d_misc, d_lbits, d_ltrail, d_tiles;
+    DevBuf d_raw_off, d_len, d_out, d_cube_lits, d_cube_off, d_overflow, d_big, d_huge, d_deep, d_chunks, d_misc, d_lbits, d_ltrail, d_tiles;
     uint32_t misc_parity = 0;
     bool last_off32 = false;
     unsigned long long *h_misc = nullptr;   // pinned, mapped
@@ -102,17 +118,27 @@ struct bbcp_handle {
     DevBuf d_mid_slab;           // second tier: per-warp hash + trail
     uint32_t mid_slab_cap = 0;   // trail capacity the slab is laid out (and zeroed) for
     uint64_t mid_slab_groups = 0;
+    bool mid_slab_warp = false;  // the slab is laid out (zeroed hash tables) for the warp-per-probe second tier
     int32_t slab_max_var = -1;   // variable range the third-tier slabs are laid out for
 
     uint64_t last_n = 0, last_n_implied = 0, last_first = 0;
     bool last_universe = false, last_implied = false;
     DevBuf d_products;
+    DevBuf d_flush;              // bbcp_l2_flush
+    uint32_t flush_count = 0;
     bool have_batch = false;
     uint64_t total_props = 0;
 
     std::vector<int32_t> assumps;
     std::vector<int8_t> solve_val;   // per var after bbcp_solve: 0 unassigned, 1 true, -1 false (level > 0)
     bool solved = false;
+
+    std::vector<DevBuf *> all_bufs()
+    {
+        return {&d_hdr, &d_slots, &d_arena, &d_litinfo, &d_order, &d_bitmaps, &d_peer_tab, &rs[0].flag, &rs[0].off, &rs[0].impl, &rs[1].flag, &rs[1].off,
+                &rs[1].impl, &d_raw_off, &d_len, &d_out, &d_cube_lits, &d_cube_off, &d_overflow, &d_big, &d_huge, &d_deep, &d_chunks, &d_misc, &d_lbits, &d_ltrail,
+                &d_tiles, &d_mid_slab, &d_products, &d_flush};
+    }
 
     int fail(int code, const std::string &msg)
     {
@@ -122,10 +148,14 @@ struct bbcp_handle {
         err = msg;
         return code;
     }
+    unsigned long long *h_dbg = nullptr;    // mapped: record of a failed check of a diagnostic build (make checks)
     bool cuda_ok(cudaError_t e, const char *what)
     {
         if (e == cudaSuccess) return true;
         fail(BBCP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        if (h_dbg && h_dbg[0])
+            err += " [check failed at bbcp_propagate.cuh/bbcp_kernels.cu line " + std::to_string(h_dbg[0]) + ", CTA " + std::to_string(h_dbg[1]) + ", thread " +
+                   std::to_string(h_dbg[2]) + ", values " + std::to_string(h_dbg[3]) + " " + std::to_string(h_dbg[4]) + "]";
         cudaGetLastError();
         return false;
     }
@@ -147,10 +177,27 @@ bool ensure_device(bbcp_handle *h)
     h->sg_blocks = scan_gather_max_blocks(h->sm_count);
     if (!h->cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
     for (auto &e : h->ev) if (!h->cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return false;
+    for (DevBuf *b : h->all_bufs()) b->s = h->stream;
+    h->d_bitmaps.pooled = false;
+    {
+        // keep freed pool memory cached in the pool (the default gives it back to the driver at every synchronisation)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     if (!h->cuda_ok(cudaHostAlloc(&h->h_misc, MISC_WORDS64 * 8, cudaHostAllocMapped), "cudaHostAlloc")) return false;
     if (!h->cuda_ok(cudaHostGetDevicePointer(&h->d_hmisc, h->h_misc, 0), "cudaHostGetDevicePointer")) return false;
+    if (cudaHostAlloc(&h->h_dbg, 65536, cudaHostAllocMapped) == cudaSuccess) {
+        memset(h->h_dbg, 0, 65536);
+        void *d = nullptr;
+        if (cudaHostGetDevicePointer(&d, h->h_dbg, 0) == cudaSuccess) set_debug_buffer(static_cast<unsigned long long *>(d));
+    }
     h->lean = getenv("BBCP_LEAN") ? atoi(getenv("BBCP_LEAN")) : 3;
-    if (!h->d_misc.reserve(2 * MISC_WORDS64 * 8, true, h->stream)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (counters)"); return false; }
+    if (const char *e = getenv("BBCP_MERGE_TIMEOUT_MS")) h->merge_timeout_ms = (uint32_t)std::max(1, atoi(e));
+    if (!h->d_misc.reserve(2 * MISC_WORDS64 * 8, true)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (counters)"); return false; }
     if (!h->cuda_ok(cudaDeviceSynchronize(), "counter init")) return false;
     h->device_ready = true;
     return true;
@@ -162,6 +209,9 @@ bool upload(bbcp_handle *h, DevBuf &b, const void *src, size_t bytes)
     if (bytes && !h->cuda_ok(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream), "upload")) return false;
     return true;
 }
+
+bool drain_peers(bbcp_handle *h);
+DbView db_view(const bbcp_handle *h);
 
 bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo, bool with_order)
 {
@@ -183,15 +233,22 @@ bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo, bool with_or
     if (!upload(h, h->d_slots, db.slots.data(), db.slots.size() * sizeof(Slot))) return false;
     if (!upload(h, h->d_arena, db.arena.data(), db.arena.size() * 4)) return false;
     if (!upload(h, h->d_litinfo, litinfo.data(), litinfo.size())) return false;
-    // probe schedule for closure reuse (only databases with binary clauses have one)
+    // probe schedule for closure reuse (only databases with binary clauses have one): built on the device from the rows
+    // just uploaded (BBCP_ORDER=host: the exact host form, HostDb::build_order; BBCP_NO_ORDER: none, variable order)
     static const bool no_order = getenv("BBCP_NO_ORDER") != nullptr;
+    static const bool host_order = getenv("BBCP_ORDER") && !strcmp(getenv("BBCP_ORDER"), "host");
     h->order_n = 0;
-    if (with_order && !no_order) {
-        db.build_order();
-        if (!db.order.empty()) {
+    if (with_order && !no_order && db.n_bin && db.hdr.size() > 2) {
+        const uint32_t nl = (uint32_t)db.hdr.size();
+        if (host_order) {
+            db.build_order();
             if (!upload(h, h->d_order, db.order.data(), db.order.size() * 4)) return false;
-            h->order_n = (uint32_t)db.order.size();
+        } else {
+            if (!h->d_order.reserve((size_t)(nl - 2) * 4) || !h->d_products.reserve(2 * (size_t)((nl + 3) & ~3u) + 4 + 1024)) { h->fail(BBCP_ERR_ALLOC, "device allocation failed (probe schedule)"); return false; }
+            DbView v = db_view(h);
+            build_order_device(v, nl, h->d_products.as<uint8_t>(), h->d_order.as<uint32_t>(), h->sm_count, h->stream);
         }
+        h->order_n = nl - 2;
     }
     h->bitmap_words = (2 * ((uint64_t)db.max_var + 1) + 31) / 32;
     const uint64_t stride = (h->bitmap_words + 3) & ~3ull;
@@ -204,10 +261,34 @@ bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo, bool with_or
         h->bm_stride = stride;
         cudaMemsetAsync(h->d_bitmaps.p, 0, h->d_bitmaps.bytes, h->stream);
     } else {
+        drain_peers(h);   // a peer may still be reading the old bitmaps (last merge)
         cudaMemsetAsync(h->d_bitmaps.p, 0, 2 * stride * 4, h->stream);   // keep the arrival flags: they are monotonic epochs
     }
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "upload sync")) return false;
     h->device_db_bytes = db.hdr.size() * sizeof(RowHdr) + db.slots.size() * sizeof(Slot) + db.arena.size() * 4 + litinfo.size() + 2 * h->bitmap_words * 4 + (size_t)h->order_n * 4;
+    return true;
+}
+
+// the time-out latch of the merging kernels: read it and clear it, so that one late peer does not fail every later merge
+bool merge_timed_out(bbcp_handle *h)
+{
+    uint32_t *latch = h->d_bitmaps.as<uint32_t>() + 2 * h->bm_stride + MERGE_CTRL_ERROR;
+    uint32_t err = 0;
+    cudaMemcpyAsync(&err, latch, 4, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    if (err) { cudaMemsetAsync(latch, 0, 4, h->stream); cudaStreamSynchronize(h->stream); }
+    return err != 0;
+}
+
+// Before this rank's bitmaps are cleared, rebuilt or unmapped: wait until every peer has finished reading them in the
+// last merge (the merge itself only waits for the peers' slices to ARRIVE, not for the peers to be done pulling ours).
+bool drain_peers(bbcp_handle *h)
+{
+    if (h->peer_world <= 1 || h->merge_epoch == 0 || h->drained_epoch == h->merge_epoch) return true;
+    launch_merge_drain(MergeArgs{static_cast<uint32_t *const *>(h->d_peer_tab.p), h->peer_rank, h->peer_world, h->bm_stride, 0, h->merge_epoch, h->merge_timeout_ms}, h->stream);
+    if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "waiting for the peers to finish reading the bitmaps")) return false;
+    h->drained_epoch = h->merge_epoch;
+    if (merge_timed_out(h)) { h->fail(BBCP_ERR_STATE, "a peer did not finish the last bitmap merge within the time-out"); return false; }
     return true;
 }
 
@@ -216,6 +297,30 @@ bool dbg_check(bbcp_handle *h, const char *what)
 {
     static const bool on = getenv("BBCP_DEBUG_SYNC") != nullptr;
     if (!on) return true;
+    static const bool verbose = atoi(getenv("BBCP_DEBUG_SYNC")) >= 2;
+    if (verbose) {
+        fprintf(stderr, "bbcp: waiting for %s\n", what);
+        fflush(stderr);
+        // diagnostic builds: give up on a kernel that does not finish within 10 s and show where its first CTAs stand
+        for (int i = 0; i < 1000 && cudaStreamQuery(h->stream) == cudaErrorNotReady; ++i) { struct timespec ts = {0, 10000000}; nanosleep(&ts, nullptr); }
+        if (cudaStreamQuery(h->stream) == cudaErrorNotReady && h->h_dbg) {
+            fprintf(stderr, "bbcp: %s still running after 10 s; per-warp marks (value:line) of the 256-thread CTAs that have not finished:\n", what);
+            int shown = 0;
+            for (int c = 0; c < 480 && shown < 12; ++c) {
+                bool any = false, dead = true;
+                for (int w = 0; w < 8; ++w) { const unsigned long long v = h->h_dbg[256 + c * 8 + w]; any |= v != 0; dead &= (v >> 32) == 0xDEAD; }
+                if (!any || dead) continue;
+                ++shown;
+                fprintf(stderr, "  CTA %d:", c);
+                for (int w = 0; w < 8; ++w) { const unsigned long long v = h->h_dbg[256 + c * 8 + w]; fprintf(stderr, " w%d=%llu:%llu", w, v >> 32, v & 0xffffffffull); }
+                fprintf(stderr, "\n");
+            }
+            fprintf(stderr, "  last long hash probe (lit:steps) %llu:%llu\n", h->h_dbg[8] >> 32, h->h_dbg[8] & 0xffffffffull);
+            fprintf(stderr, "  failed check: line %llu CTA %llu thread %llu values %llu %llu\n", h->h_dbg[0], h->h_dbg[1], h->h_dbg[2], h->h_dbg[3], h->h_dbg[4]);
+            fflush(stderr);
+            _exit(3);
+        }
+    }
     const cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) return true;
     h->fail(BBCP_ERR_CUDA, std::string("[debug] fault in ") + what + ": " + cudaGetErrorString(e));
@@ -256,7 +361,7 @@ bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
     uint64_t slabs = std::min<uint64_t>((uint64_t)h->sm_count * per_sm, (free_b / 4) / std::max<size_t>(per_slab, 1));
     slabs = std::max<uint64_t>(slabs, 1);
     h->slab_max_var = -1;
-    if (!h->d_lbits.reserve(slabs * dbv.nvars_words16 * 4, true, h->stream) || !h->d_ltrail.reserve(slabs * ((size_t)dbv.max_var + 1) * 4)) return false;
+    if (!h->d_lbits.reserve(slabs * dbv.nvars_words16 * 4, true) || !h->d_ltrail.reserve(slabs * ((size_t)dbv.max_var + 1) * 4)) return false;
     h->big_slabs = (uint32_t)slabs;
     h->slab_max_var = dbv.max_var;
     return true;
@@ -285,7 +390,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
 
     const size_t n1 = (size_t)n + 1;
     if (!h->rs[h->rb].flag.reserve(n1) || !h->d_raw_off.reserve(n1 * 8) || !h->d_len.reserve(n1 * 4 + 64) || !h->rs[h->rb].off.reserve(n1 * 8) ||
-        !h->d_overflow.reserve(n1 * 4) || !h->d_big.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_tiles.reserve((n / SG_TILE + 4) * 8))
+        !h->d_overflow.reserve(n1 * 4) || !h->d_big.reserve(n1 * 4) || !h->d_huge.reserve(n1 * 4) || !h->d_deep.reserve(n1 * 4) || !h->d_tiles.reserve((n / SG_TILE + 4) * 8))
         return h->fail(BBCP_ERR_ALLOC, "device allocation failed (batch buffers)");
 
     // lanes per probe (bbcp_propagate.cuh): a full warp. Narrower groups were measured and rejected, see DESIGN.md
@@ -295,7 +400,10 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     while (small_smem_bytes(cap, width) > 200 * 1024 && cap > 32) cap >>= 1;
     uint32_t cap_mid = opts.mid_trail ? pow2_at_least(opts.mid_trail) : 8192;
     if (!opts.mid_trail) if (const char *e = getenv("BBCP_MID_TRAIL")) cap_mid = pow2_at_least((uint32_t)atoi(e));
-    if (cap_mid > 32768) cap_mid = 32768;   // k_sort_sets sorts a whole set in shared memory (4 bytes per literal)
+    if (cap_mid > 16384) cap_mid = 16384;   // the second tier's set lives (and is sorted) in shared memory
+    // third tier: one CTA per SM on a 192 KB table; with a test-sized second tier, four times its capacity
+    uint32_t cap_big = opts.mid_trail ? std::min<uint32_t>(4 * cap_mid, 32768) : 32768;
+    if (const char *e = getenv("BBCP_BIG_TRAIL")) cap_big = std::min<uint32_t>(pow2_at_least((uint32_t)atoi(e)), 32768);
     const bool implied = (opts.flags & BBCP_OPT_IMPLIED) != 0;
     const bool off32 = (opts.flags & BBCP_OPT_OFF32) != 0;
     const bool want_kernel_times = (opts.flags & BBCP_OPT_KERNEL_TIMES) != 0 || !(h->lean & 2);
@@ -317,6 +425,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.unit = h->unit_p();
     b.mid_list = h->d_overflow.as<uint32_t>();
     b.big_list = h->d_big.as<uint32_t>();
+    b.huge_list = h->d_huge.as<uint32_t>();
     b.deep_list = h->d_deep.as<uint32_t>();
     b.off = h->rs[h->rb].off.p;
     b.off_base = h->off_base;
@@ -340,14 +449,14 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     const bool peers = h->peer_world > 1 && !d_lits && !d_off;
     uint32_t *const *ptab = static_cast<uint32_t *const *>(h->d_peer_tab.p);
     if (peers && (opts.flags & BBCP_OPT_RENDEZVOUS))
-        launch_merge(MergeArgs{ptab, h->peer_rank, h->peer_world, h->bm_stride, 0, ++h->merge_epoch}, h->sm_count, h->stream);
+        launch_merge(MergeArgs{ptab, h->peer_rank, h->peer_world, h->bm_stride, 0, ++h->merge_epoch, h->merge_timeout_ms}, h->sm_count, h->stream);
     const bool do_merge = peers && (opts.flags & BBCP_OPT_MERGE);
     if (do_merge && (opts.merge_words_per_rank == 0 || (opts.merge_words_per_rank & 3)))
         return h->fail(BBCP_ERR_ARG, "BBCP_OPT_MERGE: opts.merge_words_per_rank must be a non-zero multiple of 4");
     const uint32_t mepoch = do_merge ? ++h->merge_epoch : 0;
     // with implied sets the merge rides inside k_scan_gather (stores at its start, handshake at its end)
-    const MergeArgs no_merge{nullptr, 0, 0, 0, 0, 0};
-    const MergeArgs in_batch = do_merge ? MergeArgs{ptab, h->peer_rank, h->peer_world, h->bm_stride, opts.merge_words_per_rank, mepoch} : no_merge;
+    const MergeArgs no_merge{nullptr, 0, 0, 0, 0, 0, 0};
+    const MergeArgs in_batch = do_merge ? MergeArgs{ptab, h->peer_rank, h->peer_world, h->bm_stride, opts.merge_words_per_rank, mepoch, h->merge_timeout_ms} : no_merge;
 
     cudaEventRecord(h->ev[0], h->stream);
     for (int attempt = 0;; ++attempt) {
@@ -375,20 +484,21 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         b.out_cursor = misc + MISC_CURSOR;
         b.total = misc + MISC_TOTAL;
         uint32_t *u32 = reinterpret_cast<uint32_t *>(misc) + 2 * MISC_U32;
-        b.ticket = u32;
-        b.mid_count = u32 + 3;
-        b.big_count = u32 + 4;
-        b.deep_count = u32 + 5;
-        b.chunk_count = u32 + 6;
-        b.tile_ticket = u32 + 7;
-        b.sort_count = u32 + 10;
+        b.ticket = u32 + U32_TICKET;
+        b.mid_count = u32 + U32_MID_COUNT;
+        b.big_count = u32 + U32_BIG_COUNT;
+        b.huge_count = u32 + U32_HUGE_COUNT;
+        b.deep_count = u32 + U32_DEEP_COUNT;
+        b.chunk_count = u32 + U32_CHUNK_COUNT;
+        b.tile_ticket = u32 + U32_TILE_TICKET;
+        b.sort_count = u32 + U32_SORT_COUNT;
         b.sort_list = h->d_deep.as<uint32_t>();   // the triage queue is spent by the time the second tier runs
         const bool zero_copy = implied && n && (h->lean & 1);
         const bool kevents = want_kernel_times;
         b.host_report = zero_copy ? static_cast<unsigned long long *>(h->d_hmisc) : nullptr;
         bi.launches = 0;
         bool second = false;
-        reinterpret_cast<uint32_t *>(h->h_misc)[2 * MISC_U32 + 8] = 0;   // "report written" mark of the mapped copy
+        reinterpret_cast<uint32_t *>(h->h_misc)[2 * MISC_U32 + U32_SG_FINISHED] = 0;   // "report written" mark of the mapped copy
         if (n) {
             if (kevents) cudaEventRecord(h->ev[3], h->stream);
             launch_triage(b, dbv, h->sm_count, h->stream);
@@ -414,38 +524,62 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         if (!zero_copy) cudaMemcpyAsync(h->h_misc, misc, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
         cudaEventRecord(h->ev[2], h->stream);
         if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "propagate kernels")) return BBCP_ERR_CUDA;
-        if (zero_copy && h_u32[8] == 0) {
+        if (zero_copy && h_u32[U32_SG_FINISHED] == 0) {
             // k_scan_gather returned early (probes wait for the CTA-per-probe tiers): only then the report is missing
             cudaMemcpyAsync(h->h_misc, misc, MISC_WORDS64 * 8, cudaMemcpyDeviceToHost, h->stream);
             if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "counter read-back")) return BBCP_ERR_CUDA;
         }
-        if (n && h_u32[3] != 0) {
+        if (n && h_u32[U32_MID_COUNT] != 0) {
             // some probes outgrew the first tier: CTA-per-probe tiers, then the compaction for real
             second = true;
-            const int bps_mid = mid_blocks_per_sm(width);
-            if (bps_mid <= 0) return h->fail(BBCP_ERR_CUDA, "second-tier kernel does not fit");
-            const uint64_t gpc = MID2_THREADS / width;   // probes in flight per CTA
-            const uint64_t mid_blocks = std::min<uint64_t>((uint64_t)bps_mid * h->sm_count, ((uint64_t)h_u32[3] + gpc - 1) / gpc);
-            const uint64_t mid_groups = (uint64_t)bps_mid * h->sm_count * gpc;
-            if (h->mid_slab_cap != cap_mid || h->mid_slab_groups < mid_groups || !h->d_mid_slab.p) {
-                // (re)lay out the per-group slabs; the hash tables must start from zero
-                const size_t bytes = mid_groups * mid_slab_words_per_group(cap_mid) * 4;
-                if (!h->d_mid_slab.reserve(bytes)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (second-tier state)");
-                cudaMemsetAsync(h->d_mid_slab.p, 0, bytes, h->stream);
-                h->mid_slab_cap = cap_mid;
-                h->mid_slab_groups = mid_groups;
-            }
-            if (!ensure_slabs(h, dbv)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (third-tier state)");
+            // BBCP_TIER2=warp: the round-1 second tier (warp per probe, hash + trail in a global slab, k_deep2 + k_sort_sets)
+            // instead of the two CTA-per-probe tiers with the hash in shared memory; kept for the A/B in profiles/r02
+            static const bool tier2_warp = getenv("BBCP_TIER2") && !strcmp(getenv("BBCP_TIER2"), "warp");
+            if (!ensure_slabs(h, dbv)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (last-tier state)");
             ls.bits = h->d_lbits.as<uint32_t>();
             ls.trail = h->d_ltrail.as<uint32_t>();
-            cudaEventRecord(h->ev[1], h->stream);
-            launch_mid(dbv, b, h->d_mid_slab.as<uint32_t>(), cap_mid, width, (int)mid_blocks, h->stream);
-            if (!dbg_check(h, "k_deep2")) return BBCP_ERR_CUDA;
-            cudaEventRecord(h->ev[7], h->stream);
-            launch_big(dbv, b, ls, (int)h->big_slabs, h->stream);
-            if (!dbg_check(h, "k_big")) return BBCP_ERR_CUDA;
-            if (implied) { launch_sort_sets(b, cap_mid, h->sm_count, h->stream); ++bi.launches; }
-            if (!dbg_check(h, "k_sort_sets")) return BBCP_ERR_CUDA;
+            if (tier2_warp) {
+                const int bps_mid = mid_blocks_per_sm(width);
+                if (bps_mid <= 0) return h->fail(BBCP_ERR_CUDA, "second-tier kernel does not fit");
+                const uint64_t gpc = MID2_THREADS / width;   // probes in flight per CTA
+                const uint64_t mid_blocks = std::min<uint64_t>((uint64_t)bps_mid * h->sm_count, ((uint64_t)h_u32[U32_MID_COUNT] + gpc - 1) / gpc);
+                const uint64_t mid_groups = (uint64_t)bps_mid * h->sm_count * gpc;
+                if (h->mid_slab_cap != cap_mid || h->mid_slab_groups < mid_groups || !h->d_mid_slab.p || !h->mid_slab_warp) {
+                    // (re)lay out the per-group slabs; the hash tables must start from zero
+                    const size_t bytes = mid_groups * mid_slab_words_per_group(cap_mid) * 4;
+                    if (!h->d_mid_slab.reserve(bytes)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (second-tier state)");
+                    cudaMemsetAsync(h->d_mid_slab.p, 0, bytes, h->stream);
+                    h->mid_slab_cap = cap_mid;
+                    h->mid_slab_groups = mid_groups;
+                    h->mid_slab_warp = true;
+                }
+                cudaEventRecord(h->ev[1], h->stream);
+                launch_mid(dbv, b, h->d_mid_slab.as<uint32_t>(), cap_mid, width, (int)mid_blocks, h->stream);
+                if (!dbg_check(h, "k_deep2")) return BBCP_ERR_CUDA;
+                cudaEventRecord(h->ev[7], h->stream);
+                launch_big(dbv, b, ls, (int)h->big_slabs, false, h->stream);
+                if (!dbg_check(h, "k_big")) return BBCP_ERR_CUDA;
+                if (implied) { launch_sort_sets(b, cap_mid, h->sm_count, h->stream); ++bi.launches; }
+                if (!dbg_check(h, "k_sort_sets")) return BBCP_ERR_CUDA;
+            } else {
+                // second tier: 256-thread CTAs, several per SM; third tier: 1024-thread CTAs on (nearly) all of an SM's
+                // shared memory; last tier: dense state, any size. Each hands what it cannot hold to the next through a list.
+                const BlockTier t2 = block_tier_shape(0, cap_mid), t3 = block_tier_shape(1, cap_big);
+                const int bps2 = block_tier_blocks_per_sm(t2), bps3 = block_tier_blocks_per_sm(t3);
+                if (bps2 <= 0 || bps3 <= 0) return h->fail(BBCP_ERR_CUDA, "CTA-per-probe tier does not fit (shared memory)");
+                const uint64_t blocks2 = (uint64_t)bps2 * h->sm_count, blocks3 = (uint64_t)bps3 * h->sm_count;
+                if (!h->d_mid_slab.reserve((blocks2 * t2.cap + blocks3 * t3.cap) * 4)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (CTA-per-probe tiers)");
+                h->mid_slab_warp = false;
+                cudaEventRecord(h->ev[1], h->stream);
+                launch_block_tier(dbv, b, t2, 0, h->d_mid_slab.as<uint32_t>(), (int)std::min<uint64_t>(blocks2, h_u32[U32_MID_COUNT]), h->stream);
+                if (!dbg_check(h, "k_block (second tier)")) return BBCP_ERR_CUDA;
+                cudaEventRecord(h->ev[7], h->stream);
+                launch_block_tier(dbv, b, t3, 1, h->d_mid_slab.as<uint32_t>() + blocks2 * t2.cap, (int)blocks3, h->stream);
+                if (!dbg_check(h, "k_block (third tier)")) return BBCP_ERR_CUDA;
+                launch_big(dbv, b, ls, (int)h->big_slabs, true, h->stream);
+                if (!dbg_check(h, "k_big")) return BBCP_ERR_CUDA;
+                ++bi.launches;
+            }
             cudaEventRecord(h->ev[6], h->stream);
             bi.launches += 2;
             if (implied) {
@@ -484,11 +618,8 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "batch")) return BBCP_ERR_CUDA;
         if (do_merge) cudaEventElapsedTime(&merge_ms, h->ev_merge[0], h->ev[2]);
     }
-    if (do_merge) {
-        uint32_t err = 0;
-        cudaMemcpy(&err, h->d_bitmaps.as<uint32_t>() + 2 * h->bm_stride + 65, 4, cudaMemcpyDeviceToHost);
-        if (err) return h->fail(BBCP_ERR_CUDA, "bitmap merge: a peer did not arrive within the time-out");
-    }
+    if ((do_merge || (peers && (opts.flags & BBCP_OPT_RENDEZVOUS))) && merge_timed_out(h))
+        return h->fail(BBCP_ERR_STATE, "bitmap merge: a peer did not arrive within the time-out (BBCP_MERGE_TIMEOUT_MS)");
     if (off32 && bi.n_implied > 0xffffffffull) return h->fail(BBCP_ERR_ARG, "BBCP_OPT_OFF32: more than 2^32-1 implied literals in one batch (split it)");
     h->last_off32 = off32 && implied;
 
@@ -501,7 +632,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     bi.n_ok = h->h_misc[C_OK];
     bi.n_conflict = h->h_misc[C_CONFLICT];
     bi.n_skipped = h->h_misc[C_SKIPPED];
-    bi.n_deep = h_u32[5];
+    bi.n_deep = h_u32[U32_DEEP_COUNT];
     bi.adopted = h->h_misc[C_ADOPTED];
     bi.adopt_lits = h->h_misc[C_ADOPT_LITS];
     bi.inherited = h->h_misc[C_INHERITED];
@@ -560,11 +691,10 @@ void bbcp_release(bbcp_handle *h)
         cudaStreamSynchronize(h->stream);
         bbcp_peer_detach(h);
         for (auto &e : h->ev_merge) if (e) cudaEventDestroy(e);
-        for (DevBuf *b : {&h->d_hdr, &h->d_slots, &h->d_arena, &h->d_litinfo, &h->d_bitmaps, &h->d_peer_tab, &h->rs[0].flag, &h->rs[0].off, &h->rs[0].impl, &h->rs[1].flag, &h->rs[1].off, &h->rs[1].impl, &h->d_raw_off, &h->d_len,
-                          &h->d_out, &h->d_cube_lits, &h->d_cube_off, &h->d_overflow, &h->d_big, &h->d_deep, &h->d_chunks, &h->d_misc, &h->d_lbits,
-                          &h->d_ltrail, &h->d_tiles, &h->d_mid_slab, &h->d_products, &h->d_order})
-            b->release();
+        for (DevBuf *b : h->all_bufs()) b->release();
+        cudaStreamSynchronize(h->stream);
         if (h->h_misc) cudaFreeHost(h->h_misc);
+        if (h->h_dbg) cudaFreeHost(h->h_dbg);
         for (auto &e : h->ev_in) if (e) cudaEventDestroy(e);
         for (auto &e : h->ev_out) if (e) cudaEventDestroy(e);
         if (h->s_in) cudaStreamDestroy(h->s_in);
@@ -1031,8 +1161,19 @@ int bbcp_clear_bitmaps(bbcp_handle *h)
     int rc = need_final(h);
     if (rc) return rc;
     cudaSetDevice(h->device);
+    if (!drain_peers(h)) return h->status < 0 ? h->status : BBCP_ERR_STATE;
     cudaMemsetAsync(h->d_bitmaps.p, 0, 2 * h->bm_stride * 4, h->stream);
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "clear bitmaps") ? BBCP_OK : BBCP_ERR_CUDA;
+}
+
+int bbcp_l2_flush(bbcp_handle *h, uint64_t bytes)
+{
+    if (!h) return BBCP_ERR_ARG;
+    if (!ensure_device(h)) return h->status;
+    cudaSetDevice(h->device);
+    if (bytes == 0) bytes = 256ull << 20;
+    if (!h->d_flush.reserve(bytes)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (flush buffer)");
+    return h->cuda_ok(cudaMemsetAsync(h->d_flush.p, (int)(++h->flush_count & 0xff), bytes, h->stream), "l2 flush") ? BBCP_OK : BBCP_ERR_CUDA;
 }
 
 void *bbcp_device_failed_bitmap(bbcp_handle *h) { return h ? h->failed_p() : nullptr; }
@@ -1067,7 +1208,7 @@ int bbcp_peer_export(bbcp_handle *h, void *out)
 int bbcp_peer_detach(bbcp_handle *h)
 {
     if (!h) return BBCP_ERR_ARG;
-    if (h->device_ready) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+    if (h->device_ready) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); drain_peers(h); }
     for (int r = 0; r < (int)h->peer_base.size(); ++r)
         if (r != h->peer_rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
     cudaGetLastError();
@@ -1099,6 +1240,7 @@ int bbcp_peer_attach(bbcp_handle *h, int rank, int world, const void *all)
     }
     h->peer_rank = rank;
     h->peer_world = world;
+    h->drained_epoch = h->merge_epoch;   // nothing outstanding with the new peers
     if (!h->d_peer_tab.reserve(64 * sizeof(void *))) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (peer table)");
     cudaMemcpyAsync(h->d_peer_tab.p, h->peer_base.data(), world * sizeof(void *), cudaMemcpyHostToDevice, h->stream);
     for (auto &e : h->ev_merge) if (!e && !h->cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return BBCP_ERR_CUDA;
@@ -1114,13 +1256,11 @@ int bbcp_merge_bitmaps(bbcp_handle *h, uint64_t words_per_rank, float *ms)
     cudaSetDevice(h->device);
     ++h->merge_epoch;
     cudaEventRecord(h->ev_merge[0], h->stream);
-    launch_merge(MergeArgs{static_cast<uint32_t *const *>(h->d_peer_tab.p), h->peer_rank, h->peer_world, h->bm_stride, words_per_rank, h->merge_epoch},
+    launch_merge(MergeArgs{static_cast<uint32_t *const *>(h->d_peer_tab.p), h->peer_rank, h->peer_world, h->bm_stride, words_per_rank, h->merge_epoch, h->merge_timeout_ms},
                  h->sm_count, h->stream);
     cudaEventRecord(h->ev_merge[1], h->stream);
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "bitmap merge")) return BBCP_ERR_CUDA;
-    uint32_t err = 0;
-    cudaMemcpy(&err, h->d_bitmaps.as<uint32_t>() + 2 * h->bm_stride + 65, 4, cudaMemcpyDeviceToHost);
-    if (err) return h->fail(BBCP_ERR_CUDA, "bbcp_merge_bitmaps: a peer did not arrive within the time-out");
+    if (merge_timed_out(h)) return h->fail(BBCP_ERR_STATE, "bbcp_merge_bitmaps: a peer did not arrive within the time-out (BBCP_MERGE_TIMEOUT_MS)");
     if (ms) cudaEventElapsedTime(ms, h->ev_merge[0], h->ev_merge[1]);
     return BBCP_OK;
 }

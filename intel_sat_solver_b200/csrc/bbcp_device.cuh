@@ -50,9 +50,11 @@ struct BatchView {
     unsigned long long *counters;
     uint32_t *mid_list;         // items that did not fit the warp-private shared-memory state
     uint32_t *mid_count;
-    uint32_t *big_list;         // items that did not fit the CTA-wide shared-memory state either
+    uint32_t *big_list;         // items that outgrew the second tier
     uint32_t *big_count;
-    unsigned int *ticket;       // [3] dynamic schedulers of k_deep / k_block<mid> / k_block<big>
+    uint32_t *huge_list;        // items that outgrew the third tier (dense last tier)
+    uint32_t *huge_count;
+    unsigned int *ticket;       // [4] dynamic schedulers of the four tiers
     uint32_t *deep_list;        // items queued by the triage for propagation
     uint32_t *deep_count;
     uint32_t *sort_list;        // second-tier items whose implied set waits in the pool unsorted (k_sort_sets)
@@ -83,7 +85,9 @@ constexpr uint32_t OPT_NO_LEN_PRUNE = 2u;
 constexpr uint32_t OPT_OFF32 = 4u;
 constexpr uint8_t FLAG_OK = 0, FLAG_CONFLICT = 1, FLAG_TRIVIAL_L0 = 2, FLAG_FALSE_L0 = 3, FLAG_UNMAPPED = 4;
 constexpr uint8_t FLAG_OVERFLOW = 250;      // internal: outgrew the first tier, queued for the second (global hash state)
-constexpr uint8_t FLAG_OVERFLOW2 = 249;     // internal: outgrew the second tier, queued for the third (dense state)
+constexpr uint8_t FLAG_OVERFLOW2 = 249;     // internal: outgrew the second tier, queued for the third
+constexpr uint8_t FLAG_OVERFLOW3 = 248;     // internal: outgrew the third tier, queued for the last (dense state, any size)
+constexpr uint8_t FLAG_OVERFLOW_LAST = 248;
 constexpr uint8_t FLAG_QUEUED = 255;        // internal: written by the triage for items that wait for the first tier
 constexpr uint32_t TRAIL_CLOSED = 0x80000000u;  // trail entry mark: the literal came in with a finished closure, so every
                                                 // binary clause of its row is already satisfied (only longer clauses are re-examined)
@@ -100,11 +104,18 @@ void launch_mid(const DbView &db, const BatchView &b, uint32_t *slab, uint32_t c
 void launch_sort_sets(const BatchView &b, uint32_t cap, int sm_count, cudaStream_t s);
 size_t mid_slab_words_per_group(uint32_t cap);
 int mid_blocks_per_sm(int width);
-void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s);
+void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, bool from_huge, cudaStream_t s);
+// CTA-per-probe tiers with the hash in shared memory: cls 0 = second tier (reads mid_list), 1 = third tier (reads big_list)
+struct BlockTier { int threads; uint32_t hs, cap; };   // CTA size, hash entries (shared memory), trail capacity
+BlockTier block_tier_shape(int cls, uint32_t cap);
+int block_tier_blocks_per_sm(const BlockTier &t);
+void launch_block_tier(const DbView &db, const BatchView &b, const BlockTier &t, int cls, uint32_t *trail_slab, int blocks, cudaStream_t s);
 constexpr uint32_t SG_TILE = 2048;   // items per step of the compaction kernel
 size_t small_smem_bytes(uint32_t trail_cap, int width);
 int small_blocks_per_sm(uint32_t trail_cap, int width);
 struct MergeArgs;
+void set_debug_buffer(unsigned long long *mapped);
+void build_order_device(const DbView &db, uint32_t nl, uint8_t *d_height, uint32_t *d_order, int sm_count, cudaStream_t s);
 bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s, bool pdl);
 int scan_gather_max_blocks(int sm_count);
 void launch_products(bool off32, const uint8_t *flag, const void *off, const int32_t *impl, uint64_t npairs, uint64_t var_base, uint32_t *necessary, int32_t *equiv,
@@ -115,8 +126,12 @@ struct MergeArgs {
     uint64_t stride;              // words between the failed and the unit bitmap
     uint64_t wp;                  // bitmap words owned by each rank (multiple of 4): rank r owns [r*wp, (r+1)*wp); 0 = rendezvous only
     uint32_t epoch;
+    uint32_t timeout_ms;          // in-kernel wait limit for a peer's flag
 };
+constexpr int MERGE_CTRL_WORDS = 256;      // control words behind the two bitmaps, see merge_signal in bbcp_kernels.cu
+constexpr int MERGE_CTRL_FINISHED = 64, MERGE_CTRL_ERROR = 65, MERGE_CTRL_DONE = 128;
 void launch_merge(const MergeArgs &m, int sm_count, cudaStream_t s);
+void launch_merge_drain(const MergeArgs &m, cudaStream_t s);
 constexpr int SMALL_THREADS = 128;  // first tier: SMALL_THREADS / W probes in flight per CTA (W lanes per probe)
 constexpr int MID2_THREADS = 256;   // second tier: MID2_THREADS / W probes per CTA, state in a global slab
 constexpr int BIG_THREADS = 256;   // third tier: 8 warps share one probe, state in a global slab

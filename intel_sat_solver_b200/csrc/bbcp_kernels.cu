@@ -39,6 +39,16 @@
 
 namespace bbcp {
 
+// diagnostic builds: where a failed check leaves its record (mapped host memory); a no-op in the product build
+void set_debug_buffer(unsigned long long *mapped)
+{
+#ifdef BBCP_CHECKS
+    cudaMemcpyToSymbol(g_dbg, &mapped, sizeof(mapped));
+#else
+    (void)mapped;
+#endif
+}
+
 namespace {
 
 __device__ __forceinline__ uint32_t lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
@@ -435,40 +445,88 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_sets(const BatchView b, c
 // Probes of any size: the warps of a CTA share the per-probe state (dense 2-bit assignment + full-length trail in
 // a per-CTA slab in global memory) and walk each breadth-first level of the trail together (level-synchronous,
 // two barriers per level).
+constexpr uint32_t ADOPT_MAX = 64;   // finished sets adopted CTA-wide per level; further ones are entered by the warp that found them
+
 template <class S>
-__device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uint32_t *ctl, bool prune, WorkCounters &wc)
+__device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uint32_t *ctl, bool prune, int tier, WorkCounters &wc)
 {
     using G = Grp<32>;
+    __shared__ unsigned long long s_src[ADOPT_MAX];
+    __shared__ uint32_t s_len[ADOPT_MAX];
+    __shared__ uint32_t s_na;
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     BlockTail tl{ctl};
     uint32_t head = 0;
+    BBCP_WATCH_BEGIN();
     for (;;) {
+        BBCP_WATCH(head, ctl[0]);
+        BBCP_MARK(head);
         __syncthreads();
-        const uint32_t level_end = ctl[0];
-        const bool stop = (ctl[1] | ctl[2]) != 0 || head >= level_end;
+        const volatile uint32_t *vctl = ctl;
+        const uint32_t level_end = vctl[0];
+        const bool stop = (vctl[1] | vctl[2]) != 0 || head >= level_end;
+        if (threadIdx.x == 0) s_na = 0;
+        BBCP_MARK(level_end);
         __syncthreads();   // everybody has its snapshot before anyone appends
+        BBCP_MARK(stop);
         if (stop) break;
+        if (b.reuse && level_end > 1) {
+            // closure reuse, CTA-wide: the warps look up the literals of the level, the finished sets found are listed in
+            // shared memory, then ALL warps enter each set together (a set of this tier has tens of thousands of literals;
+            // entered by the one warp that found it, the other seven would wait at the barrier)
+            for (uint32_t bse = head + warp * 32; bse < level_end; bse += nwarps * 32) {
+                const uint32_t B = min(32u, level_end - bse);
+                const uint32_t e = lane < (int)B ? st.tget(bse + lane) : 0u;
+                uint32_t len;
+                unsigned long long off;
+                if (closure_lookup<G>(b, tl, e, B, tier, wc, len, off)) break;
+                if (G::any(len > st.cap)) { if (lane == 0) ctl[2] = 1; break; }   // a set that cannot fit: hand the probe on right away
+                uint32_t slot = ADOPT_MAX;
+                if (len > 1) slot = atomicAdd(&s_na, 1u);
+                if (slot < ADOPT_MAX) { s_src[slot] = off; s_len[slot] = len; }
+                unsigned m = G::ballot(len > 1 && slot >= ADOPT_MAX);
+                while (m) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (closure_adopt<G>(b, st, tl, G::shfl(off, k), G::shfl(len, k), 0, 32)) break;
+                }
+            }
+            __syncthreads();
+            const uint32_t na = min(s_na, ADOPT_MAX);
+            for (uint32_t a = 0; a < na && !tl.aborted(); ++a) {
+                const uint32_t n = s_len[a];
+                // successive sets start at successive warps, so that many short sets spread over the CTA as well
+                if (closure_adopt<G>(b, st, tl, s_src[a], n, ((warp + nwarps - a % nwarps) % nwarps) * 32, nwarps * 32)) break;
+                if (warp == (int)(a % nwarps) && lane == 0) { ++wc.adopted; wc.adopt_lits += n; wc.bytes += 4ull * n; }
+            }
+            // (CTA-uniform: a warp that got past this point may latch a conflict before a slower thread has looked)
+            if (__syncthreads_or((vctl[1] | vctl[2]) != 0)) continue;   // the loop head sees the latch and stops
+        }
         const bool bins_only = prune && level_end == 1;
         for (uint32_t bse = head + warp * 32; bse < level_end; bse += nwarps * 32) {
+            BBCP_MARK(bse);
             const uint32_t B = min(32u, level_end - bse);
             const uint32_t e = lane < (int)B ? st.tget(bse + lane) : 0u;
-            if (b.reuse && level_end > 1 && expand_closures<G>(b, st, tl, e, B, 3, wc)) break;
             if (process_batch<G>(db, st, tl, e, B, bins_only, wc)) break;
         }
+        BBCP_MARK(level_end);
         head = level_end;
     }
 }
 
-__global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const BatchView b, const LargeState ls)
+__global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const BatchView b, const LargeState ls, const int from_huge)
 {
     using G = Grp<32>;
     __shared__ uint32_t ctl[8];      // 0 tail, 1 conflict, 2 overflow, 3 load result, 4 ticket, 5 vmin, 6 vmax
     __shared__ unsigned long long s_off;
     __shared__ uint32_t s_warp[BIG_THREADS / 32 + 1];
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t count = *b.big_count;
+    // the last tier takes what outgrew the tier before it: the third tier's hand-over list, or the second tier's when the
+    // warp-per-probe second tier (k_deep2, BBCP_TIER2=warp) ran instead of the two CTA-per-probe tiers
+    const uint32_t *list = from_huge ? b.huge_list : b.big_list;
+    const uint32_t count = from_huge ? *b.huge_count : *b.big_count;
     if (blockIdx.x >= count) return;
-    unsigned int *ticket = b.ticket + 2;
+    unsigned int *ticket = b.ticket + 3;
 
     GmemState gs;
     gs.bits = ls.bits + (size_t)blockIdx.x * db.nvars_words16;
@@ -488,7 +546,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
         __syncthreads();
         const uint32_t t = ctl[4];
         if (t >= count) break;
-        const uint64_t item = b.big_list[t];
+        const uint64_t item = list[t];
         const Item it = get_item(b, item);
         if (warp == 0) {
             BlockTail tl{ctl};
@@ -497,7 +555,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
         }
         __syncthreads();
         const uint32_t f = ctl[3];
-        if (f == 0xff) block_propagate(db, b, gs, ctl, prune, wc);
+        if (f == 0xff) block_propagate(db, b, gs, ctl, prune, 4, wc);
         __syncthreads();
         const uint32_t tail = min(ctl[0], gs.cap);
         const bool conflict = ctl[1] != 0 || f == FLAG_CONFLICT;
@@ -590,6 +648,137 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
     wc.flush<G>(b.counters);
 }
 
+// ---------------------------------------------------------------- second / third tier: one CTA per probe, shared hash
+// Probes that outgrew the warp-private state. The CTA's warps share the probe as in k_big (level-synchronous rows,
+// CTA-wide closure adoption), but the set of true literals is a hash table in SHARED memory and only the trail streams
+// through global memory (BhashState). With closure reuse a probe of this size is mostly adoption -- thousands of
+// literals entered per step by all warps -- which is what makes a CTA per probe pay; without it (frontiers a few
+// literals wide) the warp-per-probe k_deep2 was the better second tier. The finished trail is sorted in the same
+// shared memory (the table is no longer needed) and leaves as a sorted set of internal literals.
+template <int THREADS>
+__device__ void block_bitonic_sort(uint32_t *a, uint32_t n2)
+{
+    BBCP_WATCH_BEGIN();
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            BBCP_WATCH(n2, k);
+            for (uint32_t t = threadIdx.x; t < n2 / 2; t += THREADS) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t ixj = i | j;
+                const bool up = (i & k) == 0;
+                const uint32_t x = a[i], y = a[ixj];
+                if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_block(const DbView db, const BatchView b, uint32_t *trail_slab, const uint32_t hs, const uint32_t cap, const int cls)
+{
+    using G = Grp<32>;
+    extern __shared__ uint32_t s_hash[];
+    __shared__ uint32_t ctl[8];      // 0 tail, 1 conflict, 2 overflow, 3 load result, 4 ticket
+    __shared__ unsigned long long s_off;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t *list = cls ? b.big_list : b.mid_list;
+    const uint32_t count = cls ? *b.big_count : *b.mid_count;
+    if (blockIdx.x >= count) return;
+    unsigned int *ticket = b.ticket + 1 + cls;
+    uint32_t *next_list = cls ? b.huge_list : b.big_list, *next_count = cls ? b.huge_count : b.big_count;
+    const uint8_t next_flag = cls ? FLAG_OVERFLOW3 : FLAG_OVERFLOW2;
+
+    BhashState st;
+    st.hash = s_hash;
+    st.trail = trail_slab + (size_t)blockIdx.x * cap;
+    st.hs = hs;
+    st.cap = cap;
+    for (uint32_t i = threadIdx.x; i < hs; i += THREADS) s_hash[i] = 0;
+    const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
+    WorkCounters wc;
+    BBCP_WATCH_BEGIN();
+    for (;;) {
+        BBCP_WATCH(ctl[4], count);
+        BBCP_MARK(1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ctl[4] = atomicAdd(ticket, 1u);
+            ctl[0] = ctl[1] = ctl[2] = 0;
+            ctl[3] = 0xff;
+        }
+        __syncthreads();
+        const uint32_t t = ctl[4];
+        if (t >= count) break;
+        const uint64_t item = list[t];
+        const Item it = get_item(b, item);
+        if (warp == 0) {
+            BlockTail tl{ctl};
+            const int f = it.probe_lit ? load_probe<G>(db, st, it.probe_lit, tl) : load_cube<G>(db, st, it.lits, it.n, tl);
+            if (lane == 0) ctl[3] = (uint32_t)f;
+        }
+        BBCP_MARK(2);
+        __syncthreads();
+        const uint32_t f = ctl[3];
+        if (f == 0xff) block_propagate(db, b, st, ctl, prune, 2 + cls, wc);
+        BBCP_MARK(3);
+        __syncthreads();
+        const bool overflow = ctl[2] != 0 || f == FLAG_OVERFLOW;
+        const bool conflict = !overflow && (ctl[1] != 0 || f == FLAG_CONFLICT);
+        const uint32_t tail = min(ctl[0], cap);
+        uint8_t flag = (uint8_t)f;
+        uint32_t len = 0;
+        unsigned long long off = 0;
+        if (overflow) {
+            flag = next_flag;
+            if (threadIdx.x == 0) next_list[atomicAdd(next_count, 1u)] = (uint32_t)item;   // queued before the flag shows
+        } else if (conflict) {
+            flag = FLAG_CONFLICT;
+            if (it.probe_lit && threadIdx.x == 0) mark_failed(b, 2u * (uint32_t)abs(it.probe_lit) + (it.probe_lit < 0));
+        } else if (f == 0xff) {
+            flag = FLAG_OK;
+            if (b.opts & OPT_IMPLIED) {
+                // the table has done its work: sort the trail in its place
+                uint32_t n2 = 1;
+                while (n2 < tail) n2 <<= 1;
+                for (uint32_t i = threadIdx.x; i < n2; i += THREADS) s_hash[i] = i < tail ? (st.tget(i) & ~TRAIL_CLOSED) : 0xffffffffu;
+                if (threadIdx.x == 0) {
+                    const unsigned long long o = atomicAdd(b.out_cursor, (unsigned long long)tail);
+                    s_off = o + tail <= b.out_cap ? o : ~0ull;
+                }
+                __syncthreads();
+                if (tail > 1) block_bitonic_sort<THREADS>(s_hash, n2);
+                off = s_off;
+                if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
+                else {
+                    len = tail;
+                    for (uint32_t i = threadIdx.x; i < tail; i += THREADS) b.out_lits[off + i] = (int32_t)s_hash[i];
+                    if (threadIdx.x == 0) wc.bytes += 8ull * tail;
+                }
+            }
+        }
+        BBCP_MARK(4);
+        __syncthreads();
+        // leave the table empty for the next probe (it holds the probe's literals, or the sorted trail)
+        for (uint32_t i = threadIdx.x; i < hs; i += THREADS) s_hash[i] = 0;
+        if (b.reuse) __threadfence();   // every thread: its part of the set is out (publish_result, CTA-wide)
+        BBCP_MARK(5);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            b.len[item] = len; b.raw_off[item] = off;
+            if (len) atomicAdd(&b.tile_sum[item / SG_TILE], (unsigned long long)len);
+            if (b.reuse) __threadfence();
+            *(volatile uint8_t *)&b.flag[item] = flag;
+            if (!overflow) atomicAdd(&b.counters[C_MID], 1ull);
+            wc.n_ok += flag == FLAG_OK;
+            wc.n_conf += flag == FLAG_CONFLICT;
+            wc.n_skip += flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED;
+        }
+    }
+    wc.flush<G>(b.counters);
+    BBCP_MARK(0xDEAD);
+}
+
 // ---------------------------------------------------------------- multi-GPU merge of the bitmap slices
 // All-gather over NVLink peer memory (one process per GPU, every rank runs this on its own GPU at the same
 // point of its stream). peer_base[r] = rank r's [failed | unit | control] block, mapped through CUDA IPC; rank
@@ -609,26 +798,46 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 
+// control words behind the two bitmaps (MERGE_CTRL_*): [0..63] arrival epoch per rank ("rank r's slice is final"),
+// [64] CTAs of the running merge that are done pulling (local), [65] time-out latch, [128..191] pull-done epoch per rank
+// ("rank r has finished reading my slice": what bbcp_clear_bitmaps / a re-finalize / a detach wait for before they
+// touch the bitmaps, k_merge_drain)
 __device__ __forceinline__ void merge_signal(const MergeArgs &m)
 {
     for (int p = 0; p < m.world; ++p)
         if (p != m.rank) *(volatile uint32_t *)(m.peer_base[p] + 2 * m.stride + m.rank) = m.epoch;
 }
 
-// one thread; returns false on time-out (a peer died; the host call reports it)
-__device__ bool merge_wait(const MergeArgs &m)
+// spin until every peer's word [base + p] has reached the epoch; one thread; false on time-out (a peer died or never
+// made the matching call; the host call reports it)
+__device__ bool merge_spin(const MergeArgs &m, int base)
 {
     uint32_t *ctrl = m.peer_base[m.rank] + 2 * m.stride;
-    const unsigned long long t0 = global_ns();
+    const unsigned long long t0 = global_ns(), limit = (unsigned long long)m.timeout_ms * 1000000ull;
     for (int p = 0; p < m.world; ++p) {
         if (p == m.rank) continue;
         uint32_t spins = 0;
-        while ((int32_t)(*(volatile uint32_t *)&ctrl[p] - m.epoch) < 0) {
-            if ((++spins & 0xfffu) == 0 && global_ns() - t0 > 20000000000ull) { ctrl[65] = 1; return false; }
+        while ((int32_t)(*(volatile uint32_t *)&ctrl[base + p] - m.epoch) < 0) {
+            if ((++spins & 0xfffu) == 0 && global_ns() - t0 > limit) { ctrl[MERGE_CTRL_ERROR] = 1; return false; }
         }
     }
     __threadfence();   // the loads of the pull stay behind the flag reads
     return true;
+}
+
+__device__ __forceinline__ bool merge_wait(const MergeArgs &m) { return merge_spin(m, 0); }
+
+// called by thread 0 of every CTA of a merging kernel when the CTA's share of the pull is complete (its remote loads
+// have returned: their values have been stored). The last CTA tells every peer that this rank is done reading.
+__device__ __forceinline__ void merge_cta_done(const MergeArgs &m)
+{
+    uint32_t *ctrl = m.peer_base[m.rank] + 2 * m.stride;
+    __threadfence();
+    if (atomicAdd(&ctrl[MERGE_CTRL_FINISHED], 1u) == gridDim.x - 1) {
+        ctrl[MERGE_CTRL_FINISHED] = 0;   // the next merging kernel of the stream starts after this one has drained
+        for (int p = 0; p < m.world; ++p)
+            if (p != m.rank) *(volatile uint32_t *)(m.peer_base[p] + 2 * m.stride + MERGE_CTRL_DONE + m.rank) = m.epoch;
+    }
 }
 
 __device__ __forceinline__ uint4 ld_remote(const uint4 *p)
@@ -667,6 +876,14 @@ __global__ void __launch_bounds__(256) k_merge(const MergeArgs m)
     if (threadIdx.x == 0) s_ok = merge_wait(m);
     __syncthreads();
     if (s_ok && m.wp) merge_pull(m, (uint64_t)blockIdx.x * 256 + threadIdx.x, (uint64_t)gridDim.x * 256);
+    __syncthreads();
+    if (threadIdx.x == 0) merge_cta_done(m);
+}
+
+// waits until every peer has finished reading this rank's slice in the merge of epoch m.epoch
+__global__ void k_merge_drain(const MergeArgs m)
+{
+    if (threadIdx.x == 0) merge_spin(m, MERGE_CTRL_DONE);
 }
 
 // ---------------------------------------------------------------- result compaction into canonical CSR order
@@ -860,6 +1077,8 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
         if (tid == 0) s_pos = merge_wait(mg);
         __syncthreads();
         if (s_pos) merge_pull(mg, (uint64_t)blockIdx.x * SG_THREADS + tid, (uint64_t)gridDim.x * SG_THREADS);
+        __syncthreads();
+        if (tid == 0) merge_cta_done(mg);
     }
     // the last CTA to finish copies the counter block of this launch sequence into mapped host memory: the host
     // reads it after the stream synchronisation it does anyway (no copy-engine round trip, and no fence: the
@@ -946,7 +1165,97 @@ __global__ void __launch_bounds__(256) k_products(const uint8_t *__restrict__ fl
     }
 }
 
+// ---------------------------------------------------------------- probe schedule for closure reuse, built on the device
+// height(p) = length of the longest chain of binary implications that starts at p (p -> q when the clause (not-p or q)
+// exists), capped at 255: round r of the relaxation below holds min(height, r), so an acyclic implication graph is done
+// after depth+1 rounds and literals on or above a cycle (equivalent literals) end at the cap. The schedule is the
+// literals counting-sorted by that height: children first wherever the graph is acyclic, which is all that closure reuse
+// wants (the results never depend on the order). HostDb::build_order is the exact host form (Tarjan); at 50 M clauses it
+// costs half a minute of one host core, this costs milliseconds.
+__global__ void __launch_bounds__(256) k_height_round(const DbView db, const uint8_t *__restrict__ hin, uint8_t *__restrict__ hout, const uint32_t nl,
+                                                      uint32_t *__restrict__ changed)
+{
+    bool any = false;
+    for (uint32_t l = blockIdx.x * 256 + threadIdx.x; l < nl; l += gridDim.x * 256) {
+        uint32_t h = 0;
+        if (l >= 2) {
+            const uint4 hd = __ldg(&db.hdr[l ^ 1u]);
+            for (uint32_t j = 0; j < hd.y; j += 2) {
+                const uint2 s = __ldg(&db.slots[hd.x + j / 2]);
+                h = max(h, (uint32_t)hin[s.x] + 1u);
+                if (j + 1 < hd.y) h = max(h, (uint32_t)hin[s.y] + 1u);
+            }
+            h = min(h, 255u);
+        }
+        any |= h != hin[l];
+        hout[l] = (uint8_t)h;
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) *changed = 1u;
+}
+
+__global__ void __launch_bounds__(256) k_order_hist(const uint8_t *__restrict__ h, const uint32_t nl, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t l = 2 + blockIdx.x * 256 + threadIdx.x; l < nl; l += gridDim.x * 256) atomicAdd(&s_h[h[l]], 1u);
+    __syncthreads();
+    if (s_h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) k_order_scan(uint32_t *hist)   // hist[256] -> exclusive prefix sums, in place
+{
+    __shared__ uint32_t s[256];
+    s[threadIdx.x] = hist[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < 256; ++i) { const uint32_t c = s[i]; s[i] = run; run += c; } }
+    __syncthreads();
+    hist[threadIdx.x] = s[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) k_order_scatter(const uint8_t *__restrict__ h, const uint32_t nl, uint32_t *__restrict__ cursor, uint32_t *__restrict__ order)
+{
+    // every warp walks a contiguous run of literals, so a height class keeps (roughly) the literal order
+    const uint32_t per_warp = ((nl + gridDim.x * 8 - 1) / (gridDim.x * 8) + 31) & ~31u;
+    const uint32_t w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint32_t lo = w * per_warp, hi = min(lo + per_warp, nl);
+    for (uint32_t base = lo; base < hi; base += 32) {
+        const uint32_t l = base + lane_id();
+        const bool ok = l >= 2 && l < hi;
+        const uint32_t key = ok ? h[l] : 0x100u + lane_id();
+        const unsigned m = __match_any_sync(FULL, key);
+        const int leader = __ffs(m) - 1;
+        uint32_t pos = 0;
+        if (ok && lane_id() == leader) pos = atomicAdd(&cursor[key], (uint32_t)__popc(m));
+        pos = __shfl_sync(FULL, pos, leader) + __popc(m & lanemask_lt());
+        if (ok) order[pos] = l;
+    }
+}
+
 }  // namespace
+
+// d_height: 2 * nl bytes + 1028 bytes of scratch (ping-pong heights, changed flag, histogram); d_order: nl - 2 words
+void build_order_device(const DbView &db, uint32_t nl, uint8_t *d_height, uint32_t *d_order, int sm_count, cudaStream_t s)
+{
+    uint8_t *h0 = d_height, *h1 = d_height + nl;
+    uint32_t *changed = reinterpret_cast<uint32_t *>(d_height + 2 * (size_t)((nl + 3) & ~3u));
+    uint32_t *hist = changed + 1;
+    cudaMemsetAsync(d_height, 0, 2 * (size_t)((nl + 3) & ~3u) + 4 + 1024, s);
+    const int blocks = sm_count * 8;
+    uint32_t flag = 1;
+    for (int round = 0; round < 256 && flag; round += 8) {
+        cudaMemsetAsync(changed, 0, 4, s);
+        for (int k = 0; k < 8; ++k) {
+            k_height_round<<<blocks, 256, 0, s>>>(db, h0, h1, nl, changed);
+            std::swap(h0, h1);
+        }
+        cudaMemcpyAsync(&flag, changed, 4, cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+    }
+    k_order_hist<<<blocks, 256, 0, s>>>(h0, nl, hist);
+    k_order_scan<<<1, 256, 0, s>>>(hist);
+    k_order_scatter<<<blocks, 256, 0, s>>>(h0, nl, hist, d_order);
+}
 
 static uint32_t ilog2(uint32_t x) { uint32_t l = 0; while ((1u << l) < x) ++l; return l; }
 
@@ -1019,9 +1328,40 @@ void launch_sort_sets(const BatchView &b, uint32_t cap, int sm_count, cudaStream
     k_sort_sets<<<sm_count * 4, SORT_THREADS, smem, s>>>(b, cap);
 }
 
-void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, cudaStream_t s)
+void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, bool from_huge, cudaStream_t s)
 {
-    k_big<<<blocks, BIG_THREADS, 0, s>>>(db, b, ls);
+    k_big<<<blocks, BIG_THREADS, 0, s>>>(db, b, ls, from_huge ? 1 : 0);
+}
+
+// shapes of the CTA-per-probe tiers: the second tier runs several CTAs per SM on a 64 KB table, the third one CTA per SM
+// on a 192 KB table (hash load <= 1/2 resp. 2/3 at the trail capacity, plus room for the entries every warp may add
+// before the overflow is seen)
+BlockTier block_tier_shape(int cls, uint32_t cap)
+{
+    BlockTier t;
+    t.threads = cls ? 1024 : 256;
+    t.cap = cap;
+    t.hs = cls ? cap + cap / 2 : 2 * cap;
+    t.hs = std::max<uint32_t>(t.hs, cap + 2048);
+    return t;
+}
+
+template <int THREADS> static int block_bps(const BlockTier &t)
+{
+    int nb = 0;
+    const size_t smem = (size_t)t.hs * 4;
+    if (cudaFuncSetAttribute(k_block<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_block<THREADS>, THREADS, smem);
+    return nb;
+}
+
+int block_tier_blocks_per_sm(const BlockTier &t) { return t.threads == 1024 ? block_bps<1024>(t) : block_bps<256>(t); }
+
+void launch_block_tier(const DbView &db, const BatchView &b, const BlockTier &t, int cls, uint32_t *trail_slab, int blocks, cudaStream_t s)
+{
+    const size_t smem = (size_t)t.hs * 4;
+    if (t.threads == 1024) k_block<1024><<<blocks, 1024, smem, s>>>(db, b, trail_slab, t.hs, t.cap, cls);
+    else k_block<256><<<blocks, 256, smem, s>>>(db, b, trail_slab, t.hs, t.cap, cls);
 }
 
 int scan_gather_max_blocks(int sm_count)
@@ -1053,6 +1393,8 @@ bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant
     if (giant_sets_possible) k_gather_long<<<max_blocks, 256, 0, s>>>(b);
     return cudaPeekAtLastError() == cudaSuccess;
 }
+
+void launch_merge_drain(const MergeArgs &m, cudaStream_t s) { k_merge_drain<<<1, 32, 0, s>>>(m); }
 
 void launch_merge(const MergeArgs &m, int sm_count, cudaStream_t s)
 {

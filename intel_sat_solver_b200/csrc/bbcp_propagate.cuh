@@ -11,11 +11,25 @@
 #pragma once
 #include "bbcp_device.cuh"
 
+// Diagnostic build (-DBBCP_CHECKS, `make checks`): bounds checks and a loop watchdog. A failing check records its source
+// line, CTA and thread in a mapped host buffer (device printf output is lost when the context dies) and traps; the
+// host prints the record with the CUDA error (bbcp_capi.cu, cuda_ok). Compiled out of the product build.
 #ifdef BBCP_CHECKS
 #include <cstdio>
-#define BBCP_CHECK(cond, ...) do { if (!(cond)) { printf("BBCP_CHECK failed: " #cond " | " __VA_ARGS__); __trap(); } } while (0)
+namespace bbcp { __device__ unsigned long long *g_dbg = nullptr; }   // (this header is included by bbcp_kernels.cu only)
+#define BBCP_FAIL(v0, v1) do { if (bbcp::g_dbg && bbcp::g_dbg[0] == 0ull) { bbcp::g_dbg[0] = (unsigned long long)__LINE__; \
+        bbcp::g_dbg[1] = blockIdx.x; bbcp::g_dbg[2] = threadIdx.x; bbcp::g_dbg[3] = (unsigned long long)(v0); bbcp::g_dbg[4] = (unsigned long long)(v1); \
+        __threadfence_system(); } __trap(); } while (0)
+#define BBCP_CHECK(cond, ...) do { if (!(cond)) { printf("BBCP_CHECK failed: " #cond " | " __VA_ARGS__); BBCP_FAIL(0, 0); } } while (0)
+#define BBCP_MARK(id) do { if (bbcp::g_dbg && blockIdx.x < 480 && blockDim.x == 256 && (threadIdx.x & 31) == 0) bbcp::g_dbg[256 + blockIdx.x * 8 + (threadIdx.x >> 5)] = ((unsigned long long)(id) << 32) | __LINE__; } while (0)
+#define BBCP_WATCH_BEGIN() const unsigned long long bbcp_watch_t0 = bbcp::watch_ns()
+#define BBCP_WATCH(v0, v1) do { if (bbcp::watch_ns() - bbcp_watch_t0 > 4000000000ull) BBCP_FAIL(v0, v1); } while (0)
+namespace bbcp { __device__ __forceinline__ unsigned long long watch_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; } }
 #else
 #define BBCP_CHECK(cond, ...) do { } while (0)
+#define BBCP_MARK(id) do { } while (0)
+#define BBCP_WATCH_BEGIN() do { } while (0)
+#define BBCP_WATCH(v0, v1) do { } while (0)
 #endif
 
 namespace bbcp {
@@ -158,7 +172,52 @@ struct GhashState {
     }
 };
 
-// ---------------------------------------------------------------- per-probe state, third tier (dense, global slab)
+// ---------------------------------------------------------------- per-probe state, CTA-wide (shared hash, global trail)
+// One CTA owns the probe. Only the randomly accessed part of the state -- the set of true literals -- is in shared
+// memory (up to ~200 KB: tens of thousands of literals); the trail, which is appended and consumed sequentially, streams
+// through a per-CTA slab in global memory with coalesced accesses. The per-warp global hash of k_deep2 paid a DRAM
+// sector for every look-up once the slabs of all resident warps outgrew the L2 (profiles/r02: 323 GB of DRAM reads for
+// 1.1 G implied literals on the Tseitin shape); this state pays none. Any table size (multiply-shift range reduction).
+struct BhashState {
+    uint32_t *hash;   // shared memory [hs], 0 = empty
+    uint32_t *trail;  // global [cap]
+    uint32_t hs, cap;
+
+    __device__ __forceinline__ uint32_t h(uint32_t var) const { return __umulhi(var * 0x9E3779B1u, hs); }
+    __device__ __forceinline__ int lookup(uint32_t lit) const
+    {
+        const uint32_t var = lit >> 1;
+        uint32_t s = h(var);
+        for (uint32_t guard = 0;; ++guard) {
+            BBCP_CHECK(guard <= hs, "shared hash full on lookup (hs %u cap %u blk %d)\n", hs, cap, blockIdx.x);
+#ifdef BBCP_CHECKS
+            if (guard >= 64 && bbcp::g_dbg) bbcp::g_dbg[8] = ((unsigned long long)lit << 32) | guard;   // long probe sequences
+#endif
+            const uint32_t k = *(volatile uint32_t *)&hash[s];
+            if (k == 0) return 0;
+            if ((k >> 1) == var) return k == lit ? 1 : 2;
+            if (++s == hs) s = 0;
+        }
+    }
+    __device__ __forceinline__ int insert(uint32_t lit, uint32_t &slot)
+    {
+        const uint32_t var = lit >> 1;
+        uint32_t s = h(var);
+        slot = 0;
+        for (uint32_t guard = 0;; ++guard) {
+            BBCP_CHECK(guard <= hs, "shared hash full on insert (hs %u cap %u blk %d)\n", hs, cap, blockIdx.x);
+            const uint32_t old = atomicCAS(&hash[s], 0u, lit);
+            if (old == 0) return 0;
+            if ((old >> 1) == var) return old == lit ? 1 : 2;
+            if (++s == hs) s = 0;
+        }
+    }
+    __device__ __forceinline__ uint32_t tget(uint32_t i) const { return __ldcg(&trail[i]); }
+    __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t) { __stcg(&trail[i], lit); }
+    template <class G> __device__ __forceinline__ void wipe() {}   // the kernel clears the whole table after every probe
+};
+
+// ---------------------------------------------------------------- per-probe state, last tier (dense, global slab)
 struct GmemState {
     uint32_t *bits;   // 2 bits per var: 1 = var true, 2 = var false
     uint32_t *trail;
@@ -243,7 +302,10 @@ struct GroupTail {
 struct BlockTail {
     uint32_t *ctl;  // shared: [0] tail, [1] conflict latch, [2] overflow latch
     __device__ __forceinline__ uint32_t get() const { return *(volatile uint32_t *)&ctl[0]; }
-    __device__ __forceinline__ bool aborted() const { return (*(volatile uint32_t *)&ctl[1] | *(volatile uint32_t *)&ctl[2]) != 0; }
+    // Warp-uniform by a vote: the latches are written by OTHER warps at any time, and the lanes of a warp do not
+    // necessarily read them in the same cycle; a warp whose lanes disagreed here would split -- some lanes leave
+    // process_batch, the rest wait for them at the next shuffle (seen on B200 as a CTA that never finishes)
+    __device__ __forceinline__ bool aborted() const { return __any_sync(FULL, (*(volatile uint32_t *)&ctl[1] | *(volatile uint32_t *)&ctl[2]) != 0) != 0; }
     template <class G> __device__ __forceinline__ void latch_conflict() { if (G::lane() == 0) ctl[1] = 1; }
     template <class G> __device__ __forceinline__ void drop() {}   // (the dense third-tier state cannot overflow)
     template <class G, class S, bool ADOPT = false>
@@ -338,7 +400,9 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_
     wc.slots += total;
     wc.bytes += 16ull * B + 8ull * total;
 
+    BBCP_WATCH_BEGIN();
     for (uint32_t base = 0; base < total; base += W) {
+        BBCP_WATCH(total, base);
         const uint32_t g = base + lane;
         const bool active = g < total;
         // owner row of slot g: the largest lane i with excl_i <= g
@@ -418,44 +482,73 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_
 // still gets its row walked, so the fixpoint, the conflict answer and the sorted implied set are unchanged (unit
 // propagation is confluent). What it changes is the shape of the work: the breadth-first frontier of a probe is a few
 // literals wide (the kernels were instruction-issue-bound at ~3 literals per 32-lane step), adopted sets fill the lanes.
-// `tier`: 1 shared-memory state, 2 global hash, 3 dense. Returns 0 / 1 conflict / 2 overflow.
+// `tier`: 1 warp + shared-memory state, 2 / 3 CTA + shared hash (two sizes), 4 dense. Returns 0 / 1 conflict / 2 overflow.
 __device__ __forceinline__ uint8_t ld_flag(const uint8_t *p) { return *(const volatile uint8_t *)p; }
 
-template <class G, class S, class T>
-__device__ int expand_closures(const BatchView &b, S &st, T &tl, uint32_t e, uint32_t B, int tier, WorkCounters &wc)
+// Per lane: the finished result of the lane's literal's own probe, if there is one. Returns 0, 1 (a conflict is
+// inherited) or 2 (an overflow is inherited) for the whole group; len > 1 in the lanes that have a set to adopt.
+template <class G, class T>
+__device__ __forceinline__ int closure_lookup(const BatchView &b, T &tl, uint32_t e, uint32_t B, int tier, WorkCounters &wc, uint32_t &len,
+                                              unsigned long long &off)
 {
     const int lane = G::lane();
+    len = 0;
+    off = 0;
     const uint64_t u = (uint64_t)(e & ~TRAIL_CLOSED) - 2u - b.first;      // item index of the literal's own probe
     const bool want = lane < (int)B && !(e & TRAIL_CLOSED) && (e & ~TRAIL_CLOSED) >= 2u + b.first && u < b.n;
     const uint8_t f = want ? ld_flag(&b.flag[u]) : (uint8_t)FLAG_QUEUED;
     if (G::any(f == FLAG_CONFLICT)) { tl.template latch_conflict<G>(); ++wc.inherited; return 1; }
-    if (tier < 3 && G::any(f == FLAG_OVERFLOW2 || (tier == 1 && f == FLAG_OVERFLOW))) { ++wc.inherited; return 2; }
-    unsigned m = G::ballot(f == FLAG_OK);
-    if (!m || !(b.opts & OPT_IMPLIED)) return 0;
+    // tier t hands on what outgrew it with flag FLAG_OVERFLOW - (t - 1); a literal whose probe outgrew THIS tier or a later one
+    // takes this probe with it (its set is a subset of this one)
+    if (G::any(f >= FLAG_OVERFLOW_LAST && f <= (uint8_t)(FLAG_OVERFLOW + 1 - tier))) { ++wc.inherited; return 2; }
+    if (!G::any(f == FLAG_OK) || !(b.opts & OPT_IMPLIED)) return 0;
     __threadfence();   // the set was published before the flag (publish_result)
-    uint32_t len = 0;
-    unsigned long long off = 0;
     if (f == FLAG_OK) {
         len = __ldcg(&b.len[u]);
         if (len & LEN_SELF) len = 0;         // implies only itself
-        if (len > 1) off = __ldcg((const unsigned long long *)&b.raw_off[u]);
+        if (len > 1) off = __ldcg((const unsigned long long *)&b.raw_off[u]); else len = 0;
+        BBCP_CHECK(off + len <= b.out_cap, "finished set of item %llu: off %llu len %u cap %llu\n", (unsigned long long)u, off, len, (unsigned long long)b.out_cap);
     }
-    m = G::ballot(len > 1);
+    return 0;
+}
+
+// The group enters literals [first, first + W), [first + stride, ...) ... of a finished set. Returns 0 / 1 / 2.
+template <class G, class S, class T>
+__device__ __forceinline__ int closure_adopt(const BatchView &b, S &st, T &tl, unsigned long long src, uint32_t n, uint32_t first, uint32_t stride)
+{
+    const int lane = G::lane();
+    BBCP_CHECK(src + n <= b.out_cap, "adopting off %llu len %u of %llu\n", src, n, (unsigned long long)b.out_cap);
+    BBCP_WATCH_BEGIN();
+    for (uint32_t i = first; i < n; i += stride) {
+        BBCP_WATCH(n, i);
+        const uint32_t c = i + lane < n ? (uint32_t)__ldcg(&b.out_lits[src + i + lane]) : 0u;
+        BBCP_CHECK(c == 0 || (c >= 2 && !(c & TRAIL_CLOSED)), "adopted literal %u (off %llu + %u of %u)\n", c, src, i + lane, n);
+        const int r = tl.template commit<G, S, true>(st, c);
+        if (r) return r;
+        if (tl.aborted()) return 1;
+    }
+    return 0;
+}
+
+template <class G, class S, class T>
+__device__ int expand_closures(const BatchView &b, S &st, T &tl, uint32_t e, uint32_t B, int tier, WorkCounters &wc)
+{
+    uint32_t len;
+    unsigned long long off;
+    const int r0 = closure_lookup<G>(b, tl, e, B, tier, wc, len, off);
+    if (r0) return r0;
+    unsigned m = G::ballot(len > 1);
     while (m) {
         const int k = __ffs(m) - 1;
         m &= m - 1;
         const uint32_t n = G::shfl(len, k);
         const unsigned long long src = G::shfl(off, k);
         if (n > st.cap) return 2;
-        for (uint32_t i = 0; i < n; i += G::width) {
-            const uint32_t c = i + lane < n ? (uint32_t)__ldcg(&b.out_lits[src + i + lane]) : 0u;
-            const int r = tl.template commit<G, S, true>(st, c);
-            if (r) return r;
-        }
+        const int r = closure_adopt<G>(b, st, tl, src, n, 0, G::width);
+        if (r) return r;
         ++wc.adopted;
         wc.adopt_lits += n;
         wc.bytes += 4ull * n;
-        if (tl.aborted()) return 1;
     }
     return 0;
 }
