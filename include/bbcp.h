@@ -99,6 +99,9 @@ typedef struct {
      * a trail, decisions included) and BCP() calls (m_BCPs, TopiBcp.cc:176: one per decision level opened, i.e. per
      * probe, and per cube literal that was still unassigned when its turn came -- see DESIGN.md on what is exact) */
     uint64_t assignments, bcps;
+    /* the order-independent parts, comparable with the reference run on the same items: literals put on the trails of the
+     * items that reached a fixpoint (= n_implied of a batch of probes), and props_ref restricted to those items */
+    uint64_t assignments_ok, props_ref_ok;
 } bbcp_batch_info;
 
 typedef struct {

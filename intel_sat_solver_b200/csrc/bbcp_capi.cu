@@ -532,9 +532,11 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
         if (n && h_u32[U32_MID_COUNT] != 0) {
             // some probes outgrew the first tier: CTA-per-probe tiers, then the compaction for real
             second = true;
-            // BBCP_TIER2=warp: the round-1 second tier (warp per probe, hash + trail in a global slab, k_deep2 + k_sort_sets)
-            // instead of the two CTA-per-probe tiers with the hash in shared memory; kept for the A/B in profiles/r02
-            static const bool tier2_warp = getenv("BBCP_TIER2") && !strcmp(getenv("BBCP_TIER2"), "warp");
+            // second tier: warp per probe, growing hash + trail in a global slab (k_deep2), then the dense last tier.
+            // BBCP_TIER2=block selects the alternative that was built and measured in round 2 -- two CTA-per-probe tiers with
+            // the hash in shared memory (k_block): no DRAM traffic for the state, but a CTA pays a barrier round per
+            // breadth-first level and the Tseitin probes are hundreds of levels deep: 3.0 s against 1.95 s per C3 pass
+            static const bool tier2_warp = !(getenv("BBCP_TIER2") && !strcmp(getenv("BBCP_TIER2"), "block"));
             if (!ensure_slabs(h, dbv)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (last-tier state)");
             ls.bits = h->d_lbits.as<uint32_t>();
             ls.trail = h->d_ltrail.as<uint32_t>();
@@ -636,6 +638,10 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     bi.adopted = h->h_misc[C_ADOPTED];
     bi.adopt_lits = h->h_misc[C_ADOPT_LITS];
     bi.inherited = h->h_misc[C_INHERITED];
+    bi.assignments = h->h_misc[C_ASSIGN];
+    bi.assignments_ok = h->h_misc[C_ASSIGN_OK];
+    bi.props_ref_ok = h->h_misc[C_PROPS_REF_OK];
+    bi.bcps = h->h_misc[C_BCPS];
     // bytes model: triage = 1 B of literal facts + 1 B flag + 4 B size per item (+ 4 B literal for
     // probe lists, + 16 B offsets more for cubes); propagation = row headers, row slots, clause units, stored
     // implied literals (kernel counters) + the per-item record (flag, size, position) of the queued items;
@@ -1007,6 +1013,8 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
         tot.n += bi.n; tot.n_implied += bi.n_implied; tot.n_ok += bi.n_ok; tot.n_conflict += bi.n_conflict; tot.n_skipped += bi.n_skipped;
         tot.n_large += bi.n_large; tot.n_mid += bi.n_mid; tot.props_all += bi.props_all; tot.props_ref += bi.props_ref; tot.slots += bi.slots;
         tot.clause_fetches += bi.clause_fetches; tot.kernel_bytes += bi.kernel_bytes; tot.triage_bytes += bi.triage_bytes; tot.n_deep += bi.n_deep;
+        tot.adopted += bi.adopted; tot.adopt_lits += bi.adopt_lits; tot.inherited += bi.inherited; tot.assignments += bi.assignments; tot.bcps += bi.bcps;
+        tot.assignments_ok += bi.assignments_ok; tot.props_ref_ok += bi.props_ref_ok;
         tot.kernel_ms += bi.kernel_ms; tot.total_ms += bi.total_ms; tot.launches += bi.launches; tot.triage_ms += bi.triage_ms;
         tot.deep_ms += bi.deep_ms; tot.block_ms += bi.block_ms; tot.mid_ms += bi.mid_ms; tot.compact_ms += bi.compact_ms; tot.tier1_ms += bi.tier1_ms;
     }

@@ -100,6 +100,7 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
     publish_result<G>(b, item, flag, len, off);
     wc.n_ok += flag == FLAG_OK;
     wc.n_conf += flag == FLAG_CONFLICT;
+    if (flag != FLAG_OVERFLOW) wc.end_item(flag == FLAG_OK, tail, true);   // (a probe handed on is counted by the tier that finishes it)
     G::sync();
 }
 
@@ -246,9 +247,14 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_cnt[0]) { atomicAdd(&b.counters[C_OK], (unsigned long long)s_cnt[0]); atomicAdd(&b.counters[C_PROPS_ALL], (unsigned long long)s_cnt[0]); }
+        if (s_cnt[0]) {
+            // a probe decided here assigns its own literal and runs one (empty) propagation
+            atomicAdd(&b.counters[C_OK], (unsigned long long)s_cnt[0]); atomicAdd(&b.counters[C_PROPS_ALL], (unsigned long long)s_cnt[0]);
+            atomicAdd(&b.counters[C_ASSIGN], (unsigned long long)s_cnt[0]); atomicAdd(&b.counters[C_ASSIGN_OK], (unsigned long long)s_cnt[0]);
+            atomicAdd(&b.counters[C_BCPS], (unsigned long long)s_cnt[0]);
+        }
         if (s_cnt[1]) atomicAdd(&b.counters[C_SKIPPED], (unsigned long long)s_cnt[1]);
-        if (s_cnt[2]) atomicAdd(&b.counters[C_PROPS_REF], (unsigned long long)s_cnt[2]);
+        if (s_cnt[2]) { atomicAdd(&b.counters[C_PROPS_REF], (unsigned long long)s_cnt[2]); atomicAdd(&b.counters[C_PROPS_REF_OK], (unsigned long long)s_cnt[2]); }
     }
 }
 
@@ -314,6 +320,7 @@ k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t
         BBCP_CHECK(it_idx < b.n, "queued item %llu of %llu (ndeep %u)\n", (unsigned long long)it_idx, (unsigned long long)b.n, ndeep);
         const Item it = get_item(b, it_idx);
         GroupTail tl{0};
+        wc.begin_item();
         int f = it.probe_lit ? load_probe<G>(db, st, it.probe_lit, tl) : load_cube<G>(db, st, it.lits, it.n, tl);
         int res;
         if (f == 0xff) res = propagate<G>(db, b, st, tl, prune, 1, wc);
@@ -347,8 +354,9 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
     GhashState st;
     st.hash = slab + (size_t)ggrp * ((1u << log_hs) + cap);
     st.trail = st.hash + (1u << log_hs);
-    st.log_hs = log_hs;
+    st.log_max = log_hs;
     st.cap = cap;
+    st.reset_size();
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
     WorkCounters wc;
     for (;;) {
@@ -359,6 +367,7 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
         const uint64_t item = b.mid_list[t];
         const Item it = get_item(b, item);
         GroupTail tl{0};
+        wc.begin_item();
         const int f = it.probe_lit ? load_probe<G>(db, st, it.probe_lit, tl) : load_cube<G>(db, st, it.lits, it.n, tl);
         int res;
         if (f == 0xff) res = propagate<G>(db, b, st, tl, prune, 2, wc);
@@ -366,6 +375,7 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
         else if (f == FLAG_CONFLICT) res = 1;
         else {
             st.template cleanup<G>(tl.tail);
+            st.reset_size();
             publish_result<G>(b, item, (uint8_t)f, 0, 0);
             if (lane == 0) atomicAdd(&b.counters[C_MID], 1ull);
             ++wc.n_skip;
@@ -380,6 +390,7 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
             flag = FLAG_OVERFLOW2;
             if (lane == 0) b.big_list[atomicAdd(b.big_count, 1u)] = (uint32_t)item;
             st.template wipe<G>();   // some table entries have no trail entry
+            st.reset_size();
         } else {
             if (res == 1) {
                 flag = FLAG_CONFLICT;
@@ -399,11 +410,13 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
             }
             G::sync();
             st.template cleanup<G>(tail);
+            st.reset_size();
         }
         publish_result<G>(b, item, flag, len, off);
         if (lane == 0 && flag != FLAG_OVERFLOW2) atomicAdd(&b.counters[C_MID], 1ull);
         wc.n_ok += flag == FLAG_OK;
         wc.n_conf += flag == FLAG_CONFLICT;
+        if (flag != FLAG_OVERFLOW2) wc.end_item(flag == FLAG_OK, tail, true);
         G::sync();
     }
     wc.template flush<G>(b.counters);
@@ -446,7 +459,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_sets(const BatchView b, c
 // a per-CTA slab in global memory) and walk each breadth-first level of the trail together (level-synchronous,
 // two barriers per level).
 constexpr uint32_t ADOPT_MAX = 64;   // finished sets adopted CTA-wide per level; further ones are entered by the warp that found them
+// narrow frontiers: while a level holds at most NARROW_IN literals, warp 0 walks the successive levels alone (no CTA
+// barrier per level -- a deep implication chain costs a CTA five barriers per literal otherwise); it hands back to the
+// whole CTA when the frontier widens beyond NARROW_OUT or a finished set of more than NARROW_ADOPT literals shows up
+constexpr uint32_t NARROW_IN = 32, NARROW_OUT = 128, NARROW_ADOPT = 512;
 
+// ctl: [0] tail, [1] conflict latch, [2] overflow latch, [6] "the next level is for the whole CTA", [7] head handed back by warp 0
 template <class S>
 __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uint32_t *ctl, bool prune, int tier, WorkCounters &wc)
 {
@@ -456,20 +474,54 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
     __shared__ uint32_t s_na;
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     BlockTail tl{ctl};
+    const volatile uint32_t *vctl = ctl;
     uint32_t head = 0;
     BBCP_WATCH_BEGIN();
     for (;;) {
         BBCP_WATCH(head, ctl[0]);
-        BBCP_MARK(head);
         __syncthreads();
-        const volatile uint32_t *vctl = ctl;
         const uint32_t level_end = vctl[0];
         const bool stop = (vctl[1] | vctl[2]) != 0 || head >= level_end;
+        const bool narrow = !stop && !vctl[6] && level_end - head <= NARROW_IN;
         if (threadIdx.x == 0) s_na = 0;
-        BBCP_MARK(level_end);
         __syncthreads();   // everybody has its snapshot before anyone appends
-        BBCP_MARK(stop);
         if (stop) break;
+        if (narrow) {
+            if (warp == 0) {
+                uint32_t hcur = head;
+                for (;;) {
+                    const uint32_t end = vctl[0];    // only this warp appends now
+                    if (hcur >= end) break;
+                    if (end - hcur > NARROW_OUT) { if (lane == 0) ctl[6] = 1; break; }
+                    const uint32_t B = min(32u, end - hcur);
+                    const uint32_t e = lane < (int)B ? st.tget(hcur + lane) : 0u;
+                    if (b.reuse && end > 1) {
+                        uint32_t len;
+                        unsigned long long off;
+                        const int r = closure_lookup<G>(b, tl, e, B, tier, wc, len, off);
+                        if (r == 2 && lane == 0) ctl[2] = 1;          // an inherited overflow: hand the probe on
+                        if (r) break;
+                        if (G::any(len > NARROW_ADOPT)) { if (lane == 0) ctl[6] = 1; break; }   // a large set: all warps enter it
+                        unsigned m = G::ballot(len > 1);
+                        int ra = 0;
+                        while (m && !ra) {
+                            const int k = __ffs(m) - 1;
+                            m &= m - 1;
+                            const uint32_t n = G::shfl(len, k);
+                            ra = closure_adopt<G>(b, st, tl, G::shfl(off, k), n, 0, 32);
+                            if (!ra) { ++wc.adopted; wc.adopt_lits += n; wc.bytes += 4ull * n; }
+                        }
+                        if (ra) break;
+                    }
+                    if (process_batch<G>(db, st, tl, e, B, prune && end == 1, wc)) break;
+                    hcur += B;
+                }
+                if (lane == 0) ctl[7] = hcur;
+            }
+            __syncthreads();
+            head = vctl[7];
+            continue;
+        }
         if (b.reuse && level_end > 1) {
             // closure reuse, CTA-wide: the warps look up the literals of the level, the finished sets found are listed in
             // shared memory, then ALL warps enter each set together (a set of this tier has tens of thousands of literals;
@@ -479,7 +531,9 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
                 const uint32_t e = lane < (int)B ? st.tget(bse + lane) : 0u;
                 uint32_t len;
                 unsigned long long off;
-                if (closure_lookup<G>(b, tl, e, B, tier, wc, len, off)) break;
+                const int r = closure_lookup<G>(b, tl, e, B, tier, wc, len, off);
+                if (r == 2 && lane == 0) ctl[2] = 1;                  // an inherited overflow: hand the probe on
+                if (r) break;
                 if (G::any(len > st.cap)) { if (lane == 0) ctl[2] = 1; break; }   // a set that cannot fit: hand the probe on right away
                 uint32_t slot = ADOPT_MAX;
                 if (len > 1) slot = atomicAdd(&s_na, 1u);
@@ -504,12 +558,11 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
         }
         const bool bins_only = prune && level_end == 1;
         for (uint32_t bse = head + warp * 32; bse < level_end; bse += nwarps * 32) {
-            BBCP_MARK(bse);
             const uint32_t B = min(32u, level_end - bse);
             const uint32_t e = lane < (int)B ? st.tget(bse + lane) : 0u;
             if (process_batch<G>(db, st, tl, e, B, bins_only, wc)) break;
         }
-        BBCP_MARK(level_end);
+        if (threadIdx.x == 0) ctl[6] = 0;   // (read again only behind the barrier at the loop head)
         head = level_end;
     }
 }
@@ -548,6 +601,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
         if (t >= count) break;
         const uint64_t item = list[t];
         const Item it = get_item(b, item);
+        wc.begin_item();
         if (warp == 0) {
             BlockTail tl{ctl};
             const int f = it.probe_lit ? load_probe<G>(db, gs, it.probe_lit, tl) : load_cube<G>(db, gs, it.lits, it.n, tl);
@@ -644,6 +698,8 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
             wc.n_conf += flag == FLAG_CONFLICT;
             wc.n_skip += flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED;
         }
+        // every warp settles its own share of the row counters; the trail length is counted once
+        wc.end_item(flag == FLAG_OK, threadIdx.x == 0 && flag <= FLAG_CONFLICT ? tail : 0u, threadIdx.x == 0);
     }
     wc.flush<G>(b.counters);
 }
@@ -700,11 +756,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_block(const DbView db, const Bat
     BBCP_WATCH_BEGIN();
     for (;;) {
         BBCP_WATCH(ctl[4], count);
-        BBCP_MARK(1);
-        __syncthreads();
+                __syncthreads();
         if (threadIdx.x == 0) {
             ctl[4] = atomicAdd(ticket, 1u);
-            ctl[0] = ctl[1] = ctl[2] = 0;
+            ctl[0] = ctl[1] = ctl[2] = ctl[6] = 0;
             ctl[3] = 0xff;
         }
         __syncthreads();
@@ -712,16 +767,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_block(const DbView db, const Bat
         if (t >= count) break;
         const uint64_t item = list[t];
         const Item it = get_item(b, item);
+        wc.begin_item();
         if (warp == 0) {
             BlockTail tl{ctl};
             const int f = it.probe_lit ? load_probe<G>(db, st, it.probe_lit, tl) : load_cube<G>(db, st, it.lits, it.n, tl);
             if (lane == 0) ctl[3] = (uint32_t)f;
         }
-        BBCP_MARK(2);
         __syncthreads();
         const uint32_t f = ctl[3];
         if (f == 0xff) block_propagate(db, b, st, ctl, prune, 2 + cls, wc);
-        BBCP_MARK(3);
         __syncthreads();
         const bool overflow = ctl[2] != 0 || f == FLAG_OVERFLOW;
         const bool conflict = !overflow && (ctl[1] != 0 || f == FLAG_CONFLICT);
@@ -757,12 +811,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_block(const DbView db, const Bat
                 }
             }
         }
-        BBCP_MARK(4);
         __syncthreads();
         // leave the table empty for the next probe (it holds the probe's literals, or the sorted trail)
         for (uint32_t i = threadIdx.x; i < hs; i += THREADS) s_hash[i] = 0;
         if (b.reuse) __threadfence();   // every thread: its part of the set is out (publish_result, CTA-wide)
-        BBCP_MARK(5);
         __syncthreads();
         if (threadIdx.x == 0) {
             b.len[item] = len; b.raw_off[item] = off;
@@ -774,9 +826,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_block(const DbView db, const Bat
             wc.n_conf += flag == FLAG_CONFLICT;
             wc.n_skip += flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED;
         }
+        if (!overflow) wc.end_item(flag == FLAG_OK, threadIdx.x == 0 && flag <= FLAG_CONFLICT ? tail : 0u, threadIdx.x == 0);
     }
     wc.flush<G>(b.counters);
-    BBCP_MARK(0xDEAD);
 }
 
 // ---------------------------------------------------------------- multi-GPU merge of the bitmap slices

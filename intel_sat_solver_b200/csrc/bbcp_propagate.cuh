@@ -111,16 +111,24 @@ struct SmemState {
         for (uint32_t i = G::lane(); i < (1u << log_hs); i += G::width) hash[i] = 0;
         G::sync();
     }
+    template <class G> __device__ __forceinline__ void maybe_grow(uint32_t) {}
 };
 
 // ---------------------------------------------------------------- per-probe state, second tier (global hash)
 // Same open-addressed set + trail, but in a per-group slab in global memory (L2-resident while hot): a probe
 // with a trail of thousands of literals still occupies one group of lanes, so hundreds of them run per SM,
 // where a shared-memory state of that size would allow four.
+// The table GROWS with the probe: it starts at 2^GHASH_LOG_MIN entries and is rebuilt four times larger from the trail
+// whenever it is half full, up to 2^log_max (= twice the trail capacity). A fixed full-size table made every look-up a
+// DRAM sector once the slabs of all resident warps (thousands x 96 KB) outgrew the 126 MB L2 -- ncu on the Tseitin
+// shape: 18 % L2 hit rate, 323 GB of DRAM reads for 1.1 G implied literals; most second-tier probes hold a few
+// thousand literals and now touch a few tens of KB. Invariant: the slab is all zero beyond the live table.
+constexpr uint32_t GHASH_LOG_MIN = 11;
 struct GhashState {
     uint32_t *hash;   // [1 << log_hs] true literals, 0 = empty
     uint32_t *trail;  // [cap]
-    uint32_t log_hs, cap;
+    uint32_t log_hs, cap;   // log_hs: the live size
+    uint32_t log_max;
 
     __device__ __forceinline__ uint32_t h(uint32_t var) const { return (var * 0x9E3779B1u) >> (32 - log_hs); }
     __device__ __forceinline__ int lookup(uint32_t lit) const
@@ -170,6 +178,17 @@ struct GhashState {
         for (uint32_t i = G::lane(); i < (1u << log_hs) / 4; i += G::width) __stcg(&p[i], make_uint4(0, 0, 0, 0));
         G::sync();
     }
+    // call between commits (every table entry is on the trail then): rebuild a larger table once this one is half full
+    template <class G> __device__ __forceinline__ void maybe_grow(uint32_t tail)
+    {
+        if (log_hs >= log_max || 2u * tail <= (1u << log_hs)) return;
+        wipe<G>();
+        while (log_hs < log_max && 2u * tail > (1u << log_hs)) log_hs = min(log_hs + 2u, log_max);
+        for (uint32_t i = G::lane(); i < tail; i += G::width) { uint32_t slot; insert(__ldcg(&trail[i]) & ~TRAIL_CLOSED, slot); }
+        G::sync();
+    }
+    // after cleanup / wipe: the next probe starts small again
+    __device__ __forceinline__ void reset_size() { log_hs = min(GHASH_LOG_MIN, log_max); }
 };
 
 // ---------------------------------------------------------------- per-probe state, CTA-wide (shared hash, global trail)
@@ -215,6 +234,7 @@ struct BhashState {
     __device__ __forceinline__ uint32_t tget(uint32_t i) const { return __ldcg(&trail[i]); }
     __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t) { __stcg(&trail[i], lit); }
     template <class G> __device__ __forceinline__ void wipe() {}   // the kernel clears the whole table after every probe
+    template <class G> __device__ __forceinline__ void maybe_grow(uint32_t) {}
 };
 
 // ---------------------------------------------------------------- per-probe state, last tier (dense, global slab)
@@ -241,12 +261,24 @@ struct GmemState {
     __device__ __forceinline__ uint32_t tget(uint32_t i) const { return __ldcg(&trail[i]); }
     __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t) { __stcg(&trail[i], lit); }
     template <class G> __device__ __forceinline__ void wipe() {}   // cannot overflow: the trail holds every variable
+    template <class G> __device__ __forceinline__ void maybe_grow(uint32_t) {}
 };
 
 // per-group work counters, kept in registers (uniform over the group) and flushed once
 struct WorkCounters {
     unsigned long long props_all = 0, props_ref = 0, slots = 0, fetches = 0, bytes = 0, adopt_lits = 0;
-    uint32_t n_ok = 0, n_conf = 0, n_skip = 0, adopted = 0, inherited = 0;
+    // the reference's counters: Assign calls, BCP() calls, and m_Implications restricted to the probes that
+    // reach a fixpoint (the only part that does not depend on the propagation order)
+    unsigned long long assign = 0, assign_ok = 0, props_ref_ok = 0, mark_ref = 0;
+    uint32_t n_ok = 0, n_conf = 0, n_skip = 0, adopted = 0, inherited = 0, bcps = 0;
+    __device__ __forceinline__ void begin_item() { mark_ref = props_ref; }
+    // tail = literals on the trail when the item ended (0 from the warps of a CTA that do not own the tail)
+    __device__ __forceinline__ void end_item(bool ok, uint32_t tail, bool propagated)
+    {
+        assign += tail;
+        bcps += propagated && tail;
+        if (ok) { assign_ok += tail; props_ref_ok += props_ref - mark_ref; }
+    }
     template <class G> __device__ void flush(unsigned long long *c)
     {
         if (G::lane() == 0) {
@@ -261,6 +293,10 @@ struct WorkCounters {
             if (adopted) atomicAdd(&c[C_ADOPTED], (unsigned long long)adopted);
             if (adopt_lits) atomicAdd(&c[C_ADOPT_LITS], adopt_lits);
             if (inherited) atomicAdd(&c[C_INHERITED], (unsigned long long)inherited);
+            if (assign) atomicAdd(&c[C_ASSIGN], assign);
+            if (assign_ok) atomicAdd(&c[C_ASSIGN_OK], assign_ok);
+            if (props_ref_ok) atomicAdd(&c[C_PROPS_REF_OK], props_ref_ok);
+            if (bcps) atomicAdd(&c[C_BCPS], (unsigned long long)bcps);
         }
     }
 };
@@ -466,6 +502,7 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_
         }
         G::sync();
         if (tl.aborted()) return 1;  // another warp of the CTA hit a conflict / overflow
+        st.template maybe_grow<G>(tl.get());
     }
     return 0;
 }
@@ -526,6 +563,7 @@ __device__ __forceinline__ int closure_adopt(const BatchView &b, S &st, T &tl, u
         const int r = tl.template commit<G, S, true>(st, c);
         if (r) return r;
         if (tl.aborted()) return 1;
+        st.template maybe_grow<G>(tl.get());
     }
     return 0;
 }
@@ -615,6 +653,7 @@ __device__ int load_cube(const DbView &db, S &st, const int32_t *lits, uint32_t 
             const int r = tl.template commit<G>(st, cand);
             if (r == 1) conflict = true;
             if (r == 2) overflow = true;
+            if (!r) st.template maybe_grow<G>(tl.get());
         }
         G::sync();
     }

@@ -463,3 +463,46 @@ def test_seeded_random_instances_against_checker():
         n_items += flag.size + cflag.size
         n_conf += int((flag == 1).sum() + (cflag == 1).sum())
     assert n_items > 3000 and n_conf > 300 and n_unsat > 5
+
+
+def test_counters_against_the_reference(tmp_path):
+    """SURVEY 8a A14. m_Assignments (TopiAsg.cc:49), m_BCPs (TopiBcp.cc:176) and m_Implications (TopiBcp.cc:193-198)
+    of the reference's probe loop against the engine's assignments / bcps / props_ref.
+    Exact where the reference's own numbers do not depend on its propagation order and watch history: an instance
+    of binary clauses only (every occurrence is a watch, so "row ever allocated" == "literal occurs") without failed
+    literals. On mixed instances the engine counts a popped literal whose negation OCCURS in a clause, the reference
+    one whose negation has ever WATCHED a clause, so engine >= reference on the probes that reach a fixpoint; the
+    trail lengths of those probes (assignments_ok) are the implied-set sizes on both sides."""
+    rng = np.random.default_rng(7)
+    n, m = 4000, 9000
+    a = rng.integers(1, n, size=m)
+    b = a + rng.integers(1, 40, size=m)
+    keep = b <= n
+    words = np.stack([-a[keep], b[keep], np.zeros(keep.sum(), dtype=np.int64)], axis=1).astype(np.int32).ravel()   # a -> b, a < b: no failed literal
+    inst = str(tmp_path / "dag.bcnf")
+    fileio.write_bcnf(inst, words)
+    ref, rinfo = gpu_util.run_checker(inst)
+    assert rinfo["conflicts"] == 0 and rinfo["implied_lits"] > 3 * rinfo["ran"]
+    t, rc = engine_for(words)
+    assert rc == 0
+    for kw in (dict(), dict(no_reuse=True), dict(small_trail=32, mid_trail=32)):
+        res = t.ProbeAll(**kw)
+        gpu_util.assert_same_results(res, ref.flag, ref.off, ref.lits, f"dag {kw}")
+        i = res.info
+        assert i["bcps"] == int((ref.flag <= 1).sum()), kw
+        assert i["assignments"] == i["assignments_ok"] == rinfo["assignments"] == i["n_implied"], kw
+        # (props_ref also holds the work of probes that outgrew a tier and were handed on; props_ref_ok counts the final run only)
+        assert i["props_ref"] >= i["props_ref_ok"] == rinfo["implications"] == int(ref.props[ref.flag == 0].sum()), kw
+    # mixed clause lengths, failed literals: the order-independent parts
+    with tempfile.TemporaryDirectory() as d:
+        for kind, kw in (("plaw", dict(n=6000, m=24000, seed=5)), ("aig", dict(frames=3, gates=1500, inputs=60, latches=60, window=200, seed=2))):
+            inst, _ = gpu_util.gen(kind, d, **kw)
+            ref, rinfo = gpu_util.run_checker(inst)
+            t, rc = engine_for(fileio.read_bcnf(inst))
+            res = t.ProbeAll()
+            i = res.info
+            ok = ref.flag == 0
+            assert i["assignments_ok"] == i["n_implied"] == int(np.diff(ref.off)[ok].sum())
+            assert i["bcps"] == int((ref.flag <= 1).sum())
+            assert i["props_ref_ok"] >= int(ref.props[ok].sum()) > 0
+            assert i["assignments"] >= i["assignments_ok"] and i["props_ref"] >= i["props_ref_ok"]
