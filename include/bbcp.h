@@ -41,7 +41,9 @@ enum {
     BBCP_FLAG_CONFLICT = 1,    /* unit propagation derives a conflict (a failed literal for a depth-1 probe) */
     BBCP_FLAG_TRIVIAL_L0 = 2,  /* every literal of the cube is already true at level 0 (Topi.cc:851-865) */
     BBCP_FLAG_FALSE_L0 = 3,    /* some literal of the cube is false at level 0 (Topi.cc:853-860) */
-    BBCP_FLAG_UNMAPPED = 4     /* the cube names a variable that occurs in no kept clause; not propagated */
+    BBCP_FLAG_UNMAPPED = 4,    /* the cube names a variable that occurs in no kept clause; not propagated */
+    BBCP_FLAG_SELF = 0x80      /* only with BBCP_OPT_COMPACT_SELF: fixpoint reached and the implied set is exactly the probe's
+                                  own literal; that one-literal set is NOT stored (its range in impl_off is empty) */
 };
 
 /* option bits */
@@ -56,6 +58,11 @@ enum {
                                   starts (aligns the ranks' device clocks; every rank must pass the same flags) */
     BBCP_OPT_NO_REUSE = 64u,   /* diagnostic: all-literal batches propagate every probe from scratch (no adoption of the
                                   finished probes' results, DESIGN.md "closure reuse"); results are identical */
+    BBCP_OPT_COMPACT_SELF = 128u, /* compact read-back for depth-1 probes: a probe that implies nothing but itself is reported as
+                                  BBCP_FLAG_SELF and its set is left out of impl_off / impl_lits (9 of the 13 bytes a probe
+                                  costs on the way back are that one literal and its offset). bbcp_probe_lits_to_host then
+                                  copies offsets back only from the first chunk on that stores a set: when info.n_implied
+                                  == 0 the offsets are all zero and are not written at all */
     BBCP_OPT_OFF32 = 4u        /* produce impl_off as uint32 (fetch with bbcp_fetch_implied32): halves the offset
                                   read-back; the batch fails with BBCP_ERR_ARG if it implies >= 2^32 literals */
 };
@@ -188,6 +195,14 @@ int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds
 int bbcp_probe_products(bbcp_handle *h, uint32_t *necessary, uint64_t *n_necessary, int32_t *equiv /* 2 * equiv_cap */, uint64_t equiv_cap,
                         uint64_t *n_equiv);
 
+/* diagnostic: the static analogue of the reference's WLAssertNoMissedImplications (TopiWL.cc:330-442) over the fixpoints of
+ * the last batch (run with implied sets): for items first_item, first_item + stride, ... (count of them) that reached a
+ * fixpoint, every clause of the database is evaluated under the item's implied set (+ level 0); *violations counts the
+ * clause occurrences that are unsatisfied with fewer than two unassigned literals (a missed implication or conflict).
+ * O(database) per item, on the device. */
+int bbcp_check_fixpoints(bbcp_handle *h, uint64_t first_item, uint64_t count, uint64_t stride, uint64_t *violations, uint64_t *clauses_checked,
+                         uint64_t *items_checked);
+
 /* ---- results of the last batch, device -> caller buffers */
 int bbcp_fetch_flags(bbcp_handle *h, uint8_t *flag /* n */);
 int bbcp_fetch_implied(bbcp_handle *h, uint64_t *impl_off /* n+1 */, int32_t *impl_lits /* n_implied */);
@@ -225,6 +240,11 @@ int bbcp_l2_flush(bbcp_handle *h, uint64_t bytes);
  *      BBCP_PEER_HANDLE_BYTES blobs are exchanged by the host program (e.g. a torch.distributed / MPI all-gather),
  *      every rank calls bbcp_peer_attach with all of them in rank order. A re-finalize that changes the variable
  *      range needs bbcp_peer_detach + a new exchange. Every rank must make the same sequence of merging calls.
+ *      A merge OVERWRITES this rank's copy of the peers' slices (of both bitmaps) with what the peers hold -- it does
+ *      not OR into it. A rank tells its peers when it has finished reading their slices; bbcp_clear_bitmaps,
+ *      bbcp_finalize and bbcp_peer_detach wait for that (on the device) before they touch the bitmaps, so the caller
+ *      needs no barrier between a merge and a clear. A peer that does not show up within BBCP_MERGE_TIMEOUT_MS
+ *      (environment, default 20000) fails the call with BBCP_ERR_STATE; the time-out is not sticky.
  *      *ms (optional) = device time incl. the wait. */
 #define BBCP_PEER_HANDLE_BYTES 128
 int bbcp_peer_export(bbcp_handle *h, void *out /* BBCP_PEER_HANDLE_BYTES */);

@@ -76,6 +76,7 @@ struct bbcp_handle {
     int device = -1;
     bool prepared = false, finalized = false, device_ready = false;
     uint32_t db_version = 0;
+    bool l0_dirty = false;   // level-0 facts were added on the device after the rows were built (bbcp_probe_to_fixpoint)
     int sm_count = 148;
     int sg_blocks = 148;   // co-resident CTAs of the cooperative compaction kernel
 
@@ -265,6 +266,7 @@ bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo, bool with_or
         cudaMemsetAsync(h->d_bitmaps.p, 0, 2 * stride * 4, h->stream);   // keep the arrival flags: they are monotonic epochs
     }
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "upload sync")) return false;
+    h->l0_dirty = false;
     h->device_db_bytes = db.hdr.size() * sizeof(RowHdr) + db.slots.size() * sizeof(Slot) + db.arena.size() * 4 + litinfo.size() + 2 * h->bitmap_words * 4 + (size_t)h->order_n * 4;
     return true;
 }
@@ -339,6 +341,7 @@ DbView db_view(const bbcp_handle *h)
     v.n_slots = (uint32_t)h->db.slots.size();
     v.n_arena_units = (uint32_t)(h->db.arena.size() / 4);
     v.nvars_words16 = (uint32_t)(((uint64_t)h->db.max_var + 1 + 15) / 16);
+    v.l0_dirty = h->l0_dirty ? 1u : 0u;
     return v;
 }
 
@@ -348,7 +351,7 @@ uint32_t pow2_at_least(uint32_t x) { uint32_t p = 32; while (p < x) p <<= 1; ret
 bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
 {
     if (h->d_lbits.p && h->slab_max_var == dbv.max_var) return true;   // keyed on what sizes the slabs, not on the database version
-    const size_t per_slab = (size_t)dbv.nvars_words16 * 4 + ((size_t)dbv.max_var + 1) * 4;
+    const size_t per_slab = (size_t)dbv.nvars_words16 * 4 + (size_t)big_trail_words((uint32_t)dbv.max_var) * 4;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     free_b += h->d_lbits.bytes + h->d_ltrail.bytes;
@@ -361,7 +364,7 @@ bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
     uint64_t slabs = std::min<uint64_t>((uint64_t)h->sm_count * per_sm, (free_b / 4) / std::max<size_t>(per_slab, 1));
     slabs = std::max<uint64_t>(slabs, 1);
     h->slab_max_var = -1;
-    if (!h->d_lbits.reserve(slabs * dbv.nvars_words16 * 4, true) || !h->d_ltrail.reserve(slabs * ((size_t)dbv.max_var + 1) * 4)) return false;
+    if (!h->d_lbits.reserve(slabs * dbv.nvars_words16 * 4, true) || !h->d_ltrail.reserve(slabs * (size_t)big_trail_words((uint32_t)dbv.max_var) * 4)) return false;
     h->big_slabs = (uint32_t)slabs;
     h->slab_max_var = dbv.max_var;
     return true;
@@ -432,6 +435,9 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.tile_sum = h->d_tiles.as<unsigned long long>();
     b.zero_words = MISC_WORDS64;
     b.opts = opts.flags;
+    // rows older than the level-0 facts: a ternary clause may have shrunk to a binary one, so the triage cannot tell from the
+    // row shape which probes imply only themselves
+    if (h->l0_dirty) b.opts |= BBCP_OPT_NO_LEN_PRUNE;
     // closure reuse: all-literal batches only (item i is the probe of internal literal first + i + 2)
     static const bool no_reuse = getenv("BBCP_NO_REUSE") != nullptr;
     if (!d_lits && !d_off && !no_reuse && !(opts.flags & BBCP_OPT_NO_REUSE)) {
@@ -729,10 +735,10 @@ static int intake_guard(bbcp_handle *h)
     return BBCP_OK;
 }
 
-// internal literals are 2*var+neg in 32 bits with bit 31 reserved (TRAIL_CLOSED, placeholder values): variables stop
-// below 2^30. The reference reports STATUS_INDEX_TOO_NARROW for what its index type cannot hold (TopiConflictAnalysis.cc:67-71)
-static inline bool lit_in_range(int32_t l) { return l > -(1 << 30) && l < (1 << 30); }
-static const char *const LIT_RANGE_MSG = "literal out of range (|literal| must be below 2^30)";
+// internal literals are 2*var+neg in 30 bits (the two bits above are the trail-entry mode, bbcp_device.cuh): variables stop
+// below 2^29. The reference reports STATUS_INDEX_TOO_NARROW for what its index type cannot hold (TopiConflictAnalysis.cc:67-71)
+static inline bool lit_in_range(int32_t l) { return l > -(1 << 29) && l < (1 << 29); }
+static const char *const LIT_RANGE_MSG = "literal out of range (|literal| must be below 2^29)";
 
 int bbcp_add(bbcp_handle *h, int32_t lit)
 {
@@ -993,6 +999,7 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
     memset(&tot, 0, sizeof(tot));
     uint64_t base = 0;
     int ret = BBCP_OK;
+    bool any_stored = false;
     for (uint64_t k = 0; k < nchunks && ret == BBCP_OK; ++k) {
         const uint64_t lo = k * csize, cnt = std::min(csize, n - lo);
         h->rb = (int)(k & 1);
@@ -1006,7 +1013,11 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
         // the batch is complete (run_batch synchronises): its results leave on the output stream while the next
         // chunk computes into the other result set
         cudaMemcpyAsync(flag_out + lo, h->rs[h->rb].flag.p, cnt, cudaMemcpyDeviceToHost, h->s_out);
-        cudaMemcpyAsync(static_cast<char *>(off_out) + lo * osz, h->rs[h->rb].off.p, cnt * osz, cudaMemcpyDeviceToHost, h->s_out);
+        // compact read-back: while no chunk has stored a set, every offset is zero and nothing but the flags travels
+        const bool compact = (opts.flags & BBCP_OPT_COMPACT_SELF) != 0;
+        if (compact && bi.n_implied && !any_stored && lo) memset(off_out, 0, lo * osz);   // the chunks skipped so far
+        any_stored |= bi.n_implied != 0;
+        if (!compact || any_stored) cudaMemcpyAsync(static_cast<char *>(off_out) + lo * osz, h->rs[h->rb].off.p, cnt * osz, cudaMemcpyDeviceToHost, h->s_out);
         if (bi.n_implied) cudaMemcpyAsync(impl_out + base, h->rs[h->rb].impl.p, bi.n_implied * 4, cudaMemcpyDeviceToHost, h->s_out);
         cudaEventRecord(h->ev_out[k & 1], h->s_out);
         base += bi.n_implied;
@@ -1028,6 +1039,7 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
         if (base > 0xffffffffull) return h->fail(BBCP_ERR_ARG, "BBCP_OPT_OFF32: more than 2^32-1 implied literals");
         static_cast<uint32_t *>(off_out)[n] = (uint32_t)base;
     } else static_cast<uint64_t *>(off_out)[n] = base;
+    (void)any_stored;
     if (info) *info = tot;
     return BBCP_OK;
 }
@@ -1061,9 +1073,12 @@ int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds
     if (h->status == BBCP_OK && !h->finalized) bbcp_finalize(h);
     int rc = need_final(h);
     if (rc) return rc;
+    // BBCP_FIXPOINT=rebuild: the round-1 loop (re-finalize = host rebuild of the database after every round)
+    static const bool rebuild = getenv("BBCP_FIXPOINT") && !strcmp(getenv("BBCP_FIXPOINT"), "rebuild");
     uint64_t total_units = 0;
     uint32_t round = 0;
     std::vector<uint32_t> unit;
+    std::vector<int32_t> cube, lits;
     for (; max_rounds == 0 || round < max_rounds; ++round) {
         bbcp_opts o;
         memset(&o, 0, sizeof(o));   // flags and bitmaps only
@@ -1071,22 +1086,50 @@ int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds
         if ((rc = bbcp_probe_all(h, &o, nullptr)) != BBCP_OK) return rc;
         unit.assign(bbcp_bitmap_words(h), 0);
         if ((rc = bbcp_fetch_bitmaps(h, nullptr, unit.data())) != BBCP_OK) return rc;
-        uint64_t found = 0;
+        cube.clear();
         for (size_t w = 0; w < unit.size(); ++w)
             for (uint32_t m = unit[w]; m; m &= m - 1) {
                 const uint32_t il = (uint32_t)(w * 32) + (uint32_t)__builtin_ctz(m);
-                const int32_t ext[2] = {(il & 1) ? -(int32_t)(il >> 1) : (int32_t)(il >> 1), 0};
-                h->db.add_words(ext, 2);
-                ++found;
+                cube.push_back((il & 1) ? -(int32_t)(il >> 1) : (int32_t)(il >> 1));
             }
         if (rounds_out) *rounds_out = round + 1;
-        if (!found) break;
-        total_units += found;
+        if (cube.empty()) break;
+        total_units += cube.size();
         if (units_out) *units_out = total_units;
-        h->finalized = false;
-        h->prepared = false;
-        rc = bbcp_finalize(h);
-        if (rc != BBCP_OK) return rc;   // BBCP_CONTRADICTORY: x and not-x both failed, or the units propagate to a conflict
+        // the units join the clause stream either way, so that a later bbcp_finalize rebuilds the simplified database
+        try {
+            for (int32_t l : cube) { const int32_t c[2] = {l, 0}; h->db.add_words(c, 2); }
+        } catch (const std::bad_alloc &) { return h->fail(BBCP_ERR_ALLOC, "host allocation failed (unit clauses)"); }
+        if (rebuild) {
+            h->finalized = false;
+            h->prepared = false;
+            rc = bbcp_finalize(h);
+            if (rc != BBCP_OK) return rc;   // BBCP_CONTRADICTORY: x and not-x both failed, or the units propagate to a conflict
+            continue;
+        }
+        // ON THE DEVICE: the new units are one cube; its fixpoint is what level 0 gains (Topi.cc:1311-1333: Assign at level
+        // 0 + BCP). The rows are NOT rebuilt: the gained literals are marked in litinfo and every later look-up of an
+        // unassigned literal consults it (value_of), which is what dropping the satisfied clauses and the false literals
+        // (SimplifyIfRequired, TopiCompression.cc:509-640) would achieve. bbcp_finalize re-simplifies for real.
+        const uint64_t off[2] = {0, cube.size()};
+        bbcp_batch_info bi;
+        if ((rc = bbcp_propagate_batch(h, cube.data(), off, 1, nullptr, &bi)) != BBCP_OK) return rc;
+        uint8_t flag = 0;
+        if (bbcp_fetch_flags(h, &flag)) return h->status;
+        if (flag == BBCP_FLAG_CONFLICT || flag == BBCP_FLAG_FALSE_L0) { ++h->db_version; return h->fail(BBCP_CONTRADICTORY, "the failed-literal units refute the instance at level 0"); }
+        if (bi.n_implied) {
+            uint64_t ioff[2];
+            lits.resize(bi.n_implied);
+            if (bbcp_fetch_implied(h, ioff, lits.data())) return h->status;
+            for (int32_t l : lits) {
+                const uint32_t v = (uint32_t)(l < 0 ? -l : l);
+                h->db.varinfo[v] = (h->db.varinfo[v] & ~3) | (l < 0 ? 2 : 1);
+            }
+            launch_mark_level0(h->d_litinfo.as<uint8_t>(), h->rs[h->rb].impl.as<int32_t>(), bi.n_implied, h->stream);
+            if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "level-0 marking")) return BBCP_ERR_CUDA;
+            h->l0_dirty = true;
+            h->have_batch = false;
+        }
     }
     return BBCP_OK;
 }
@@ -1121,6 +1164,36 @@ int bbcp_probe_products(bbcp_handle *h, uint32_t *necessary, uint64_t *n_necessa
     }
     if (n_necessary) *n_necessary = hc[0];
     if (n_equiv) *n_equiv = hc[1];   // may exceed equiv_cap: call again with a larger buffer
+    return BBCP_OK;
+}
+
+// The static no-missed-implication check (TopiWL.cc:330-442) over the last batch's fixpoints, on the device.
+int bbcp_check_fixpoints(bbcp_handle *h, uint64_t first_item, uint64_t count, uint64_t stride, uint64_t *violations, uint64_t *clauses_checked, uint64_t *items_checked)
+{
+    if (violations) *violations = 0;
+    if (clauses_checked) *clauses_checked = 0;
+    if (items_checked) *items_checked = 0;
+    if (!h || !h->have_batch) return h ? h->fail(BBCP_ERR_STATE, "no batch results") : BBCP_ERR_ARG;
+    if (!h->last_implied) return h->fail(BBCP_ERR_STATE, "bbcp_check_fixpoints needs a batch run with implied sets");
+    if (stride == 0) stride = 1;
+    if (first_item >= h->last_n || count == 0) return BBCP_OK;
+    count = std::min<uint64_t>(count, (h->last_n - first_item + stride - 1) / stride);
+    cudaSetDevice(h->device);
+    const DbView dbv = db_view(h);
+    const int blocks = (int)std::min<uint64_t>(count, (uint64_t)h->sm_count * 4);
+    // scratch: one dense assignment per CTA + three counters (the products buffer doubles as scratch)
+    const size_t words = (size_t)blocks * dbv.nvars_words16;
+    if (!h->d_products.reserve(words * 4 + 32)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (fixpoint checker)");
+    cudaMemsetAsync(h->d_products.p, 0, words * 4 + 32, h->stream);
+    unsigned long long *out = reinterpret_cast<unsigned long long *>(h->d_products.as<uint32_t>() + ((words + 1) & ~(size_t)1));
+    launch_check_fixpoints(dbv, h->last_off32, h->rs[h->rb].flag.as<uint8_t>(), h->rs[h->rb].off.p, h->rs[h->rb].impl.as<int32_t>(), first_item, count, stride,
+                           h->d_products.as<uint32_t>(), blocks, out, h->stream);
+    unsigned long long res[3] = {0, 0, 0};
+    cudaMemcpyAsync(res, out, 24, cudaMemcpyDeviceToHost, h->stream);
+    if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "fixpoint checker")) return BBCP_ERR_CUDA;
+    if (violations) *violations = res[0];
+    if (clauses_checked) *clauses_checked = res[1];
+    if (items_checked) *items_checked = res[2];
     return BBCP_OK;
 }
 

@@ -25,6 +25,9 @@ struct DbView {
     int32_t max_var;
     uint32_t n_slots, n_arena_units;   // extents (bounds checks of debug builds: -DBBCP_CHECKS)
     uint32_t nvars_words16;    // words of a 2-bit-per-var dense assignment: ceil((max_var+1)/16)
+    // 1: literals became true / false at level 0 AFTER the rows were built (unit-feedback rounds, bbcp_probe_to_fixpoint): the
+    // rows still hold them, so a literal the probe has not assigned is also looked up in litinfo (value_of)
+    uint32_t l0_dirty;
 };
 
 constexpr uint8_t LI_TRUE_L0 = 1, LI_FALSE_L0 = 2, LI_MAPPED = 4, LI_HAS_BIN = 8, LI_NONEMPTY = 16;
@@ -83,19 +86,33 @@ struct BatchView {
 constexpr uint32_t OPT_IMPLIED = 1u;
 constexpr uint32_t OPT_NO_LEN_PRUNE = 2u;
 constexpr uint32_t OPT_OFF32 = 4u;
+constexpr uint32_t OPT_COMPACT_SELF = 128u;
+constexpr uint8_t FLAG_SELF = 0x80;         // OPT_COMPACT_SELF: flag OK + "the implied set is the probe's own literal" (not stored)
 constexpr uint8_t FLAG_OK = 0, FLAG_CONFLICT = 1, FLAG_TRIVIAL_L0 = 2, FLAG_FALSE_L0 = 3, FLAG_UNMAPPED = 4;
 constexpr uint8_t FLAG_OVERFLOW = 250;      // internal: outgrew the first tier, queued for the second (global hash state)
 constexpr uint8_t FLAG_OVERFLOW2 = 249;     // internal: outgrew the second tier, queued for the third
 constexpr uint8_t FLAG_OVERFLOW3 = 248;     // internal: outgrew the third tier, queued for the last (dense state, any size)
 constexpr uint8_t FLAG_OVERFLOW_LAST = 248;
 constexpr uint8_t FLAG_QUEUED = 255;        // internal: written by the triage for items that wait for the first tier
-constexpr uint32_t TRAIL_CLOSED = 0x80000000u;  // trail entry mark: the literal came in with a finished closure, so every
-                                                // binary clause of its row is already satisfied (only longer clauses are re-examined)
+// Trail entries carry a 2-bit mode above the 30-bit literal (variables stop below 2^29):
+//   0            an implication found by a row scan: its whole row is walked when it is dequeued;
+//   TRAIL_CLOSED the literal came in with a finished closure, so every binary clause of its row is already satisfied:
+//                only the ternary / long part of the row is walked;
+//   TRAIL_SKIP   it came in with a finished closure that was LARGER than the state it was entered into: its row is not
+//                walked at all -- instead the literals that were there before get a second walk (TRAIL_RESCAN);
+//   TRAIL_RESCAN a second walk (ternary / long part) of a literal that is already on the trail: NOT a member of the
+//                implied set, not looked up for adoption.
+// See expand_closures in bbcp_propagate.cuh for why that is complete.
+constexpr uint32_t TRAIL_LIT = 0x3fffffffu, TRAIL_RESCAN = 0x40000000u, TRAIL_CLOSED = 0x80000000u, TRAIL_SKIP = 0xc0000000u;
 constexpr uint8_t FLAG_OUT_OVERFLOW = 251;  // internal: implied-literal buffer full, re-run in a later launch
+
+// last tier: the trail holds every variable once plus the second-walk entries (TRAIL_RESCAN: each SKIP adoption at least
+// quadruples the member count, so they stay below a third of the members)
+__host__ __device__ inline uint32_t big_trail_words(uint32_t max_var) { return max_var + 1u + (max_var + 1u) / 2u + 64u; }
 
 struct LargeState {
     uint32_t *bits;    // [slabs][nvars_words16] 2 bits per var, all zero between probes
-    uint32_t *trail;   // [slabs][max_var + 1]
+    uint32_t *trail;   // [slabs][big_trail_words(max_var)]
 };
 
 void launch_triage(const BatchView &b, const DbView &db, int sm_count, cudaStream_t s);
@@ -130,6 +147,10 @@ struct MergeArgs {
 };
 constexpr int MERGE_CTRL_WORDS = 256;      // control words behind the two bitmaps, see merge_signal in bbcp_kernels.cu
 constexpr int MERGE_CTRL_FINISHED = 64, MERGE_CTRL_ERROR = 65, MERGE_CTRL_DONE = 128;
+void launch_check_fixpoints(const DbView &db, bool off32, const uint8_t *flag, const void *off, const int32_t *impl, uint64_t first, uint64_t count, uint64_t stride,
+                            uint32_t *scratch, int blocks, unsigned long long *out, cudaStream_t s);
+// marks the n external literals of `lits` true at level 0 in litinfo (and their negations false)
+void launch_mark_level0(uint8_t *litinfo, const int32_t *lits, uint64_t n, cudaStream_t s);
 void launch_merge(const MergeArgs &m, int sm_count, cudaStream_t s);
 void launch_merge_drain(const MergeArgs &m, cudaStream_t s);
 constexpr int SMALL_THREADS = 128;  // first tier: SMALL_THREADS / W probes in flight per CTA (W lanes per probe)

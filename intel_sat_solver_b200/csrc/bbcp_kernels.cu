@@ -83,7 +83,7 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
         if (b.opts & OPT_IMPLIED) {
             uint32_t n2 = 1;
             while (n2 < tail) n2 <<= 1;
-            for (uint32_t i = lane; i < n2; i += G::width) st.trail[i] = i < tail ? (st.trail[i] & ~TRAIL_CLOSED) : 0xffffffffu;
+            for (uint32_t i = lane; i < n2; i += G::width) st.trail[i] = i < tail ? (st.trail[i] & TRAIL_LIT) : 0xffffffffu;
             G::sync();
             if (tail > 1) bitonic_sort<G>(st.trail, n2);
             off = out_alloc<G>(b, tail);
@@ -129,14 +129,15 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
         if (!(li & LI_MAPPED)) q = FLAG_UNMAPPED;
         else if (li & LI_FALSE_L0) q = FLAG_FALSE_L0;
         else if (li & LI_TRUE_L0) q = FLAG_TRIVIAL_L0;
-        else if (prune && !(li & LI_HAS_BIN)) q = FLAG_OK | TQ_SELF | ((li & LI_NONEMPTY) ? TQ_REF : 0u);  // implies exactly itself
+        else if (prune && !(li & LI_HAS_BIN)) q = ((b.opts & OPT_COMPACT_SELF) ? FLAG_SELF : FLAG_OK) | TQ_SELF | ((li & LI_NONEMPTY) ? TQ_REF : 0u);  // implies exactly itself
         else q = 0xffu | TQ_DEEP;
         s_lut[li] = (uint16_t)q;
     }
     // housekeeping: the counter block of the NEXT launch sequence starts from zero (no memset nodes on the stream)
     if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < b.zero_words; i += 256) b.zero_next[i] = 0ull;
     __syncthreads();
-    const uint32_t selflen = (b.opts & OPT_IMPLIED) ? (LEN_SELF | 1u) : 0u;
+    // (compact read-back: a self-implying probe is told by a flag bit, its one-literal set is not materialised)
+    const uint32_t selflen = (b.opts & OPT_IMPLIED) && !(b.opts & OPT_COMPACT_SELF) ? (LEN_SELF | 1u) : 0u;
     const uint32_t n = (uint32_t)b.n;   // run_batch refuses n >= 2^31
     uint32_t n_ok = 0, n_skip = 0, n_ref = 0;
     const uint32_t stride = gridDim.x * 256u * TRIAGE_ITEMS;
@@ -398,11 +399,20 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
             } else {
                 flag = FLAG_OK;
                 if (b.opts & OPT_IMPLIED) {
-                    off = out_alloc<G>(b, tail);
+                    const uint32_t nmem = tl.members();
+                    off = out_alloc<G>(b, nmem);
                     if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
                     else {
-                        len = tail;
-                        for (uint32_t i = lane; i < tail; i += W) b.out_lits[off + i] = (int32_t)(st.tget(i) & ~TRAIL_CLOSED);   // internal literals, trail order
+                        // internal literals, trail order, without the second-walk entries
+                        len = nmem;
+                        uint32_t w = 0;
+                        for (uint32_t base = 0; base < tail; base += W) {
+                            const uint32_t ent = base + lane < tail ? st.tget(base + lane) : TRAIL_RESCAN;
+                            const bool mem = (ent & TRAIL_SKIP) != TRAIL_RESCAN;
+                            const unsigned mm = G::ballot(mem);
+                            if (mem) b.out_lits[off + w + __popc(mm & G::lt())] = (int32_t)(ent & TRAIL_LIT);
+                            w += __popc(mm);
+                        }
                         if (lane == 0) b.sort_list[atomicAdd(b.sort_count, 1u)] = (uint32_t)item;
                         wc.bytes += 4ull * tail;
                     }
@@ -416,7 +426,7 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
         if (lane == 0 && flag != FLAG_OVERFLOW2) atomicAdd(&b.counters[C_MID], 1ull);
         wc.n_ok += flag == FLAG_OK;
         wc.n_conf += flag == FLAG_CONFLICT;
-        if (flag != FLAG_OVERFLOW2) wc.end_item(flag == FLAG_OK, tail, true);
+        if (flag != FLAG_OVERFLOW2) wc.end_item(flag == FLAG_OK, tl.members(), true);
         G::sync();
     }
     wc.template flush<G>(b.counters);
@@ -507,8 +517,10 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
                         while (m && !ra) {
                             const int k = __ffs(m) - 1;
                             m &= m - 1;
-                            const uint32_t n = G::shfl(len, k);
-                            ra = closure_adopt<G>(b, st, tl, G::shfl(off, k), n, 0, 32);
+                            const uint32_t n = G::shfl(len, k), t0 = vctl[0];
+                            const bool skip = n >= 4u * t0 && 2ull * t0 + n <= st.cap;     // SKIP mode, see expand_closures
+                            ra = closure_adopt<G>(b, st, tl, G::shfl(off, k), n, 0, 32, skip ? TRAIL_SKIP : TRAIL_CLOSED);
+                            if (!ra && skip) ra = tl.template append_rescan<G>(st, t0, hcur);
                             if (!ra) { ++wc.adopted; wc.adopt_lits += n; wc.bytes += 4ull * n; }
                         }
                         if (ra) break;
@@ -547,11 +559,20 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
             }
             __syncthreads();
             const uint32_t na = min(s_na, ADOPT_MAX);
-            for (uint32_t a = 0; a < na && !tl.aborted(); ++a) {
+            // the largest set of the level may go in SKIP mode (expand_closures): its literals get no walk, the members
+            // that were there before and will not be walked any more get a second one instead
+            uint32_t best = 0;
+            for (uint32_t a = 1; a < na; ++a) if (s_len[a] > s_len[best]) best = a;
+            const uint32_t t0 = vctl[0];
+            const bool skip = na && !((vctl[1] | vctl[2]) != 0) && s_len[best] >= 4u * t0 && 2ull * t0 + s_len[best] <= st.cap;
+            __syncthreads();   // everybody has t0 before anyone appends
+            if (skip && tl.template append_rescan<G>(st, t0, head, warp * 32, nwarps * 32)) { /* overflow latched */ }
+            for (uint32_t k = 0; k < na && !tl.aborted(); ++k) {
+                const uint32_t a = k == 0 ? best : (k == best ? 0 : k);    // the largest first
                 const uint32_t n = s_len[a];
                 // successive sets start at successive warps, so that many short sets spread over the CTA as well
-                if (closure_adopt<G>(b, st, tl, s_src[a], n, ((warp + nwarps - a % nwarps) % nwarps) * 32, nwarps * 32)) break;
-                if (warp == (int)(a % nwarps) && lane == 0) { ++wc.adopted; wc.adopt_lits += n; wc.bytes += 4ull * n; }
+                if (closure_adopt<G>(b, st, tl, s_src[a], n, ((warp + nwarps - k % nwarps) % nwarps) * 32, nwarps * 32, skip && k == 0 ? TRAIL_SKIP : TRAIL_CLOSED)) break;
+                if (warp == (int)(k % nwarps) && lane == 0) { ++wc.adopted; wc.adopt_lits += n; wc.bytes += 4ull * n; }
             }
             // (CTA-uniform: a warp that got past this point may latch a conflict before a slower thread has looked)
             if (__syncthreads_or((vctl[1] | vctl[2]) != 0)) continue;   // the loop head sees the latch and stops
@@ -570,7 +591,7 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
 __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const BatchView b, const LargeState ls, const int from_huge)
 {
     using G = Grp<32>;
-    __shared__ uint32_t ctl[8];      // 0 tail, 1 conflict, 2 overflow, 3 load result, 4 ticket, 5 vmin, 6 vmax
+    __shared__ uint32_t ctl[12];     // 0 tail, 1 conflict, 2 overflow, 3 load result, 4 ticket, 5 vmin, 6 vmax / whole-CTA level, 7 head, 8 second-walk entries
     __shared__ unsigned long long s_off;
     __shared__ uint32_t s_warp[BIG_THREADS / 32 + 1];
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -583,15 +604,15 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
 
     GmemState gs;
     gs.bits = ls.bits + (size_t)blockIdx.x * db.nvars_words16;
-    gs.trail = ls.trail + (size_t)blockIdx.x * ((size_t)db.max_var + 1);
-    gs.cap = (uint32_t)db.max_var + 1;
+    gs.cap = big_trail_words((uint32_t)db.max_var);
+    gs.trail = ls.trail + (size_t)blockIdx.x * gs.cap;
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
     WorkCounters wc;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
             ctl[4] = atomicAdd(ticket, 1u);
-            ctl[0] = ctl[1] = ctl[2] = 0;
+            ctl[0] = ctl[1] = ctl[2] = ctl[8] = 0;
             ctl[3] = 0xff;
             ctl[5] = 0xffffffffu;
             ctl[6] = 0;
@@ -612,6 +633,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
         if (f == 0xff) block_propagate(db, b, gs, ctl, prune, 4, wc);
         __syncthreads();
         const uint32_t tail = min(ctl[0], gs.cap);
+        const uint32_t nmem = tail - min(ctl[8], tail);     // members of the implied set (the trail also holds second-walk entries)
         const bool conflict = ctl[1] != 0 || f == FLAG_CONFLICT;
         uint8_t flag = (uint8_t)f;
         uint32_t len = 0;
@@ -624,18 +646,18 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
                 flag = FLAG_OK;
                 if (b.opts & OPT_IMPLIED) {
                     if (threadIdx.x == 0) {
-                        const unsigned long long o = atomicAdd(b.out_cursor, (unsigned long long)tail);
-                        s_off = o + tail <= b.out_cap ? o : ~0ull;
+                        const unsigned long long o = atomicAdd(b.out_cursor, (unsigned long long)nmem);
+                        s_off = o + nmem <= b.out_cap ? o : ~0ull;
                     }
                     __syncthreads();
                     off = s_off;
                     if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
                     else {
                         // ordered emission: sweep the dense assignment between the smallest and largest assigned var
-                        len = tail;
+                        len = nmem;
                         uint32_t vmin = 0xffffffffu, vmax = 0;
                         for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
-                            const uint32_t var = (gs.tget(i) & ~TRAIL_CLOSED) >> 1;
+                            const uint32_t var = (gs.tget(i) & TRAIL_LIT) >> 1;
                             vmin = min(vmin, var);
                             vmax = max(vmax, var);
                         }
@@ -683,7 +705,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
         __syncthreads();
         // leave the state empty for the next probe
         for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
-            const uint32_t var = (gs.tget(i) & ~TRAIL_CLOSED) >> 1;
+            const uint32_t var = (gs.tget(i) & TRAIL_LIT) >> 1;
             atomicAnd(&gs.bits[var >> 4], ~(3u << ((var & 15u) * 2u)));
         }
         if (b.reuse) __threadfence();   // every thread: its part of the set is out (publish_result, CTA-wide)
@@ -699,7 +721,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
             wc.n_skip += flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED;
         }
         // every warp settles its own share of the row counters; the trail length is counted once
-        wc.end_item(flag == FLAG_OK, threadIdx.x == 0 && flag <= FLAG_CONFLICT ? tail : 0u, threadIdx.x == 0);
+        wc.end_item(flag == FLAG_OK, threadIdx.x == 0 && flag <= FLAG_CONFLICT ? nmem : 0u, threadIdx.x == 0);
     }
     wc.flush<G>(b.counters);
 }
@@ -735,7 +757,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_block(const DbView db, const Bat
 {
     using G = Grp<32>;
     extern __shared__ uint32_t s_hash[];
-    __shared__ uint32_t ctl[8];      // 0 tail, 1 conflict, 2 overflow, 3 load result, 4 ticket
+    __shared__ uint32_t ctl[12];     // 0 tail, 1 conflict, 2 overflow, 3 load result, 4 ticket, 6 whole-CTA level, 7 head, 8 second-walk entries
     __shared__ unsigned long long s_off;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t *list = cls ? b.big_list : b.mid_list;
@@ -759,7 +781,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_block(const DbView db, const Bat
                 __syncthreads();
         if (threadIdx.x == 0) {
             ctl[4] = atomicAdd(ticket, 1u);
-            ctl[0] = ctl[1] = ctl[2] = ctl[6] = 0;
+            ctl[0] = ctl[1] = ctl[2] = ctl[6] = ctl[8] = 0;
             ctl[3] = 0xff;
         }
         __syncthreads();
@@ -780,6 +802,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_block(const DbView db, const Bat
         const bool overflow = ctl[2] != 0 || f == FLAG_OVERFLOW;
         const bool conflict = !overflow && (ctl[1] != 0 || f == FLAG_CONFLICT);
         const uint32_t tail = min(ctl[0], cap);
+        const uint32_t nmem = tail - min(ctl[8], tail);     // members of the implied set (the trail also holds second-walk entries)
         uint8_t flag = (uint8_t)f;
         uint32_t len = 0;
         unsigned long long off = 0;
@@ -795,18 +818,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_block(const DbView db, const Bat
                 // the table has done its work: sort the trail in its place
                 uint32_t n2 = 1;
                 while (n2 < tail) n2 <<= 1;
-                for (uint32_t i = threadIdx.x; i < n2; i += THREADS) s_hash[i] = i < tail ? (st.tget(i) & ~TRAIL_CLOSED) : 0xffffffffu;
+                for (uint32_t i = threadIdx.x; i < n2; i += THREADS) {
+                    const uint32_t ent = i < tail ? st.tget(i) : TRAIL_RESCAN;
+                    s_hash[i] = (ent & TRAIL_SKIP) != TRAIL_RESCAN ? (ent & TRAIL_LIT) : 0xffffffffu;   // second-walk entries sort behind the set
+                }
                 if (threadIdx.x == 0) {
-                    const unsigned long long o = atomicAdd(b.out_cursor, (unsigned long long)tail);
-                    s_off = o + tail <= b.out_cap ? o : ~0ull;
+                    const unsigned long long o = atomicAdd(b.out_cursor, (unsigned long long)nmem);
+                    s_off = o + nmem <= b.out_cap ? o : ~0ull;
                 }
                 __syncthreads();
                 if (tail > 1) block_bitonic_sort<THREADS>(s_hash, n2);
                 off = s_off;
                 if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
                 else {
-                    len = tail;
-                    for (uint32_t i = threadIdx.x; i < tail; i += THREADS) b.out_lits[off + i] = (int32_t)s_hash[i];
+                    len = nmem;
+                    for (uint32_t i = threadIdx.x; i < nmem; i += THREADS) b.out_lits[off + i] = (int32_t)s_hash[i];
                     if (threadIdx.x == 0) wc.bytes += 8ull * tail;
                 }
             }
@@ -826,7 +852,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_block(const DbView db, const Bat
             wc.n_conf += flag == FLAG_CONFLICT;
             wc.n_skip += flag >= FLAG_TRIVIAL_L0 && flag <= FLAG_UNMAPPED;
         }
-        if (!overflow) wc.end_item(flag == FLAG_OK, threadIdx.x == 0 && flag <= FLAG_CONFLICT ? tail : 0u, threadIdx.x == 0);
+        if (!overflow) wc.end_item(flag == FLAG_OK, threadIdx.x == 0 && flag <= FLAG_CONFLICT ? nmem : 0u, threadIdx.x == 0);
     }
     wc.flush<G>(b.counters);
 }
@@ -1217,6 +1243,92 @@ __global__ void __launch_bounds__(256) k_products(const uint8_t *__restrict__ fl
     }
 }
 
+// ---------------------------------------------------------------- fixpoint checker (diagnostic)
+// The static analogue of the reference's WLAssertNoMissedImplications (TopiWL.cc:330-442): for the items of the last
+// batch that reached a fixpoint, walk EVERY row of the database under the item's implied set (+ level 0) and count the
+// clauses that are not satisfied and have fewer than two unassigned literals -- a missed implication or a missed
+// conflict. One CTA per item, the assignment as a dense 2-bit-per-variable scratch bitmap. O(database) per item: a test
+// and debugging aid (bbcp_check_fixpoints), not part of any batch.
+template <bool OFF32>
+__global__ void __launch_bounds__(256) k_check_fixpoints(const DbView db, const uint8_t *__restrict__ flag, const void *__restrict__ off_, const int32_t *__restrict__ impl,
+                                                        const uint64_t first, const uint64_t count, const uint64_t stride, uint32_t *__restrict__ scratch,
+                                                        unsigned long long *__restrict__ out)
+{
+    uint32_t *bits = scratch + (size_t)blockIdx.x * db.nvars_words16;
+    const uint32_t nl = 2u * ((uint32_t)db.max_var + 1u);
+    auto val = [&](uint32_t lit) -> int {      // 0 unassigned, 1 true, 2 false
+        const uint32_t var = lit >> 1;
+        const uint32_t o = (bits[var >> 4] >> ((var & 15u) * 2u)) & 3u;
+        if (o) return (o == 1u) == ((lit & 1u) == 0u) ? 1 : 2;
+        const uint8_t li = db.litinfo[lit];
+        return (li & LI_TRUE_L0) ? 1 : (li & LI_FALSE_L0) ? 2 : 0;
+    };
+    for (uint64_t k = blockIdx.x; k < count; k += gridDim.x) {
+        const uint64_t item = first + k * stride;
+        if (flag[item] != FLAG_OK) continue;
+        uint64_t o0, o1;
+        if (OFF32) { o0 = ((const uint32_t *)off_)[item]; o1 = ((const uint32_t *)off_)[item + 1]; }
+        else { o0 = ((const uint64_t *)off_)[item]; o1 = ((const uint64_t *)off_)[item + 1]; }
+        for (uint64_t i = o0 + threadIdx.x; i < o1; i += 256) {
+            const int32_t l = impl[i];
+            const uint32_t var = (uint32_t)(l < 0 ? -l : l);
+            atomicOr(&bits[var >> 4], (l < 0 ? 2u : 1u) << ((var & 15u) * 2u));
+        }
+        __syncthreads();
+        unsigned long long bad = 0, seen = 0;
+        for (uint32_t l = 2 + threadIdx.x; l < nl; l += 256) {
+            const uint4 hd = db.hdr[l];
+            if (!(hd.y | hd.z | hd.w)) continue;
+            const int vl = val(l);
+            const uint2 *row = db.slots + hd.x;
+            for (uint32_t j = 0; j < hd.y; ++j) {                         // binary clauses (l, o)
+                const uint32_t o = (j & 1) ? row[j / 2].y : row[j / 2].x;
+                const int vo = val(o);
+                ++seen;
+                bad += vl != 1 && vo != 1 && (vl == 2 || vo == 2);
+            }
+            row += (hd.y + 1) / 2;
+            for (uint32_t j = 0; j < hd.z; ++j) {                         // ternary clauses (l, a, b)
+                const int va = val(row[j].x), vb = val(row[j].y);
+                ++seen;
+                const int nfree = (vl == 0) + (va == 0) + (vb == 0);
+                bad += vl != 1 && va != 1 && vb != 1 && nfree < 2;
+            }
+            row += hd.z;
+            for (uint32_t j = 0; j < hd.w; ++j) {                         // long clauses from the arena
+                const uint32_t *c = reinterpret_cast<const uint32_t *>(db.arena + row[j].y);
+                const uint32_t size = c[0];
+                int nfree = 0;
+                bool sat = false;
+                for (uint32_t q = 1; q <= size; ++q) { const int v = val(c[q]); sat |= v == 1; nfree += v == 0; }
+                ++seen;
+                bad += !sat && nfree < 2;
+            }
+        }
+        if (bad) atomicAdd(&out[0], bad);
+        atomicAdd(&out[1], seen);
+        if (threadIdx.x == 0) atomicAdd(&out[2], 1ull);
+        __syncthreads();
+        for (uint64_t i = o0 + threadIdx.x; i < o1; i += 256) {
+            const int32_t l = impl[i];
+            const uint32_t var = (uint32_t)(l < 0 ? -l : l);
+            atomicAnd(&bits[var >> 4], ~(3u << ((var & 15u) * 2u)));
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- unit feedback on the device (survey "next" row N2)
+__global__ void __launch_bounds__(256) k_mark_level0(uint8_t *__restrict__ litinfo, const int32_t *__restrict__ lits, const uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
+        const int32_t l = lits[i];
+        const uint32_t il = 2u * (uint32_t)(l < 0 ? -l : l) + (l < 0);
+        litinfo[il] = (litinfo[il] & ~(LI_TRUE_L0 | LI_FALSE_L0)) | LI_TRUE_L0;          // one byte per literal, one literal per variable: no races
+        litinfo[il ^ 1u] = (litinfo[il ^ 1u] & ~(LI_TRUE_L0 | LI_FALSE_L0)) | LI_FALSE_L0;
+    }
+}
+
 // ---------------------------------------------------------------- probe schedule for closure reuse, built on the device
 // height(p) = length of the longest chain of binary implications that starts at p (p -> q when the clause (not-p or q)
 // exists), capped at 255: round r of the relaxation below holds min(height, r), so an acyclic implication graph is done
@@ -1444,6 +1556,18 @@ bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant
     }
     if (giant_sets_possible) k_gather_long<<<max_blocks, 256, 0, s>>>(b);
     return cudaPeekAtLastError() == cudaSuccess;
+}
+
+void launch_check_fixpoints(const DbView &db, bool off32, const uint8_t *flag, const void *off, const int32_t *impl, uint64_t first, uint64_t count, uint64_t stride,
+                            uint32_t *scratch, int blocks, unsigned long long *out, cudaStream_t s)
+{
+    if (off32) k_check_fixpoints<true><<<blocks, 256, 0, s>>>(db, flag, off, impl, first, count, stride, scratch, out);
+    else k_check_fixpoints<false><<<blocks, 256, 0, s>>>(db, flag, off, impl, first, count, stride, scratch, out);
+}
+
+void launch_mark_level0(uint8_t *litinfo, const int32_t *lits, uint64_t n, cudaStream_t s)
+{
+    if (n) k_mark_level0<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, s>>>(litinfo, lits, n);
 }
 
 void launch_merge_drain(const MergeArgs &m, cudaStream_t s) { k_merge_drain<<<1, 32, 0, s>>>(m); }

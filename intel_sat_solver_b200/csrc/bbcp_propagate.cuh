@@ -163,7 +163,7 @@ struct GhashState {
         const uint32_t hs = 1u << log_hs, mask = hs - 1u;
         if (tail * 8u >= hs) { wipe<G>(); return; }
         for (uint32_t i = G::lane(); i < tail; i += G::width) {
-            const uint32_t lit = __ldcg(&trail[i]) & ~TRAIL_CLOSED;
+            const uint32_t lit = __ldcg(&trail[i]) & TRAIL_LIT;
             uint32_t s = h(lit >> 1);
             while (__ldcg(&hash[s]) != lit) s = (s + 1) & mask;
             __stcg(&trail[i], s);
@@ -184,7 +184,7 @@ struct GhashState {
         if (log_hs >= log_max || 2u * tail <= (1u << log_hs)) return;
         wipe<G>();
         while (log_hs < log_max && 2u * tail > (1u << log_hs)) log_hs = min(log_hs + 2u, log_max);
-        for (uint32_t i = G::lane(); i < tail; i += G::width) { uint32_t slot; insert(__ldcg(&trail[i]) & ~TRAIL_CLOSED, slot); }
+        for (uint32_t i = G::lane(); i < tail; i += G::width) { uint32_t slot; insert(__ldcg(&trail[i]) & TRAIL_LIT, slot); }   // (a TRAIL_RESCAN duplicate finds its literal present)
         G::sync();
     }
     // after cleanup / wipe: the next probe starts small again
@@ -306,15 +306,17 @@ struct WorkCounters {
 // probe, the tail and the conflict / overflow latches live in shared memory.
 struct GroupTail {
     uint32_t tail;
+    uint32_t nres = 0;   // TRAIL_RESCAN entries on the trail (not members of the implied set)
     __device__ __forceinline__ uint32_t get() const { return tail; }
+    __device__ __forceinline__ uint32_t members() const { return tail - nres; }
     __device__ __forceinline__ bool aborted() const { return false; }
     template <class G> __device__ __forceinline__ void latch_conflict() {}
-    template <class G> __device__ __forceinline__ void drop() { tail = 0; }   // the state was wiped: nothing is on the trail
+    template <class G> __device__ __forceinline__ void drop() { tail = 0; nres = 0; }   // the state was wiped: nothing is on the trail
     // Commit one round of candidate implications (one candidate per lane, 0 = none). Group-converged.
     // ADOPT: the candidates are the literals of a finished closure -- pairwise distinct (no duplicate search) and
-    // entered on the trail with the TRAIL_CLOSED mark. Returns 0 ok, 1 conflict, 2 state overflow.
+    // entered on the trail with `mark` (TRAIL_CLOSED / TRAIL_SKIP). Returns 0 ok, 1 conflict, 2 state overflow.
     template <class G, class S, bool ADOPT = false>
-    __device__ __forceinline__ int commit(S &st, uint32_t cand)
+    __device__ __forceinline__ int commit(S &st, uint32_t cand, uint32_t mark = TRAIL_CLOSED)
     {
         const bool has = cand != 0;
         bool leader = has;
@@ -329,14 +331,34 @@ struct GroupTail {
         const unsigned newm = G::ballot(leader && r == 0);
         const uint32_t nnew = __popc(newm);
         if (tail + nnew > st.cap) return 2;  // caller wipes the whole table: the new entries are not on the trail
-        if (leader && r == 0) st.tset(tail + __popc(newm & G::lt()), ADOPT ? (cand | TRAIL_CLOSED) : cand, slot);
+        if (leader && r == 0) st.tset(tail + __popc(newm & G::lt()), ADOPT ? (cand | mark) : cand, slot);
         tail += nnew;
         return any_conf ? 1 : 0;
+    }
+    // Second walks (one TRAIL_RESCAN entry each) for the members among the trail entries [0, upto) that will not get a
+    // walk of their own any more: the ones before `head` (walked already) and the TRAIL_SKIP ones. Returns 2 when they
+    // do not fit.
+    template <class G, class S>
+    __device__ __forceinline__ int append_rescan(S &st, uint32_t upto, uint32_t head)
+    {
+        for (uint32_t base = 0; base < upto; base += G::width) {
+            const uint32_t i = base + G::lane();
+            const uint32_t e = i < upto ? st.tget(i) : TRAIL_RESCAN;
+            const uint32_t mode = e & TRAIL_SKIP;
+            const bool has = mode != TRAIL_RESCAN && (i < head || mode == TRAIL_SKIP);
+            const unsigned m = G::ballot(has);
+            const uint32_t n = __popc(m);
+            if (tail + n > st.cap) return 2;
+            if (has) st.tset(tail + __popc(m & G::lt()), (e & TRAIL_LIT) | TRAIL_RESCAN, 0xffffu);
+            tail += n;
+            nres += n;
+        }
+        return 0;
     }
 };
 
 struct BlockTail {
-    uint32_t *ctl;  // shared: [0] tail, [1] conflict latch, [2] overflow latch
+    uint32_t *ctl;  // shared: [0] tail, [1] conflict latch, [2] overflow latch, [8] TRAIL_RESCAN entries on the trail
     __device__ __forceinline__ uint32_t get() const { return *(volatile uint32_t *)&ctl[0]; }
     // Warp-uniform by a vote: the latches are written by OTHER warps at any time, and the lanes of a warp do not
     // necessarily read them in the same cycle; a warp whose lanes disagreed here would split -- some lanes leave
@@ -345,7 +367,7 @@ struct BlockTail {
     template <class G> __device__ __forceinline__ void latch_conflict() { if (G::lane() == 0) ctl[1] = 1; }
     template <class G> __device__ __forceinline__ void drop() {}   // (the dense third-tier state cannot overflow)
     template <class G, class S, bool ADOPT = false>
-    __device__ __forceinline__ int commit(S &st, uint32_t cand)
+    __device__ __forceinline__ int commit(S &st, uint32_t cand, uint32_t mark = TRAIL_CLOSED)
     {
         const bool has = cand != 0;
         bool leader = has;
@@ -364,12 +386,45 @@ struct BlockTail {
             if (G::lane() == 0) pos = atomicAdd(&ctl[0], nnew);
             pos = G::shfl(pos, 0);
             if (pos + nnew > st.cap) { if (G::lane() == 0) ctl[2] = 1; ret = 2; }
-            else if (leader && r == 0) st.tset(pos + __popc(newm & G::lt()), ADOPT ? (cand | TRAIL_CLOSED) : cand, slot);
+            else if (leader && r == 0) st.tset(pos + __popc(newm & G::lt()), ADOPT ? (cand | mark) : cand, slot);
         }
         if (any_conf) { if (G::lane() == 0) ctl[1] = 1; if (!ret) ret = 1; }
         return ret;
     }
+    // second walks for the trail entries first, first + stride, ... below upto (this warp's share); see GroupTail
+    template <class G, class S>
+    __device__ __forceinline__ int append_rescan(S &st, uint32_t upto, uint32_t head, uint32_t first = 0, uint32_t stride = 32)
+    {
+        for (uint32_t base = first; base < upto; base += stride) {
+            const uint32_t i = base + G::lane();
+            const uint32_t e = i < upto ? st.tget(i) : TRAIL_RESCAN;
+            const uint32_t mode = e & TRAIL_SKIP;
+            const bool has = mode != TRAIL_RESCAN && (i < head || mode == TRAIL_SKIP);
+            const unsigned m = G::ballot(has);
+            const uint32_t n = __popc(m);
+            if (!n) continue;
+            uint32_t pos = 0;
+            if (G::lane() == 0) { pos = atomicAdd(&ctl[0], n); atomicAdd(&ctl[8], n); }
+            pos = G::shfl(pos, 0);
+            if (pos + n > st.cap) { if (G::lane() == 0) ctl[2] = 1; return 2; }
+            if (has) st.tset(pos + __popc(m & G::lt()), (e & TRAIL_LIT) | TRAIL_RESCAN, 0xffffu);
+        }
+        return 0;
+    }
 };
+
+// Value of a literal for this probe: the probe's own assignment, and -- only while level-0 facts are newer than the rows
+// (DbView::l0_dirty) -- the level-0 value. 0 unassigned, 1 true, 2 false.
+template <class S>
+__device__ __forceinline__ int value_of(const DbView &db, const S &st, uint32_t lit)
+{
+    int v = st.lookup(lit);
+    if (v == 0 && db.l0_dirty) {
+        const uint8_t li = __ldg(&db.litinfo[lit]);
+        v = (li & LI_TRUE_L0) ? 1 : (li & LI_FALSE_L0) ? 2 : 0;
+    }
+    return v;
+}
 
 // Judge a long clause (>= 4 literals) from scratch: TopiBcp.cc:262-367 without the watch bookkeeping.
 // Returns the literal to imply (0 = none); sets confl when every literal is false.
@@ -389,7 +444,7 @@ __device__ __forceinline__ uint32_t visit_long(const DbView &db, const S &st, ui
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (k < have && i < size && !sat) {
-                const int v = st.lookup(l[k]);
+                const int v = value_of(db, st, l[k]);
                 if (v == 1) sat = true;
                 else if (v == 0) { ++nfree; cand = l[k]; }
                 ++i;
@@ -409,19 +464,26 @@ __device__ __forceinline__ uint32_t visit_long(const DbView &db, const S &st, ui
 // One group scans the rows of up to W newly true literals (lane i holds literal p for i < B): one header
 // gather, then the union of the rows is flattened and walked W eight-byte slots at a time.
 // Returns 0 ok, 1 conflict, 2 overflow.
-// e = trail entries: the literal, | TRAIL_CLOSED when it came in with a finished closure (then its binary clauses are
-// known to be satisfied and only the ternary / long part of its row is walked).
+// e = trail entries: literal | mode (bbcp_device.cuh: TRAIL_CLOSED / TRAIL_RESCAN walk the ternary / long part of the row
+// only, TRAIL_SKIP walks nothing).
 template <class G, class S, class T>
 __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_t B, bool bins_only, WorkCounters &wc)
 {
     constexpr int W = G::width;
     const int lane = G::lane();
-    const uint32_t p = e & ~TRAIL_CLOSED;
+    const uint32_t p = e & TRAIL_LIT, mode = e & TRAIL_SKIP;
+    const bool in = lane < (int)B;
     uint4 hd = make_uint4(0, 0, 0, 0);
-    BBCP_CHECK(lane >= (int)B || (p >= 2 && p < 2u * ((uint32_t)db.max_var + 1)), "trail literal %u (B %u lane %d blk %d thr %d)\n", p, B, lane, blockIdx.x, threadIdx.x);
-    if (lane < (int)B) hd = __ldg(&db.hdr[p ^ 1u]);
-    wc.props_ref += __popc(G::ballot((hd.y | hd.z | hd.w) != 0));
-    if (e & TRAIL_CLOSED) { hd.x += (hd.y + 1u) >> 1; hd.y = 0; }
+    BBCP_CHECK(!in || (p >= 2 && p < 2u * ((uint32_t)db.max_var + 1)), "trail literal %u (B %u lane %d blk %d thr %d)\n", p, B, lane, blockIdx.x, threadIdx.x);
+    bool nonempty;
+    if (in && mode != TRAIL_SKIP) {
+        hd = __ldg(&db.hdr[p ^ 1u]);
+        nonempty = (hd.y | hd.z | hd.w) != 0;
+    } else nonempty = in && (__ldg(&db.litinfo[p]) & LI_NONEMPTY) != 0;   // (one byte, L2-resident: only the reference's counter wants it)
+    // the reference counts a propagation per dequeued literal whose row was ever allocated; a second walk is not a dequeue
+    wc.props_ref += __popc(G::ballot(nonempty && mode != TRAIL_RESCAN));
+    wc.props_all += __popc(G::ballot(in && mode != TRAIL_RESCAN));
+    if (mode != 0) { hd.x += (hd.y + 1u) >> 1; hd.y = 0; }
     const uint32_t nb2 = (hd.y + 1u) >> 1;
     const uint32_t cnt = bins_only ? nb2 : nb2 + hd.z + hd.w;
     uint32_t incl = cnt;
@@ -432,9 +494,8 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_
     }
     const uint32_t excl = incl - cnt;
     const uint32_t total = G::shfl(incl, W - 1);
-    wc.props_all += B;
     wc.slots += total;
-    wc.bytes += 16ull * B + 8ull * total;
+    wc.bytes += 16ull * __popc(G::ballot(in && mode != TRAIL_SKIP)) + __popc(G::ballot(in && mode == TRAIL_SKIP)) + 8ull * total;   // headers (or one byte of litinfo) + slots
 
     BBCP_WATCH_BEGIN();
     for (uint32_t base = 0; base < total; base += W) {
@@ -461,17 +522,17 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_
             const uint2 s = __ldg(&db.slots[r_start + k]);
             if (k < r_nb2) {
                 // binary clauses (TopiBcp.cc:207-246)
-                int v = st.lookup(s.x);
+                int v = value_of(db, st, s.x);
                 if (v == 0) c0 = s.x; else if (v == 2) confl = true;
                 if (s.y) {
-                    v = st.lookup(s.y);
+                    v = value_of(db, st, s.y);
                     if (v == 0) c1 = s.y; else if (v == 2) confl = true;
                 }
             } else if (k < r_nb2 + r_nt) {
                 // inline ternary clause (falsified literal, s.x, s.y)
-                const int va = st.lookup(s.x);
+                const int va = value_of(db, st, s.x);
                 if (va != 1) {
-                    const int vb = st.lookup(s.y);
+                    const int vb = value_of(db, st, s.y);
                     if (vb != 1) {
                         if (va == 2 && vb == 2) confl = true;
                         else if (va == 2) c0 = s.y;
@@ -480,7 +541,7 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_
                 }
             } else {
                 // long clause: cached literal first (TopiBcp.cc:255-259), then the clause itself
-                if (st.lookup(s.x) != 1) c0 = visit_long(db, st, s.y, confl, fetched16);
+                if (value_of(db, st, s.x) != 1) c0 = visit_long(db, st, s.y, confl, fetched16);
             }
         }
         const unsigned fm = G::ballot(fetched16 != 0);
@@ -531,8 +592,8 @@ __device__ __forceinline__ int closure_lookup(const BatchView &b, T &tl, uint32_
     const int lane = G::lane();
     len = 0;
     off = 0;
-    const uint64_t u = (uint64_t)(e & ~TRAIL_CLOSED) - 2u - b.first;      // item index of the literal's own probe
-    const bool want = lane < (int)B && !(e & TRAIL_CLOSED) && (e & ~TRAIL_CLOSED) >= 2u + b.first && u < b.n;
+    const uint64_t u = (uint64_t)(e & TRAIL_LIT) - 2u - b.first;      // item index of the literal's own probe
+    const bool want = lane < (int)B && !(e & TRAIL_SKIP) && (e & TRAIL_LIT) >= 2u + b.first && u < b.n;
     const uint8_t f = want ? ld_flag(&b.flag[u]) : (uint8_t)FLAG_QUEUED;
     if (G::any(f == FLAG_CONFLICT)) { tl.template latch_conflict<G>(); ++wc.inherited; return 1; }
     // tier t hands on what outgrew it with flag FLAG_OVERFLOW - (t - 1); a literal whose probe outgrew THIS tier or a later one
@@ -551,7 +612,8 @@ __device__ __forceinline__ int closure_lookup(const BatchView &b, T &tl, uint32_
 
 // The group enters literals [first, first + W), [first + stride, ...) ... of a finished set. Returns 0 / 1 / 2.
 template <class G, class S, class T>
-__device__ __forceinline__ int closure_adopt(const BatchView &b, S &st, T &tl, unsigned long long src, uint32_t n, uint32_t first, uint32_t stride)
+__device__ __forceinline__ int closure_adopt(const BatchView &b, S &st, T &tl, unsigned long long src, uint32_t n, uint32_t first, uint32_t stride,
+                                             uint32_t mark = TRAIL_CLOSED)
 {
     const int lane = G::lane();
     BBCP_CHECK(src + n <= b.out_cap, "adopting off %llu len %u of %llu\n", src, n, (unsigned long long)b.out_cap);
@@ -559,8 +621,8 @@ __device__ __forceinline__ int closure_adopt(const BatchView &b, S &st, T &tl, u
     for (uint32_t i = first; i < n; i += stride) {
         BBCP_WATCH(n, i);
         const uint32_t c = i + lane < n ? (uint32_t)__ldcg(&b.out_lits[src + i + lane]) : 0u;
-        BBCP_CHECK(c == 0 || (c >= 2 && !(c & TRAIL_CLOSED)), "adopted literal %u (off %llu + %u of %u)\n", c, src, i + lane, n);
-        const int r = tl.template commit<G, S, true>(st, c);
+        BBCP_CHECK(c == 0 || (c >= 2 && !(c & TRAIL_SKIP)), "adopted literal %u (off %llu + %u of %u)\n", c, src, i + lane, n);
+        const int r = tl.template commit<G, S, true>(st, c, mark);
         if (r) return r;
         if (tl.aborted()) return 1;
         st.template maybe_grow<G>(tl.get());
@@ -568,8 +630,16 @@ __device__ __forceinline__ int closure_adopt(const BatchView &b, S &st, T &tl, u
     return 0;
 }
 
+// `head` = trail entries [0, head) have had their row walked, [head, tail) are waiting for theirs.
+// SKIP mode. Let S be the state (all trail members) when a finished set A is entered, and suppose A is several times
+// larger than S. A is closed under unit propagation on its own, so a clause can only become unit now if it has false
+// literals on BOTH sides, in A \ S and in S. Every such clause is seen from the S side: the members of S whose walk is
+// still to come see all of A when it comes, and the members already walked get a second walk (TRAIL_RESCAN, ternary /
+// long part: the binary clauses of a walked literal are satisfied). So the literals of A need no walk at all
+// (TRAIL_SKIP): |S| row walks instead of |A|. Later sets are treated the same way against the then-current state, which
+// contains A's members as ordinary members (they are rescanned if a still larger set arrives).
 template <class G, class S, class T>
-__device__ int expand_closures(const BatchView &b, S &st, T &tl, uint32_t e, uint32_t B, int tier, WorkCounters &wc)
+__device__ int expand_closures(const BatchView &b, S &st, T &tl, uint32_t e, uint32_t B, uint32_t head, int tier, WorkCounters &wc)
 {
     uint32_t len;
     unsigned long long off;
@@ -582,7 +652,12 @@ __device__ int expand_closures(const BatchView &b, S &st, T &tl, uint32_t e, uin
         const uint32_t n = G::shfl(len, k);
         const unsigned long long src = G::shfl(off, k);
         if (n > st.cap) return 2;
-        const int r = closure_adopt<G>(b, st, tl, src, n, 0, G::width);
+        const uint32_t t0 = tl.get();
+        // (the first tier's sets are a few hundred literals: not worth the second walks, and its slot index array has no
+        // room for them)
+        const bool skip = tier >= 2 && n >= 4u * t0 && 2ull * t0 + n <= st.cap;
+        int r = closure_adopt<G>(b, st, tl, src, n, 0, G::width, skip ? TRAIL_SKIP : TRAIL_CLOSED);
+        if (!r && skip) r = tl.template append_rescan<G>(st, t0, head);
         if (r) return r;
         ++wc.adopted;
         wc.adopt_lits += n;
@@ -603,7 +678,7 @@ __device__ int propagate(const DbView &db, const BatchView &b, S &st, GroupTail 
         // while a single literal is assigned only binary clauses can become unit
         const bool first_step = tl.tail == 1;
         if (b.reuse && !first_step) {
-            const int r = expand_closures<G>(b, st, tl, e, B, tier, wc);
+            const int r = expand_closures<G>(b, st, tl, e, B, head, tier, wc);
             if (r) return r;
         }
         const int r = process_batch<G>(db, st, tl, e, B, prune && first_step, wc);

@@ -8,9 +8,15 @@ replicated; nothing else is exchanged on the data path.
 
 Two implementations of that all-gather:
 
-* ``peer_attach`` + ``merge_bitmaps``: the engine's own kernel over NVLink peer memory (``bbcp_merge_bitmaps``:
-  every rank stores its slice of both bitmaps straight into every peer's bitmaps, then a flag handshake; one
-  launch, no staging copies). ``torch.distributed`` is used once, at set-up, to exchange the CUDA IPC handles.
+* ``peer_attach`` + ``merge_bitmaps``: the engine's own kernel over NVLink peer memory (``bbcp_merge_bitmaps``), a
+  PULL protocol: every rank raises an epoch flag in every peer once its own slice is final, waits for the peers'
+  flags and then copies the peers' slices of the FAILED-literal bitmap out of their (CUDA-IPC-mapped) memory with
+  16-byte remote loads; the unit bitmap of those slices is derived on the spot (negating a literal swaps the two
+  bits of its variable). A rank OVERWRITES its copy of the peers' slices (it does not OR into it): bits it held
+  there from another sharding are discarded. When a rank has finished pulling it tells its peers so (a second
+  epoch word per rank); ``bbcp_clear_bitmaps``, a re-finalize and ``bbcp_peer_detach`` wait for that before they
+  touch the bitmaps, so no host barrier is needed between a merge and a clear. One launch, no staging copies;
+  ``torch.distributed`` is used once, at set-up, to exchange the CUDA IPC handles.
 * ``allgather_bitmap``: ``torch.distributed.all_gather_into_tensor`` (NCCL / gloo) -- the baseline the kernel
   is checked against, and the path the CPU tests cover.
 """

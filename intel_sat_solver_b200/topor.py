@@ -25,6 +25,8 @@ OPT_KERNEL_TIMES = 8
 OPT_MERGE = 16
 OPT_RENDEZVOUS = 32
 OPT_NO_REUSE = 64
+OPT_COMPACT_SELF = 128
+FLAG_SELF = 0x80
 
 
 class TToporReturnVal(enum.IntEnum):
@@ -131,11 +133,11 @@ class BatchedTopor:
 
     @staticmethod
     def _opts(implied=True, small_trail=0, out_capacity=0, no_len_prune=False, mid_trail=0, off32=False, kernel_times=False,
-              merge=0, rendezvous=False, no_reuse=False) -> Opts:
+              merge=0, rendezvous=False, no_reuse=False, compact_self=False) -> Opts:
         """merge: 0, or the bitmap words owned by each rank (sharding.Shard.words_per_rank) to all-gather the slices in the batch"""
         return Opts((OPT_IMPLIED if implied else 0) | (OPT_NO_LEN_PRUNE if no_len_prune else 0) | (OPT_OFF32 if off32 else 0)
                     | (OPT_KERNEL_TIMES if kernel_times else 0) | (OPT_MERGE if merge else 0) | (OPT_RENDEZVOUS if rendezvous else 0)
-                    | (OPT_NO_REUSE if no_reuse else 0),
+                    | (OPT_NO_REUSE if no_reuse else 0) | (OPT_COMPACT_SELF if compact_self else 0),
                     small_trail, out_capacity, mid_trail, int(merge))
 
     def _fetch(self, info: BatchInfo, implied: bool, fetch: bool, off32: bool = False) -> BatchResult:
@@ -184,6 +186,27 @@ class BatchedTopor:
                                                     impl_out.ctypes.data, impl_out.size, C.byref(info)))
         return BatchResult(info.as_dict(), flag_out[:n], off_out[: n + 1], impl_out[: info.n_implied])
 
+    @staticmethod
+    def ExpandCompact(lits, res: BatchResult) -> BatchResult:
+        """Host-side expansion of a compact read-back (compact_self=True: BBCP_FLAG_SELF instead of a stored one-literal
+        set; offsets not written at all when nothing was stored) into the standard flag / CSR form."""
+        lits = np.asarray(lits, dtype=np.int32)
+        n = lits.size
+        self_ = (res.flag & FLAG_SELF) != 0
+        flag = (res.flag & ~np.uint8(FLAG_SELF)).astype(np.uint8)
+        stored = np.diff(res.impl_off.astype(np.int64)) if res.info["n_implied"] else np.zeros(n, dtype=np.int64)
+        sizes = stored + self_
+        off = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(sizes, out=off[1:])
+        out = np.empty(int(off[n]), dtype=np.int32)
+        out[off[:-1][self_].astype(np.int64)] = lits[self_]
+        if res.info["n_implied"]:
+            nz = np.nonzero(stored)[0]
+            src0, dst0 = res.impl_off.astype(np.int64)[nz], off[:-1].astype(np.int64)[nz]
+            idx = np.repeat(dst0 - src0, stored[nz]) + np.arange(int(res.info["n_implied"]))
+            out[idx] = res.impl_lits
+        return BatchResult(res.info, flag, off, out)
+
     def PropagateBatch(self, cube_lits, cube_off, implied=True, fetch=True, **kw) -> BatchResult:
         lits = np.ascontiguousarray(cube_lits, dtype=np.int32)
         off = np.ascontiguousarray(cube_off, dtype=np.uint64)
@@ -193,6 +216,12 @@ class BatchedTopor:
         o = self._opts(implied=implied, **kw)
         self._check(self._L.bbcp_propagate_batch(self._h, lits.ctypes.data, off.ctypes.data, off.size - 1, C.byref(o), C.byref(info)))
         return self._fetch(info, implied, fetch, kw.get("off32", False))
+
+    def CheckFixpoints(self, first: int = 0, count: int = 1 << 62, stride: int = 1) -> dict:
+        """No-missed-implication check of the last batch's fixpoints on the device (bbcp_check_fixpoints)."""
+        v, c, i = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self._L.bbcp_check_fixpoints(self._h, int(first), int(count), int(stride), C.byref(v), C.byref(c), C.byref(i)))
+        return {"violations": v.value, "clauses_checked": c.value, "items_checked": i.value}
 
     def ProbeToFixpoint(self, max_rounds: int = 0) -> dict:
         """Failed-literal probing with unit feedback until a pass finds no new failed literal (bbcp_probe_to_fixpoint).

@@ -506,3 +506,114 @@ def test_counters_against_the_reference(tmp_path):
             assert i["bcps"] == int((ref.flag <= 1).sum())
             assert i["props_ref_ok"] >= int(ref.props[ok].sum()) > 0
             assert i["assignments"] >= i["assignments_ok"] and i["props_ref"] >= i["props_ref_ok"]
+
+
+def test_device_unit_feedback_equals_host_rebuild(tmp_path):
+    """bbcp_probe_to_fixpoint applies the failed-literal units ON THE DEVICE (level-0 facts marked in litinfo, rows left as
+    they are); the round-1 loop re-finalized (host rebuild) after every round. Same rounds, same units, same level-0
+    assignment, and afterwards the same probe results as a freshly built database with the units added."""
+    import json, subprocess, sys
+    multi = 0
+    for kind, kw in (("plaw", dict(n=20000, m=80000, seed=5)), ("aig", dict(frames=4, gates=3000, inputs=100, latches=100, window=300, seed=2)),
+                     ("comm", dict(n=20000, m=70000, comms=20, seed=3))):
+        inst, _ = gpu_util.gen(kind, str(tmp_path), **kw)
+        words = fileio.read_bcnf(inst)
+        t, rc = engine_for(words)
+        got = t.ProbeToFixpoint()
+        prog = ("import sys, json; sys.path.insert(0, %r)\n"
+                "from intel_sat_solver_b200 import BatchedTopor, fileio\n"
+                "t = BatchedTopor(); t.AddClauses(fileio.read_bcnf(%r)); t.Finalize(); g = t.ProbeToFixpoint()\n"
+                "print(json.dumps({'got': g, 'level0': t.Level0().tolist()}))" % (gpu_util.ROOT, inst))
+        ref = json.loads(subprocess.run([sys.executable, "-c", prog], check=True, capture_output=True, text=True, env=dict(os.environ, BBCP_FIXPOINT="rebuild")).stdout)
+        assert got == ref["got"], kind
+        multi += got["status"] == 0 and got["rounds"] >= 2 and got["units"] > 0
+        _after_fixpoint(t, words, got, ref)
+    assert multi >= 1
+
+
+def _after_fixpoint(t, words, got, ref):
+    if got["status"] == 0:
+        assert t.Level0().tolist() == ref["level0"]
+        # the database with level-0 facts newer than its rows answers like a rebuilt one
+        res = t.ProbeAll()
+        t2 = BatchedTopor()
+        t2.AddClauses(words)
+        t2.AddClauses(np.stack([t.Level0(), np.zeros_like(t.Level0())], axis=1).ravel())
+        assert t2.Finalize() == 0
+        res2 = t2.ProbeAll()
+        gpu_util.assert_same_results(res, res2.flag, res2.impl_off, res2.impl_lits, "dirty level 0 vs rebuilt")
+        cl = np.asarray([5, -7, 11, 0, -5, 0, 13, 17, -19, 23], dtype=np.int32)
+        co = np.asarray([0, 3, 4, 5, 10], dtype=np.uint64)
+        ra, rb = t.PropagateBatch(cl, co), t2.PropagateBatch(cl, co)
+        gpu_util.assert_same_results(ra, rb.flag, rb.impl_off, rb.impl_lits, "dirty level 0 vs rebuilt, cubes")
+
+
+def test_compact_read_back_expands_to_the_same_results(tmp_path):
+    """BBCP_OPT_COMPACT_SELF: self-implying probes come back as a flag bit instead of a stored one-literal set (and no
+    offsets at all when nothing was stored); expanded on the host the results are the standard ones, bit for bit."""
+    for kind, kw in (("3sat", dict(n=30000, m=126000, seed=1)), ("plaw", dict(n=20000, m=80000, seed=5)), ("aig", dict(frames=2, gates=2000, inputs=80, latches=80, window=200, seed=2))):
+        inst, _ = gpu_util.gen(kind, str(tmp_path), **kw)
+        t, rc = engine_for(fileio.read_bcnf(inst))
+        n = 2 * t.max_var
+        idx = np.arange(n)
+        lits = np.where(idx & 1, -(idx // 2 + 1), idx // 2 + 1).astype(np.int32)
+        lits[::97] = 0                      # a 0 in a probe list names no variable
+        std = t.ProbeLits(lits)
+        for off32 in (False, True):
+            off_buf = np.full(n + 1, 0xdeadbeef, dtype=np.uint32 if off32 else np.uint64)
+            raw = t.ProbeLitsToHost(lits, off_out=off_buf, compact_self=True, off32=off32)
+            assert (raw.flag & 0x80).any()
+            if kind == "3sat":
+                assert raw.info["n_implied"] == 0 and (off_buf[:n] == 0xdeadbeef).all()   # nothing stored: offsets never travel
+            exp = BatchedTopor.ExpandCompact(lits, raw)
+            gpu_util.assert_same_results(exp, std.flag, std.impl_off, std.impl_lits, f"{kind} compact off32={off32}")
+
+
+def test_no_missed_implication_checker(golden, tmp_path):
+    """The static analogue of WLAssertNoMissedImplications (TopiWL.cc:330-442): under every fixpoint the engine reports,
+    no clause of the database is unsatisfied with fewer than two unassigned literals. Run over the regression corpus, the
+    synthetic shapes, tiny tiers (every tier's code path), cubes, and a database whose level-0 facts are newer than its rows;
+    a deliberately truncated implied set must be caught."""
+    total = 0
+    for name in ["regr_47", "regr_72", "regr_20", "fuzz_10", "fuzz_5", "hand_long", "ddtbug_32499"]:
+        t, rc = engine_for(golden[f"{name}/words"])
+        for kw in (dict(), dict(small_trail=32, mid_trail=32)):
+            t.ProbeAll(fetch=False, **kw)
+            r = t.CheckFixpoints()
+            assert r["violations"] == 0 and r["items_checked"] > 0, (name, kw, r)
+            total += r["clauses_checked"]
+        t.PropagateBatch(golden[f"{name}/cube_lits"], golden[f"{name}/cube_off"], fetch=False)
+        assert t.CheckFixpoints()["violations"] == 0, name
+    for kind, kw in (("aig", dict(frames=3, gates=2000, inputs=80, latches=80, window=200, seed=2)), ("plaw", dict(n=8000, m=32000, seed=5)),
+                     ("comm", dict(n=8000, m=32000, comms=10, seed=3))):
+        inst, _ = gpu_util.gen(kind, str(tmp_path), **kw)
+        t, rc = engine_for(fileio.read_bcnf(inst))
+        for okw in (dict(), dict(small_trail=32), dict(small_trail=32, mid_trail=64), dict(no_reuse=True)):
+            t.ProbeAll(fetch=False, **okw)
+            r = t.CheckFixpoints(stride=7)
+            assert r["violations"] == 0 and r["items_checked"] > 100, (kind, okw, r)
+            total += r["clauses_checked"]
+        if kind == "plaw":
+            t.ProbeToFixpoint()
+            t.ProbeAll(fetch=False)
+            assert t.CheckFixpoints(stride=5)["violations"] == 0
+    assert total > 10_000_000
+    # negative control: an engine whose results are cut short is caught (drop the last literal of every set on the device)
+    import torch
+    t, rc = engine_for(golden["fuzz_10/words"])
+    res = t.ProbeAll()
+    off = torch.as_tensor(res.impl_off.astype(np.int64))
+    sizes = np.diff(res.impl_off.astype(np.int64))
+    big = np.nonzero(sizes > 3)[0]
+    assert big.size > 0
+    from intel_sat_solver_b200._lib import load
+    ptr = load().bbcp_device_impl_lits(t.handle)
+    class Arr:
+        __cuda_array_interface__ = {"shape": (int(res.impl_off[-1]),), "typestr": "<i4", "data": (ptr, False), "version": 3}
+    dev = torch.as_tensor(Arr(), device="cuda")
+    # overwrite the last literal of each large set with a duplicate of its first one: the set loses a member
+    last = torch.as_tensor(res.impl_off[big + 1].astype(np.int64) - 1, device="cuda")
+    firsts = torch.as_tensor(res.impl_off[big].astype(np.int64), device="cuda")
+    dev[last] = dev[firsts]
+    torch.cuda.synchronize()
+    assert t.CheckFixpoints()["violations"] > 0

@@ -34,8 +34,21 @@ def _worker(rank, world, port, names, q):
             res = t.ProbeRange(s.first, s.last)
             ms = sharding.merge_bitmaps(t, s)
         # the same with the merge as the last kernel of the batch (and a device-side rendezvous before it), with
-        # state budgets that send some probes through the second launch sequence on some ranks only
+        # state budgets that send some probes through the second launch sequence on some ranks only.
+        # NO host barrier between the merge above and the clear: a rank must not wipe its slice while a slower peer
+        # is still pulling it (the pull-done acknowledgement; the ranks are skewed on purpose)
+        if rank % 2:
+            import time
+            time.sleep(0.05 * rank)
         t.ClearBitmaps()
+        for rep in range(2):   # merge -> clear -> merge without any host synchronisation between the ranks
+            res = t.ProbeRange(s.first, s.last, merge=s.words_per_rank)
+            f1, _ = t.Bitmaps()
+            nw = sharding.bitmap_words(t.max_var)
+            bits = np.zeros(nw * 32, dtype=np.uint8)
+            bits[np.nonzero(golden[f"{name}/probe_flag"] == 1)[0] + 2] = 1
+            ok &= bool(np.array_equal(f1, np.packbits(bits, bitorder="little").view(np.uint32)))
+            t.ClearBitmaps()
         dist.barrier()
         for kw in (dict(), dict(small_trail=32, mid_trail=32), dict(out_capacity=16), dict(implied=False)):
             res = t.ProbeRange(s.first, s.last, merge=s.words_per_rank, rendezvous=True, **kw)
