@@ -124,6 +124,19 @@ class ClockSampler:
     def mark(self):
         return len(self.rows)
 
+    def wait_first(self, timeout=4.0):
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def under_load(self, fn, want=3, limit=2.0):
+        """The timed regions here are micro- to milliseconds long, nvidia-smi samples every 200 ms: keep the SAME step running
+        (untimed) until a few samples have been taken under that load."""
+        m0, t0 = self.mark(), time.perf_counter()
+        while self.proc and self.mark() - m0 < want and time.perf_counter() - t0 < limit:
+            fn()
+        return self.summary(m0)
+
     def summary(self, lo=0, hi=None):
         rows = self.rows[lo:hi]
         sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
@@ -218,7 +231,7 @@ def peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def timed_passes(eng, call, steps, warmup=1):
+def timed_passes(eng, call, steps, warmup=2):
     """`call(opts_kw)` runs one pass and returns its BatchResult. L2 is flushed ON THE ENGINE'S STREAM before every
     pass (bbcp_l2_flush), so the pass's kernels are already queued when the device gets to them."""
     ms, last = [], None
@@ -270,9 +283,11 @@ def workload_block(key, scale_cpu_seconds, clocks, cores, pre=None):
         call = lambda kw: eng.ProbeAll(fetch=False, **kw)
     mark = clocks.mark() if clocks else 0
     ms, res, kt = timed_passes(eng, call, steps=2)
+    clk = clocks.summary(mark) if clocks else None
+    if clocks and (not clk or clk["samples"] < 2):
+        clk = clocks.under_load(lambda: call({}))     # a pass of a few milliseconds: keep it running for a few samples
     res = call({})     # results kept on the device for the parity sample
     info = res.info
-    clk = clocks.summary(mark) if clocks else None
     sec = sum(ms) / len(ms) / 1e3
     peak, peak_src = peak_hbm()
     prop_ms = kt["deep_ms"] + kt["block_ms"]
@@ -459,18 +474,7 @@ def ours_arm(args, rank, local_rank, world):
     cores = os.cpu_count() or 1
     wl_keys = [k for k in args.workloads.split(",") if k in WORKLOADS] if args.workloads != "none" else []
 
-    # the C5 checker processes need minutes to load 50 M clauses: start them first, on a few cores, and collect them last
     pre_c5 = None
-    c5_cores = min(4, max(1, cores // 4))
-    if rank == 0 and world == 1 and "c5" in wl_keys and not args.no_cpu:
-        w = WORKLOADS["c5"]
-        inst5, _ = generate(w["kind"], "wl", **w["gen"])
-        d5 = tempfile.TemporaryDirectory()
-        stride5 = max(1, int(25_000_000 / (w["rate_guess"] * 6.0 * c5_cores)))
-        procs, kind = start_cpu_shards(inst5, c5_cores, stride5, 1, None, d5.name)
-        pre_c5 = (procs, kind, stride5, d5)
-        cores = max(1, cores - c5_cores)     # the other CPU legs leave those cores alone
-
     nvars, ncls = args.vars * world, int(args.vars * world * args.ratio)
     if rank == 0:
         make_instance(nvars, ncls, args.seed, "c2")
@@ -511,6 +515,7 @@ def ours_arm(args, rank, local_rank, world):
     if rank == 0:
         clocks = ClockSampler(range(world))    # ONE sampler for the box (rank 0), not one per rank
         clocks.start()
+        clocks.wait_first()
     kstats = {"triage_ms": [], "deep_ms": [], "compact_ms": [], "block_ms": [], "merge_ms": []}
     step_ms = []
     mark_c2 = clocks.mark() if clocks else 0
@@ -533,6 +538,12 @@ def ours_arm(args, rank, local_rank, world):
         assert rc == 0, eng.GetStatusExplanation()
         for k in kstats:
             kstats[k].append(getattr(info, k))
+    barrier()
+    # clocks under this load: the timed steps are ~30 us each, so the same step keeps running (untimed, all ranks) until the
+    # sampler has a few rows
+    for _ in range(8000):      # (a fixed count: with peers every rank must make the same sequence of merging calls)
+        rc = L.bbcp_probe_range(h, first, last, C.byref(opts), C.byref(info))
+        assert rc == 0, eng.GetStatusExplanation()
     barrier()
     clk = clocks.summary(mark_c2) if clocks else None
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -602,6 +613,18 @@ def ours_arm(args, rank, local_rank, world):
                "props_per_sec": r["implications_per_pass"] / r["pass_seconds"][-1], "failed_literals": r["conflicts"] // 2,
                "implications": r["implications_per_pass"], "engine_props_ref": int(props_ref)}
     del eng
+
+    # the C5 checker processes need minutes to load 50 M clauses: start them now (the C2 CPU leg above had every core),
+    # on a few cores, and collect them last; the other workloads' CPU legs leave those cores alone
+    if rank == 0 and world == 1 and "c5" in wl_keys and not args.no_cpu:
+        w = WORKLOADS["c5"]
+        c5_cores = min(4, max(1, cores // 4))
+        inst5, _ = generate(w["kind"], "wl", **w["gen"])
+        d5 = tempfile.TemporaryDirectory()
+        stride5 = max(1, int(25_000_000 / (w["rate_guess"] * 6.0 * c5_cores)))
+        procs, kind = start_cpu_shards(inst5, c5_cores, stride5, 1, None, d5.name)
+        pre_c5 = (procs, kind, stride5, d5)
+        cores = max(1, cores - c5_cores)
 
     mcheck = merge_check(rank, world, dist, torch) if world > 1 else None
     workloads = {}

@@ -95,6 +95,7 @@ struct bbcp_handle {
     std::vector<void *> peer_base;          // mapped base of every rank's d_bitmaps (own entry = own pointer)
     DevBuf d_peer_tab;                      // the same table on the device
     uint32_t merge_epoch = 0, drained_epoch = 0;
+    bool bitmaps_dirty = false;             // some batch since the last clear found a failed literal
     uint32_t merge_timeout_ms = 20000;      // BBCP_MERGE_TIMEOUT_MS: how long a merging kernel waits for a peer (ranks may be seconds apart on skewed shards)
     cudaEvent_t ev_merge[2] = {nullptr, nullptr};
     uint64_t bitmap_words = 0;
@@ -267,6 +268,7 @@ bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo, bool with_or
     }
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "upload sync")) return false;
     h->l0_dirty = false;
+    h->bitmaps_dirty = false;
     h->device_db_bytes = db.hdr.size() * sizeof(RowHdr) + db.slots.size() * sizeof(Slot) + db.arena.size() * 4 + litinfo.size() + 2 * h->bitmap_words * 4 + (size_t)h->order_n * 4;
     return true;
 }
@@ -287,7 +289,7 @@ bool merge_timed_out(bbcp_handle *h)
 bool drain_peers(bbcp_handle *h)
 {
     if (h->peer_world <= 1 || h->merge_epoch == 0 || h->drained_epoch == h->merge_epoch) return true;
-    launch_merge_drain(MergeArgs{static_cast<uint32_t *const *>(h->d_peer_tab.p), h->peer_rank, h->peer_world, h->bm_stride, 0, h->merge_epoch, h->merge_timeout_ms}, h->stream);
+    launch_merge_drain(MergeArgs{static_cast<uint32_t *const *>(h->d_peer_tab.p), h->peer_rank, h->peer_world, h->bm_stride, 0, h->merge_epoch, h->merge_timeout_ms, 1u}, h->stream);
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "waiting for the peers to finish reading the bitmaps")) return false;
     h->drained_epoch = h->merge_epoch;
     if (merge_timed_out(h)) { h->fail(BBCP_ERR_STATE, "a peer did not finish the last bitmap merge within the time-out"); return false; }
@@ -455,14 +457,14 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     const bool peers = h->peer_world > 1 && !d_lits && !d_off;
     uint32_t *const *ptab = static_cast<uint32_t *const *>(h->d_peer_tab.p);
     if (peers && (opts.flags & BBCP_OPT_RENDEZVOUS))
-        launch_merge(MergeArgs{ptab, h->peer_rank, h->peer_world, h->bm_stride, 0, ++h->merge_epoch, h->merge_timeout_ms}, h->sm_count, h->stream);
+        launch_merge(MergeArgs{ptab, h->peer_rank, h->peer_world, h->bm_stride, 0, ++h->merge_epoch, h->merge_timeout_ms, 1u}, h->sm_count, h->stream);
     const bool do_merge = peers && (opts.flags & BBCP_OPT_MERGE);
     if (do_merge && (opts.merge_words_per_rank == 0 || (opts.merge_words_per_rank & 3)))
         return h->fail(BBCP_ERR_ARG, "BBCP_OPT_MERGE: opts.merge_words_per_rank must be a non-zero multiple of 4");
     const uint32_t mepoch = do_merge ? ++h->merge_epoch : 0;
     // with implied sets the merge rides inside k_scan_gather (stores at its start, handshake at its end)
-    const MergeArgs no_merge{nullptr, 0, 0, 0, 0, 0, 0};
-    const MergeArgs in_batch = do_merge ? MergeArgs{ptab, h->peer_rank, h->peer_world, h->bm_stride, opts.merge_words_per_rank, mepoch, h->merge_timeout_ms} : no_merge;
+    const MergeArgs no_merge{nullptr, 0, 0, 0, 0, 0, 0, 0};
+    const MergeArgs in_batch = do_merge ? MergeArgs{ptab, h->peer_rank, h->peer_world, h->bm_stride, opts.merge_words_per_rank, mepoch, h->merge_timeout_ms, h->bitmaps_dirty ? 1u : 0u} : no_merge;
 
     cudaEventRecord(h->ev[0], h->stream);
     for (int attempt = 0;; ++attempt) {
@@ -671,6 +673,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     h->last_n_implied = bi.n_implied;
     h->have_batch = true;
     h->total_props += bi.props_ref;
+    if (bi.n_conflict) h->bitmaps_dirty = true;
     if (info) *info = bi;
     return BBCP_OK;
 }
@@ -1243,6 +1246,7 @@ int bbcp_clear_bitmaps(bbcp_handle *h)
     if (rc) return rc;
     cudaSetDevice(h->device);
     if (!drain_peers(h)) return h->status < 0 ? h->status : BBCP_ERR_STATE;
+    h->bitmaps_dirty = false;
     cudaMemsetAsync(h->d_bitmaps.p, 0, 2 * h->bm_stride * 4, h->stream);
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "clear bitmaps") ? BBCP_OK : BBCP_ERR_CUDA;
 }
@@ -1337,7 +1341,7 @@ int bbcp_merge_bitmaps(bbcp_handle *h, uint64_t words_per_rank, float *ms)
     cudaSetDevice(h->device);
     ++h->merge_epoch;
     cudaEventRecord(h->ev_merge[0], h->stream);
-    launch_merge(MergeArgs{static_cast<uint32_t *const *>(h->d_peer_tab.p), h->peer_rank, h->peer_world, h->bm_stride, words_per_rank, h->merge_epoch, h->merge_timeout_ms},
+    launch_merge(MergeArgs{static_cast<uint32_t *const *>(h->d_peer_tab.p), h->peer_rank, h->peer_world, h->bm_stride, words_per_rank, h->merge_epoch, h->merge_timeout_ms, 1u},
                  h->sm_count, h->stream);
     cudaEventRecord(h->ev_merge[1], h->stream);
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "bitmap merge")) return BBCP_ERR_CUDA;

@@ -144,9 +144,10 @@ struct MergeArgs {
     uint64_t wp;                  // bitmap words owned by each rank (multiple of 4): rank r owns [r*wp, (r+1)*wp); 0 = rendezvous only
     uint32_t epoch;
     uint32_t timeout_ms;          // in-kernel wait limit for a peer's flag
+    uint32_t dirty_before;        // this rank's slice may hold failed literals from earlier batches (no empty-slice hint)
 };
 constexpr int MERGE_CTRL_WORDS = 256;      // control words behind the two bitmaps, see merge_signal in bbcp_kernels.cu
-constexpr int MERGE_CTRL_FINISHED = 64, MERGE_CTRL_ERROR = 65, MERGE_CTRL_DONE = 128;
+constexpr int MERGE_CTRL_FINISHED = 64, MERGE_CTRL_ERROR = 65, MERGE_CTRL_DONE = 128, MERGE_CTRL_EMPTY = 192;
 void launch_check_fixpoints(const DbView &db, bool off32, const uint8_t *flag, const void *off, const int32_t *impl, uint64_t first, uint64_t count, uint64_t stride,
                             uint32_t *scratch, int blocks, unsigned long long *out, cudaStream_t s);
 // marks the n external literals of `lits` true at level 0 in litinfo (and their negations false)

@@ -880,10 +880,17 @@ __device__ __forceinline__ unsigned long long global_ns()
 // [64] CTAs of the running merge that are done pulling (local), [65] time-out latch, [128..191] pull-done epoch per rank
 // ("rank r has finished reading my slice": what bbcp_clear_bitmaps / a re-finalize / a detach wait for before they
 // touch the bitmaps, k_merge_drain)
-__device__ __forceinline__ void merge_signal(const MergeArgs &m)
+// slice_empty: this rank's slice holds no failed literal (the usual case on real instances): the peers are told so and
+// clear their copy locally instead of pulling it. The hint travels as a second word; if it lands after the arrival
+// flag has been seen the peer just pulls the (all-zero) slice -- slower, never wrong.
+__device__ __forceinline__ void merge_signal(const MergeArgs &m, bool slice_empty)
 {
-    for (int p = 0; p < m.world; ++p)
-        if (p != m.rank) *(volatile uint32_t *)(m.peer_base[p] + 2 * m.stride + m.rank) = m.epoch;
+    for (int p = 0; p < m.world; ++p) {
+        if (p == m.rank) continue;
+        uint32_t *ctrl = m.peer_base[p] + 2 * m.stride;
+        if (slice_empty) *(volatile uint32_t *)(ctrl + MERGE_CTRL_EMPTY + m.rank) = m.epoch;
+        *(volatile uint32_t *)(ctrl + m.rank) = m.epoch;
+    }
 }
 
 // spin until every peer's word [base + p] has reached the epoch; one thread; false on time-out (a peer died or never
@@ -904,6 +911,32 @@ __device__ bool merge_spin(const MergeArgs &m, int base)
 }
 
 __device__ __forceinline__ bool merge_wait(const MergeArgs &m) { return merge_spin(m, 0); }
+
+// the same wait by a whole warp: lane p (and p + 32) watches peer p's flag, so eight peers cost one L2 round trip, not eight
+__device__ bool merge_wait_warp(const MergeArgs &m)
+{
+    uint32_t *ctrl = m.peer_base[m.rank] + 2 * m.stride;
+    const int lane = lane_id();
+    const unsigned long long t0 = global_ns(), limit = (unsigned long long)m.timeout_ms * 1000000ull;
+    bool ok = true;
+    for (int p = lane; p < m.world; p += 32) {
+        if (p == m.rank) continue;
+        uint32_t spins = 0;
+        while ((int32_t)(*(volatile uint32_t *)&ctrl[p] - m.epoch) < 0) {
+            if ((++spins & 0xfffu) == 0 && global_ns() - t0 > limit) { ctrl[MERGE_CTRL_ERROR] = 1; ok = false; break; }
+        }
+    }
+    ok = __all_sync(FULL, ok);
+    __threadfence();   // the loads of the pull stay behind the flag reads
+    return ok;
+}
+
+// tells every peer that this rank has finished reading their slices (called once, by the last CTA of a merging kernel)
+__device__ __forceinline__ void merge_done_signal(const MergeArgs &m)
+{
+    for (int p = 0; p < m.world; ++p)
+        if (p != m.rank) *(volatile uint32_t *)(m.peer_base[p] + 2 * m.stride + MERGE_CTRL_DONE + m.rank) = m.epoch;
+}
 
 // called by thread 0 of every CTA of a merging kernel when the CTA's share of the pull is complete (its remote loads
 // have returned: their values have been stored). The last CTA tells every peer that this rank is done reading.
@@ -936,12 +969,13 @@ __device__ __forceinline__ void merge_pull(const MergeArgs &m, uint64_t gtid, ui
     const uint64_t wp4 = m.wp / 4, s4 = m.stride / 4;           // both multiples of 4 words
     const uint64_t total = merge_total(m);
     uint4 *mine = reinterpret_cast<uint4 *>(m.peer_base[m.rank]);
+    const volatile uint32_t *empty = m.peer_base[m.rank] + 2 * m.stride + MERGE_CTRL_EMPTY;
     for (uint64_t i = gtid; i < total; i += gsize) {
         const int pi = (int)(i / wp4);
         const int p = pi + (pi >= m.rank);
         const uint64_t v = (uint64_t)p * wp4 + (i - (uint64_t)pi * wp4);   // vector index inside the bitmap
         if (v >= s4) continue;                                             // the last rank's slice may be short
-        const uint4 f = ld_remote(reinterpret_cast<const uint4 *>(m.peer_base[p]) + v);
+        const uint4 f = empty[p] == m.epoch ? make_uint4(0, 0, 0, 0) : ld_remote(reinterpret_cast<const uint4 *>(m.peer_base[p]) + v);
         mine[v] = f;
         mine[s4 + v] = make_uint4(swap_polarity(f.x), swap_polarity(f.y), swap_polarity(f.z), swap_polarity(f.w));
     }
@@ -950,7 +984,7 @@ __device__ __forceinline__ void merge_pull(const MergeArgs &m, uint64_t gtid, ui
 __global__ void __launch_bounds__(256) k_merge(const MergeArgs m)
 {
     __shared__ int s_ok;
-    if (blockIdx.x == 0 && threadIdx.x == 0) merge_signal(m);
+    if (blockIdx.x == 0 && threadIdx.x == 0) merge_signal(m, false);
     if (threadIdx.x == 0) s_ok = merge_wait(m);
     __syncthreads();
     if (s_ok && m.wp) merge_pull(m, (uint64_t)blockIdx.x * 256 + threadIdx.x, (uint64_t)gridDim.x * 256);
@@ -1003,7 +1037,8 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
     // peers now -- unless the implied-literal pool overflowed and the whole batch is about to be re-run
     // (MERGE is a template parameter so that the single-GPU kernel does not carry the merge's registers)
     const bool merging = MERGE && mg.world > 1 && *(volatile unsigned long long *)b.out_cursor <= b.out_cap;
-    if (merging && blockIdx.x == 0 && threadIdx.x == 0) merge_signal(mg);
+    if (merging && blockIdx.x == 0 && threadIdx.x == 0)
+        merge_signal(mg, !mg.dirty_before && ((volatile unsigned long long *)b.counters)[C_CONFLICT] == 0ull);
     __shared__ unsigned long long s_warp[SG_THREADS / 32], s_red[SG_THREADS / 32];
     __shared__ uint32_t s_nbig, s_pos;
     __shared__ uint16_t s_big[SG_TILE];
@@ -1152,16 +1187,16 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
         // (measured and dropped: issuing the remote loads early and holding the values to the end -- +16 registers, one
         // CTA less per SM, no gain; letting only the last-dispatched CTAs pull -- slower as well)
         __syncthreads();
-        if (tid == 0) s_pos = merge_wait(mg);
+        if (warp == 0) { const bool ok = merge_wait_warp(mg); if (lane == 0) s_pos = ok; }
         __syncthreads();
         if (s_pos) merge_pull(mg, (uint64_t)blockIdx.x * SG_THREADS + tid, (uint64_t)gridDim.x * SG_THREADS);
-        __syncthreads();
-        if (tid == 0) merge_cta_done(mg);
     }
     // the last CTA to finish copies the counter block of this launch sequence into mapped host memory: the host
     // reads it after the stream synchronisation it does anyway (no copy-engine round trip, and no fence: the
     // kernel has completed by then)
-    if (b.host_report) {
+    // (a merging kernel counts its CTAs in as well: the last one tells the peers that this rank is done reading their slices --
+    // its own remote loads have returned, their values are stored, and so have those of every CTA counted before it)
+    if (b.host_report || merging) {
         __syncthreads();   // this CTA's stores (offsets, total) are issued; warp 0 alone counts the CTA in, the rest leaves
         if (warp == 0) {
             unsigned last = 0;
@@ -1170,8 +1205,11 @@ __global__ void __launch_bounds__(SG_THREADS) k_scan_gather(const BatchView b, c
                 last = atomicAdd(b.tile_ticket + 1, 1u) == gridDim.x - 1;
             }
             if (__shfl_sync(FULL, last, 0)) {
-                __threadfence();
-                for (uint32_t i = lane; i < b.zero_words; i += 32) b.host_report[i] = ((volatile unsigned long long *)b.counters)[i];
+                if (merging && lane == 0) merge_done_signal(mg);
+                if (b.host_report) {
+                    __threadfence();
+                    for (uint32_t i = lane; i < b.zero_words; i += 32) b.host_report[i] = ((volatile unsigned long long *)b.counters)[i];
+                }
             }
         }
     }

@@ -561,7 +561,7 @@ def test_compact_read_back_expands_to_the_same_results(tmp_path):
         std = t.ProbeLits(lits)
         for off32 in (False, True):
             off_buf = np.full(n + 1, 0xdeadbeef, dtype=np.uint32 if off32 else np.uint64)
-            raw = t.ProbeLitsToHost(lits, off_out=off_buf, compact_self=True, off32=off32)
+            raw = t.ProbeLitsToHost(lits, impl_cap=std.info["n_implied"] + 16, off_out=off_buf, compact_self=True, off32=off32)
             assert (raw.flag & 0x80).any()
             if kind == "3sat":
                 assert raw.info["n_implied"] == 0 and (off_buf[:n] == 0xdeadbeef).all()   # nothing stored: offsets never travel
