@@ -109,6 +109,8 @@ typedef struct {
     /* the order-independent parts, comparable with the reference run on the same items: literals put on the trails of the
      * items that reached a fixpoint (= n_implied of a batch of probes), and props_ref restricted to those items */
     uint64_t assignments_ok, props_ref_ok;
+    uint64_t hot_rows;         /* rows left unwalked because they were several times longer than everything the probe had walked so far
+                                  (the earlier members were re-walked instead; DESIGN.md "hot rows") */
 } bbcp_batch_info;
 
 typedef struct {

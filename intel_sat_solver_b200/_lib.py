@@ -21,7 +21,7 @@ class BatchInfo(C.Structure):
                 ("triage_ms", C.c_float), ("deep_ms", C.c_float), ("block_ms", C.c_float), ("mid_ms", C.c_float), ("n_mid", C.c_uint64),
                 ("compact_ms", C.c_float), ("merge_ms", C.c_float),
                 ("adopted", C.c_uint64), ("adopt_lits", C.c_uint64), ("inherited", C.c_uint64), ("assignments", C.c_uint64), ("bcps", C.c_uint64),
-                ("assignments_ok", C.c_uint64), ("props_ref_ok", C.c_uint64)]
+                ("assignments_ok", C.c_uint64), ("props_ref_ok", C.c_uint64), ("hot_rows", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -266,6 +266,27 @@ bool upload_db(bbcp_handle *h, const std::vector<uint8_t> &varinfo, bool with_or
         drain_peers(h);   // a peer may still be reading the old bitmaps (last merge)
         cudaMemsetAsync(h->d_bitmaps.p, 0, 2 * stride * 4, h->stream);   // keep the arrival flags: they are monotonic epochs
     }
+    // L2 persistence window (measured in round 2, OFF by default: BBCP_L2_WINDOW=hdr|slots|litinfo): keep one array of the
+    // database resident in the set-aside part of the L2 for every kernel of this stream
+    if (const char *w = getenv("BBCP_L2_WINDOW")) {
+        DevBuf *buf = !strcmp(w, "hdr") ? &h->d_hdr : !strcmp(w, "slots") ? &h->d_slots : !strcmp(w, "litinfo") ? &h->d_litinfo : nullptr;
+        int max_win = 0, max_persist = 0;
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+        if (buf && buf->p && max_win > 0 && max_persist > 0) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            const size_t bytes = std::min<size_t>(buf->bytes, (size_t)max_win);
+            attr.accessPolicyWindow.base_ptr = buf->p;
+            attr.accessPolicyWindow.num_bytes = bytes;
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaGetLastError();
+        }
+    }
     if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "upload sync")) return false;
     h->l0_dirty = false;
     h->bitmaps_dirty = false;
@@ -401,6 +422,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     // lanes per probe (bbcp_propagate.cuh): a full warp. Narrower groups were measured and rejected, see DESIGN.md
     const int width = 32;
     uint32_t cap = opts.small_trail ? pow2_at_least(opts.small_trail) : 512u;
+    if (!opts.small_trail) if (const char *e = getenv("BBCP_SMALL_TRAIL")) cap = pow2_at_least((uint32_t)atoi(e));
     if (cap > 8192) cap = 8192;
     while (small_smem_bytes(cap, width) > 200 * 1024 && cap > 32) cap >>= 1;
     uint32_t cap_mid = opts.mid_trail ? pow2_at_least(opts.mid_trail) : 8192;
@@ -650,6 +672,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     bi.assignments_ok = h->h_misc[C_ASSIGN_OK];
     bi.props_ref_ok = h->h_misc[C_PROPS_REF_OK];
     bi.bcps = h->h_misc[C_BCPS];
+    bi.hot_rows = h->h_misc[C_HOT_ROWS];
     // bytes model: triage = 1 B of literal facts + 1 B flag + 4 B size per item (+ 4 B literal for
     // probe lists, + 16 B offsets more for cubes); propagation = row headers, row slots, clause units, stored
     // implied literals (kernel counters) + the per-item record (flag, size, position) of the queued items;
@@ -1028,7 +1051,7 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
         tot.n_large += bi.n_large; tot.n_mid += bi.n_mid; tot.props_all += bi.props_all; tot.props_ref += bi.props_ref; tot.slots += bi.slots;
         tot.clause_fetches += bi.clause_fetches; tot.kernel_bytes += bi.kernel_bytes; tot.triage_bytes += bi.triage_bytes; tot.n_deep += bi.n_deep;
         tot.adopted += bi.adopted; tot.adopt_lits += bi.adopt_lits; tot.inherited += bi.inherited; tot.assignments += bi.assignments; tot.bcps += bi.bcps;
-        tot.assignments_ok += bi.assignments_ok; tot.props_ref_ok += bi.props_ref_ok;
+        tot.assignments_ok += bi.assignments_ok; tot.props_ref_ok += bi.props_ref_ok; tot.hot_rows += bi.hot_rows;
         tot.kernel_ms += bi.kernel_ms; tot.total_ms += bi.total_ms; tot.launches += bi.launches; tot.triage_ms += bi.triage_ms;
         tot.deep_ms += bi.deep_ms; tot.block_ms += bi.block_ms; tot.mid_ms += bi.mid_ms; tot.compact_ms += bi.compact_ms; tot.tier1_ms += bi.tier1_ms;
     }

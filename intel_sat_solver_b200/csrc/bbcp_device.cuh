@@ -33,7 +33,7 @@ struct DbView {
 constexpr uint8_t LI_TRUE_L0 = 1, LI_FALSE_L0 = 2, LI_MAPPED = 4, LI_HAS_BIN = 8, LI_NONEMPTY = 16;
 constexpr uint32_t LEN_SELF = 0x80000000u;   // len[] flag: the implied set is the item's own literal (not stored)
 
-enum Counter { C_PROPS_ALL = 0, C_PROPS_REF, C_SLOTS, C_CLAUSE_FETCH, C_BYTES, C_LARGE, C_MID, C_OK, C_CONFLICT, C_SKIPPED, C_ADOPTED, C_ADOPT_LITS, C_INHERITED, C_PROPS_REF_OK, C_ASSIGN, C_ASSIGN_OK, C_BCPS, C_N };
+enum Counter { C_PROPS_ALL = 0, C_PROPS_REF, C_SLOTS, C_CLAUSE_FETCH, C_BYTES, C_LARGE, C_MID, C_OK, C_CONFLICT, C_SKIPPED, C_ADOPTED, C_ADOPT_LITS, C_INHERITED, C_PROPS_REF_OK, C_ASSIGN, C_ASSIGN_OK, C_BCPS, C_HOT_ROWS, C_N };
 
 struct BatchView {
     // input: cubes (external literals, CSR); or, when cube_off == nullptr, a list of probe literals

@@ -36,6 +36,7 @@
 #include "bbcp_propagate.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace bbcp {
 
@@ -64,8 +65,8 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // Result of one probe of the first tier: flag, implied set (sorted in shared memory, written to the pool as
 // external literals) or hand-over to the second tier.
 template <class G>
-__device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, const Item &it, int res, uint32_t tail,
-                             WorkCounters &wc)
+__device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, const Item &it, int res, uint32_t tail, uint32_t nmem,
+                             WorkCounters &wc, DeferredFlags &df)
 {
     const int lane = G::lane();
     if (res == 2) st.template wipe<G>(); else st.template cleanup<G>(tail);
@@ -83,24 +84,28 @@ __device__ void finish_small(const BatchView &b, SmemState &st, uint64_t item, c
         if (b.opts & OPT_IMPLIED) {
             uint32_t n2 = 1;
             while (n2 < tail) n2 <<= 1;
-            for (uint32_t i = lane; i < n2; i += G::width) st.trail[i] = i < tail ? (st.trail[i] & TRAIL_LIT) : 0xffffffffu;
+            // (second-walk entries are not members: they sort behind the set)
+            for (uint32_t i = lane; i < n2; i += G::width) {
+                const uint32_t ent = i < tail ? st.trail[i] : TRAIL_RESCAN;
+                st.trail[i] = (ent & TRAIL_SKIP) != TRAIL_RESCAN ? (ent & TRAIL_LIT) : 0xffffffffu;
+            }
             G::sync();
             if (tail > 1) bitonic_sort<G>(st.trail, n2);
-            off = out_alloc<G>(b, tail);
+            off = out_alloc<G>(b, nmem);
             if (off == ~0ull) { flag = FLAG_OUT_OVERFLOW; off = 0; }
             else {
                 // the pool holds INTERNAL literals (ascending = ascending variable): other probes adopt the set as it is
                 // (expand_closures); k_scan_gather turns it into external literals on its way to the canonical place
-                len = tail;
-                for (uint32_t i = lane; i < tail; i += G::width) b.out_lits[off + i] = (int32_t)st.trail[i];
-                wc.bytes += 4ull * tail;
+                len = nmem;
+                for (uint32_t i = lane; i < nmem; i += G::width) b.out_lits[off + i] = (int32_t)st.trail[i];
+                wc.bytes += 4ull * nmem;
             }
         }
     }
-    publish_result<G>(b, item, flag, len, off);
+    df.template add<G>(b, item, flag, len, off);
     wc.n_ok += flag == FLAG_OK;
     wc.n_conf += flag == FLAG_CONFLICT;
-    if (flag != FLAG_OVERFLOW) wc.end_item(flag == FLAG_OK, tail, true);   // (a probe handed on is counted by the tier that finishes it)
+    if (flag != FLAG_OVERFLOW) wc.end_item(flag == FLAG_OK, nmem, true);   // (a probe handed on is counted by the tier that finishes it)
     G::sync();
 }
 
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
 // (bbcp_propagate.cuh), SMALL_THREADS / W probes in flight per CTA.
 template <int W>
 __global__ void __launch_bounds__(SMALL_THREADS)
-k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t cap)
+k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t cap, const uint32_t stage_rows)
 {
     using G = Grp<W>;
     extern __shared__ uint32_t smem[];
@@ -274,13 +279,19 @@ k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t
     const uint32_t ndeep = *b.deep_count;
     if ((uint64_t)blockIdx.x * GROUPS >= ndeep) return;
     const uint32_t hs = 1u << log_hs;
-    const uint32_t per_grp = hs + cap + cap / 2;  // words: hash, trail, tslot (u16)
+    const uint32_t per_grp = hs + cap + cap / 2 + (stage_rows ? 2 * (STAGE_SLOTS + 2) + 4 : 0);  // words: hash, trail, tslot (u16) [, staging buffer, mbarrier]
     SmemState st;
     st.hash = smem + grp * per_grp;
     st.trail = st.hash + hs;
     st.tslot = reinterpret_cast<uint16_t *>(st.trail + cap);
     st.log_hs = log_hs;
     st.cap = cap;
+    if (stage_rows) {
+        st.stage = reinterpret_cast<uint2 *>(st.trail + cap + cap / 2);      // (hs, cap multiples of 32 words: 16-byte aligned)
+        st.stage_bar = reinterpret_cast<unsigned long long *>(st.stage + STAGE_SLOTS + 2);
+        if (lane == 0) mbar_init(st.stage_bar);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (uint32_t i = lane; i < hs; i += W) st.hash[i] = 0;
     G::sync();
 
@@ -292,6 +303,7 @@ k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t
     constexpr uint32_t ORDER_CHUNK = 8;
     unsigned pending = 0;
     uint32_t mine = 0;
+    DeferredFlags df;
     for (;;) {
         uint64_t it_idx;
         if (b.order) {
@@ -329,13 +341,14 @@ k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t
         else if (f == FLAG_CONFLICT) res = 1;
         else {
             st.template cleanup<G>(tl.tail);
-            publish_result<G>(b, it_idx, (uint8_t)f, 0, 0);
+            df.template add<G>(b, it_idx, (uint8_t)f, 0, 0);
             ++wc.n_skip;
             G::sync();
             continue;
         }
-        finish_small<G>(b, st, it_idx, it, res, tl.tail, wc);
+        finish_small<G>(b, st, it_idx, it, res, tl.tail, tl.members(), wc, df);
     }
+    df.template flush<G>(b);
     wc.template flush<G>(b.counters);
 }
 
@@ -343,7 +356,7 @@ k_deep(const DbView db, const BatchView b, const uint32_t log_hs, const uint32_t
 // Probes that outgrew the shared-memory state. Same propagation code, state in a per-group slab (GhashState).
 // The implied set is written to the pool UNSORTED as internal literals and the item is queued for k_sort_sets.
 template <int W>
-__global__ void __launch_bounds__(MID2_THREADS)
+__global__ void __launch_bounds__(MID2_THREADS, 4)
 k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_hs, const uint32_t cap)
 {
     using G = Grp<W>;
@@ -1462,7 +1475,11 @@ void build_order_device(const DbView &db, uint32_t nl, uint8_t *d_height, uint32
 static uint32_t ilog2(uint32_t x) { uint32_t l = 0; while ((1u << l) < x) ++l; return l; }
 
 // first tier: (hash 2*cap + trail cap + slot indices cap/2) words per probe, SMALL_THREADS / W probes per CTA
-size_t small_smem_bytes(uint32_t cap, int width) { return (size_t)(SMALL_THREADS / width) * (2 * cap + cap + cap / 2) * 4; }
+static bool stage_rows_enabled() { static const bool on = getenv("BBCP_TMA_ROWS") != nullptr && atoi(getenv("BBCP_TMA_ROWS")) != 0; return on; }
+size_t small_smem_bytes(uint32_t cap, int width)
+{
+    return (size_t)(SMALL_THREADS / width) * (2 * cap + cap + cap / 2 + (stage_rows_enabled() ? 2 * (STAGE_SLOTS + 2) + 4 : 0)) * 4;
+}
 
 template <int W> static int small_bps_w(uint32_t cap)
 {
@@ -1505,7 +1522,7 @@ void launch_small(const DbView &db, const BatchView &b, uint32_t cap, int width,
 {
     const size_t smem = small_smem_bytes(cap, width);
     const uint32_t lh = ilog2(2 * cap);
-    launch_pdl(k_deep<32>, dim3(blocks), dim3(SMALL_THREADS), smem, s, pdl, db, b, lh, cap);
+    launch_pdl(k_deep<32>, dim3(blocks), dim3(SMALL_THREADS), smem, s, pdl, db, b, lh, cap, stage_rows_enabled() ? 1u : 0u);
 }
 
 size_t mid_slab_words_per_group(uint32_t cap) { return (size_t)2 * cap + cap; }

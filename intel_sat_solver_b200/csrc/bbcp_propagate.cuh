@@ -67,11 +67,34 @@ struct Grp {
 };
 
 // ---------------------------------------------------------------- per-probe state, first tier (shared memory)
+// Bulk-async staging of long rows (the "TMA stages hot watch blocks" of the north star), measured in round 2 and OFF by
+// default (BBCP_TMA_ROWS=1 turns it on; profiles/r02): when a step walks one long row, its slots come into shared memory
+// STAGE_SLOTS at a time with ONE cp.async.bulk (UBLKCP in SASS) completing on an mbarrier, instead of eight 8-byte LDGs
+// per lane. The walk is bound by the two hash look-ups per slot, not by fetching the slots, and the 2 KB per warp cost a
+// resident CTA per SM.
+constexpr uint32_t STAGE_SLOTS = 256, STAGE_MIN = 512;
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar))); }
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
 struct SmemState {
     uint32_t *hash;    // [1 << log_hs] true literals, 0 = empty
     uint32_t *trail;   // [cap]
     uint16_t *tslot;   // [cap] hash slot of each trail entry (for the O(|trail|) clean-up)
     uint32_t log_hs, cap;
+    uint2 *stage = nullptr;               // [STAGE_SLOTS + 2] staging buffer of this warp (16-byte aligned), or nullptr
+    unsigned long long *stage_bar = nullptr;
+    uint32_t stage_phase = 0;
 
     __device__ __forceinline__ uint32_t h(uint32_t var) const { return (var * 0x9E3779B1u) >> (32 - log_hs); }
     // 0 unassigned, 1 true, 2 false
@@ -102,7 +125,7 @@ struct SmemState {
     __device__ __forceinline__ void tset(uint32_t i, uint32_t lit, uint32_t slot) { trail[i] = lit; tslot[i] = (uint16_t)slot; }
     template <class G> __device__ __forceinline__ void cleanup(uint32_t tail)
     {
-        for (uint32_t i = G::lane(); i < tail; i += G::width) hash[tslot[i]] = 0;
+        for (uint32_t i = G::lane(); i < tail; i += G::width) { const uint32_t s = tslot[i]; if (s != 0xffffu) hash[s] = 0; }   // (0xffff: a second-walk entry, it owns no slot)
         G::sync();
     }
     // after an overflow some table entries have no trail entry: wipe everything
@@ -270,7 +293,7 @@ struct WorkCounters {
     // the reference's counters: Assign calls, BCP() calls, and m_Implications restricted to the probes that
     // reach a fixpoint (the only part that does not depend on the propagation order)
     unsigned long long assign = 0, assign_ok = 0, props_ref_ok = 0, mark_ref = 0;
-    uint32_t n_ok = 0, n_conf = 0, n_skip = 0, adopted = 0, inherited = 0, bcps = 0;
+    uint32_t n_ok = 0, n_conf = 0, n_skip = 0, adopted = 0, inherited = 0, bcps = 0, hot_rows = 0;
     __device__ __forceinline__ void begin_item() { mark_ref = props_ref; }
     // tail = literals on the trail when the item ended (0 from the warps of a CTA that do not own the tail)
     __device__ __forceinline__ void end_item(bool ok, uint32_t tail, bool propagated)
@@ -297,6 +320,7 @@ struct WorkCounters {
             if (assign_ok) atomicAdd(&c[C_ASSIGN_OK], assign_ok);
             if (props_ref_ok) atomicAdd(&c[C_PROPS_REF_OK], props_ref_ok);
             if (bcps) atomicAdd(&c[C_BCPS], (unsigned long long)bcps);
+            if (hot_rows) atomicAdd(&c[C_HOT_ROWS], (unsigned long long)hot_rows);
         }
     }
 };
@@ -305,8 +329,13 @@ struct WorkCounters {
 // GroupTail: one group owns the probe, the trail tail is a register. BlockTail: the warps of a CTA share one
 // probe, the tail and the conflict / overflow latches live in shared memory.
 struct GroupTail {
+    static constexpr bool HOT_ROWS = true;
     uint32_t tail;
     uint32_t nres = 0;   // TRAIL_RESCAN entries on the trail (not members of the implied set)
+    // hot rows (process_batch): ternary / long slots of the rows walked so far, "a TRAIL_SKIP set is on the trail", and
+    // "the batch just walked skipped a hot row: the caller owes the second walks"
+    unsigned long long lsum = 0;
+    bool skipped_set = false, hot_pending = false;
     __device__ __forceinline__ uint32_t get() const { return tail; }
     __device__ __forceinline__ uint32_t members() const { return tail - nres; }
     __device__ __forceinline__ bool aborted() const { return false; }
@@ -358,7 +387,10 @@ struct GroupTail {
 };
 
 struct BlockTail {
-    uint32_t *ctl;  // shared: [0] tail, [1] conflict latch, [2] overflow latch, [8] TRAIL_RESCAN entries on the trail
+    static constexpr bool HOT_ROWS = false;   // (the CTA tiers hold the large probes: their rows are walked as they are)
+    uint32_t *ctl;
+    unsigned long long lsum = 0;
+    bool skipped_set = false, hot_pending = false;  // shared: [0] tail, [1] conflict latch, [2] overflow latch, [8] TRAIL_RESCAN entries on the trail
     __device__ __forceinline__ uint32_t get() const { return *(volatile uint32_t *)&ctl[0]; }
     // Warp-uniform by a vote: the latches are written by OTHER warps at any time, and the lanes of a warp do not
     // necessarily read them in the same cycle; a warp whose lanes disagreed here would split -- some lanes leave
@@ -426,6 +458,11 @@ __device__ __forceinline__ int value_of(const DbView &db, const S &st, uint32_t 
     return v;
 }
 
+template <class S> __device__ __forceinline__ uint2 st_stage_slot(const S &, uint32_t) { return make_uint2(0, 0); }
+__device__ __forceinline__ uint2 st_stage_slot(const SmemState &st, uint32_t i) { return st.stage[i]; }
+template <class S> struct Staging { static constexpr bool available = false; };
+template <> struct Staging<SmemState> { static constexpr bool available = true; };
+
 // Judge a long clause (>= 4 literals) from scratch: TopiBcp.cc:262-367 without the watch bookkeeping.
 // Returns the literal to imply (0 = none); sets confl when every literal is false.
 template <class S>
@@ -484,6 +521,26 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_
     wc.props_ref += __popc(G::ballot(nonempty && mode != TRAIL_RESCAN));
     wc.props_all += __popc(G::ballot(in && mode != TRAIL_RESCAN));
     if (mode != 0) { hd.x += (hd.y + 1u) >> 1; hd.y = 0; }
+    if (T::HOT_ROWS && !bins_only) {
+        // HOT ROW. The ternary / long part of the row of a literal that occurs in very many clauses (a power-law instance: a
+        // million) is walked by every probe that falsifies it, although the probe has assigned a handful of literals.
+        // A clause of that row can only be unit if ANOTHER of its literals is false: one assigned later sees this literal
+        // when its own row is walked; one assigned earlier is given a second walk (TRAIL_RESCAN) now. So when the row is
+        // several times longer than all rows walked so far together, it is not walked (its binary part always is) and the
+        // members before this batch are re-walked instead. One such row per batch (the batch-mates are walked in this very
+        // call and see the literal), and not after a TRAIL_SKIP adoption (those members are never walked).
+        const uint32_t L = (in && mode != TRAIL_SKIP) ? hd.z + hd.w : 0u;
+        const bool cand = !tl.skipped_set && (mode == 0 || mode == TRAIL_CLOSED) && L >= 256u && (unsigned long long)L > 4ull * (tl.lsum + 64ull);
+        uint32_t key = cand ? ((min(L, 0x03ffffffu) << 5) | (uint32_t)lane) : 0u;
+#pragma unroll
+        for (int d = W / 2; d; d >>= 1) key = max(key, G::shfl_xor(key, d));
+        uint32_t sum = (mode != TRAIL_RESCAN) ? L : 0u;
+#pragma unroll
+        for (int d = W / 2; d; d >>= 1) sum += G::shfl_xor(sum, d);
+        tl.lsum += sum;
+        if (key && (int)(key & 31u) == lane) { hd.z = 0; hd.w = 0; }
+        if (key) tl.hot_pending = true;
+    }
     const uint32_t nb2 = (hd.y + 1u) >> 1;
     const uint32_t cnt = bins_only ? nb2 : nb2 + hd.z + hd.w;
     uint32_t incl = cnt;
@@ -497,9 +554,26 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_
     wc.slots += total;
     wc.bytes += 16ull * __popc(G::ballot(in && mode != TRAIL_SKIP)) + __popc(G::ballot(in && mode == TRAIL_SKIP)) + 8ull * total;   // headers (or one byte of litinfo) + slots
 
+    // one long row and a staging buffer: the slots come through shared memory, STAGE_SLOTS per bulk copy
+    bool staged = false;
+    uint32_t stage_first = 0;     // slot index (within the row) of stage[0]
+    if constexpr (Staging<S>::available) staged = st.stage != nullptr && B == 1 && total >= STAGE_MIN;
     BBCP_WATCH_BEGIN();
     for (uint32_t base = 0; base < total; base += W) {
         BBCP_WATCH(total, base);
+        if constexpr (Staging<S>::available) {
+            if (staged && base % STAGE_SLOTS == 0) {
+                // (the row lives at 8-byte granularity, the bulk copy wants 16: start one slot early if need be)
+                const uint32_t row0 = G::shfl(hd.x, 0) + base;
+                const uint32_t lead = row0 & 1u;
+                const uint32_t n = min(STAGE_SLOTS, total - base) + lead;
+                G::sync();     // everybody is done with the previous chunk
+                if (lane == 0) bulk_load(st.stage, db.slots + (row0 - lead), ((n + 1u) & ~1u) * 8u, st.stage_bar);
+                mbar_wait(st.stage_bar, st.stage_phase);
+                st.stage_phase ^= 1u;
+                stage_first = base - lead;   // stage[i] = row slot stage_first + i  (stage_first may be "-1" = 0xffffffff: lead slot)
+            }
+        }
         const uint32_t g = base + lane;
         const bool active = g < total;
         // owner row of slot g: the largest lane i with excl_i <= g
@@ -519,7 +593,8 @@ __device__ int process_batch(const DbView &db, S &st, T &tl, uint32_t e, uint32_
         uint32_t fetched16 = 0;
         if (active) {
             BBCP_CHECK(r_start + k < db.n_slots, "slot %u + %u of %u (lo %d total %u base %u)\n", r_start, k, db.n_slots, lo, total, base);
-            const uint2 s = __ldg(&db.slots[r_start + k]);
+            uint2 s;
+            if (staged) s = st_stage_slot(st, k - stage_first); else s = __ldg(&db.slots[r_start + k]);
             if (k < r_nb2) {
                 // binary clauses (TopiBcp.cc:207-246)
                 int v = value_of(db, st, s.x);
@@ -657,7 +732,7 @@ __device__ int expand_closures(const BatchView &b, S &st, T &tl, uint32_t e, uin
         // room for them)
         const bool skip = tier >= 2 && n >= 4u * t0 && 2ull * t0 + n <= st.cap;
         int r = closure_adopt<G>(b, st, tl, src, n, 0, G::width, skip ? TRAIL_SKIP : TRAIL_CLOSED);
-        if (!r && skip) r = tl.template append_rescan<G>(st, t0, head);
+        if (!r && skip) { r = tl.template append_rescan<G>(st, t0, head); tl.skipped_set = true; }
         if (r) return r;
         ++wc.adopted;
         wc.adopt_lits += n;
@@ -683,6 +758,12 @@ __device__ int propagate(const DbView &db, const BatchView &b, S &st, GroupTail 
         }
         const int r = process_batch<G>(db, st, tl, e, B, prune && first_step, wc);
         if (r) return r;
+        if (tl.hot_pending) {
+            // a hot row was left out: the members walked before this batch get their second walk
+            tl.hot_pending = false;
+            ++wc.hot_rows;
+            if (tl.template append_rescan<G>(st, head, head)) return 2;
+        }
         head += B;
     }
     return 0;
@@ -690,6 +771,33 @@ __device__ int propagate(const DbView &db, const BatchView &b, S &st, GroupTail 
 
 // A finished probe makes its result visible to the other probes of the launch (expand_closures): the set and its
 // position first, the flag last, each behind a fence.
+// Deferred form for the first tier, whose probes are a few microseconds long: the two fences of publish_result would be a
+// fifth of a probe's life (and a gpu-scope fence also drops the SM's L1 lines, which is where the hot rows live). The warp
+// writes set, size and position at once, keeps (item, flag) in a lane and publishes the flags of PUBLISH_BATCH finished probes
+// behind ONE fence. A flag that shows a little later only means that a neighbour propagates instead of adopting.
+constexpr uint32_t PUBLISH_BATCH = 8;
+struct DeferredFlags {
+    uint32_t item = 0, n = 0;     // lane k < n holds the k-th finished item
+    uint8_t flag = 0;
+    template <class G> __device__ __forceinline__ void flush(const BatchView &b)
+    {
+        if (!n) return;
+        if (b.reuse) __threadfence();     // every lane: the sets (and lane 0's sizes / positions) are out
+        G::sync();
+        if (G::lane() < (int)n) *(volatile uint8_t *)&b.flag[item] = flag;
+        n = 0;
+    }
+    template <class G> __device__ __forceinline__ void add(const BatchView &b, uint64_t it, uint8_t f, uint32_t len, unsigned long long off)
+    {
+        if (G::lane() == 0) {
+            b.len[it] = len; b.raw_off[it] = off;
+            if (len) atomicAdd(&b.tile_sum[it / SG_TILE], (unsigned long long)len);
+        }
+        if (G::lane() == (int)n) { item = (uint32_t)it; flag = f; }
+        if (++n == PUBLISH_BATCH) flush<G>(b);
+    }
+};
+
 template <class G>
 __device__ __forceinline__ void publish_result(const BatchView &b, uint64_t item, uint8_t flag, uint32_t len, unsigned long long off)
 {
