@@ -188,6 +188,11 @@ int bbcp_propagate_batch_device(bbcp_handle *h, const int32_t *d_lits, const uin
  * instance. *rounds = passes run, *units = failed literals turned into units; bbcp_level0_lits has the result. */
 int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds, uint64_t *units);
 
+/* the units bbcp_probe_to_fixpoint has derived so far (negations of failed literals), in derivation order: each one follows
+ * by unit propagation (RUP) from the clauses plus the units before it, which is the order a DRAT trace needs
+ * (TopiConflictAnalysis.cc:1117-1184 logs learnt units the same way). Copies up to cap, returns the count. */
+uint64_t bbcp_unit_log(const bbcp_handle *h, int32_t *out, uint64_t cap);
+
 /* products of the last all-literal pass with implied sets (bbcp_probe_all, or bbcp_probe_range with even bounds),
  * computed on the device ("next" row N4; not in the reference, defined on the per-probe implied sets the reference
  * would produce): necessary literals -- x implied by +v and by -v, so x is a unit -- as a bitmap over internal

@@ -47,6 +47,7 @@ _SIGS = {
     "bbcp_host_prepare": (C.c_int, [C.c_void_p]),
     "bbcp_get_db_info": (C.c_int, [C.c_void_p, C.POINTER(DbInfo)]),
     "bbcp_level0_lits": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "bbcp_unit_log": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "bbcp_host_row": (C.c_uint64, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
     "bbcp_host_order": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "bbcp_status": (C.c_int, [C.c_void_p]),

@@ -131,6 +131,7 @@ struct bbcp_handle {
     bool have_batch = false;
     uint64_t total_props = 0;
 
+    std::vector<int32_t> unit_log;   // failed-literal units in the order bbcp_probe_to_fixpoint derived them (each is RUP after the ones before)
     std::vector<int32_t> assumps;
     std::vector<int8_t> solve_val;   // per var after bbcp_solve: 0 unassigned, 1 true, -1 false (level > 0)
     bool solved = false;
@@ -920,6 +921,13 @@ uint64_t bbcp_level0_lits(const bbcp_handle *h, int32_t *out, uint64_t cap)
     return n;
 }
 
+uint64_t bbcp_unit_log(const bbcp_handle *h, int32_t *out, uint64_t cap)
+{
+    if (!h) return 0;
+    for (size_t i = 0; i < h->unit_log.size() && i < cap; ++i) out[i] = h->unit_log[i];
+    return h->unit_log.size();
+}
+
 uint64_t bbcp_host_row(const bbcp_handle *h, uint32_t ilit, uint32_t *out, uint64_t cap)
 {
     if (!h || !h->prepared || ilit >= h->db.hdr.size()) return 0;
@@ -1122,6 +1130,8 @@ int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds
         if (cube.empty()) break;
         total_units += cube.size();
         if (units_out) *units_out = total_units;
+        try { h->unit_log.insert(h->unit_log.end(), cube.begin(), cube.end()); }
+        catch (const std::bad_alloc &) { return h->fail(BBCP_ERR_ALLOC, "host allocation failed (unit log)"); }
         // the units join the clause stream either way, so that a later bbcp_finalize rebuilds the simplified database
         try {
             for (int32_t l : cube) { const int32_t c[2] = {l, 0}; h->db.add_words(c, 2); }

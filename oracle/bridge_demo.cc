@@ -6,9 +6,13 @@
 //      bridge: CToporWithGpuProbing<CTopor>, AddClause*, GpuProbe() [GPU: probing to a fixpoint + products,
 //              units fed back through AddClause / GetNextUnitClause], Solve(assumps)
 // and that the cube filter keeps every cube the reference finds satisfiable.
-// usage: bridge_demo <instance(.cnf | .bcnf)> [--cubes f.cubes]   -> one JSON line; exit 0 iff all answers agree
+// With --learnts the CPU solver's learnt clauses (SetCbNewLearntCls) flow into the GPU database and a GPU pass runs inside
+// the running Solve every 20 learnt clauses (units back through GetNextUnitClause); with --drat <file> every unit fed to the
+// CPU solver is logged as a DRAT text line in derivation order (tests/test_bridge.py re-checks each one by unit propagation).
+// usage: bridge_demo <instance(.cnf | .bcnf)> [--cubes f.cubes] [--learnts] [--drat f]   -> one JSON line; exit 0 iff all answers agree
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <string>
 #include <vector>
 
@@ -37,15 +41,22 @@ int main(int argc, char **argv)
     if (bcp_read_instance(argv[1], &ins) != 0) { fprintf(stderr, "cannot read %s\n", argv[1]); return 3; }
     const auto clauses = clauses_of(ins);
     std::vector<std::vector<int32_t>> queries;
-    if (argc >= 4 && !strcmp(argv[2], "--cubes")) {
-        bcp_cubes cubes;
-        memset(&cubes, 0, sizeof(cubes));
-        if (bcp_read_cubes(argv[3], &cubes) != 0) { fprintf(stderr, "cannot read %s\n", argv[3]); return 3; }
-        for (uint64_t i = 0; i < cubes.ncubes; ++i) queries.emplace_back(cubes.lits + cubes.off[i], cubes.lits + cubes.off[i + 1]);
+    bool learnts = false;
+    std::ofstream drat;
+    for (int a = 2; a < argc; ++a) {
+        if (!strcmp(argv[a], "--cubes") && a + 1 < argc) {
+            bcp_cubes cubes;
+            memset(&cubes, 0, sizeof(cubes));
+            if (bcp_read_cubes(argv[++a], &cubes) != 0) { fprintf(stderr, "cannot read %s\n", argv[a]); return 3; }
+            for (uint64_t i = 0; i < cubes.ncubes; ++i) queries.emplace_back(cubes.lits + cubes.off[i], cubes.lits + cubes.off[i + 1]);
+        } else if (!strcmp(argv[a], "--learnts")) learnts = true;
+        else if (!strcmp(argv[a], "--drat") && a + 1 < argc) drat.open(argv[++a]);
     }
     if (queries.empty()) queries.push_back({});
 
     bbcp::CToporWithGpuProbing<Ref> bridge;
+    if (learnts) bridge.IngestLearntClauses(Topor::TStopTopor::VAL_CONTINUE, 8, 20);
+    if (drat.is_open()) bridge.SetDratLog(&drat);
     for (const auto &c : clauses) bridge.AddClause(c);
     const long fed = bridge.GpuProbe();
     if (fed == -2) { fprintf(stderr, "engine error: %s\n", bridge.Gpu().GetStatusExplanation().c_str()); return 4; }
@@ -69,7 +80,9 @@ int main(int argc, char **argv)
         unsat += a == Topor::TToporReturnVal::RET_UNSAT;
         if (!alive[qi]) { ++filtered; filter_wrong += a != Topor::TToporReturnVal::RET_UNSAT; }
     }
-    printf("{\"queries\": %zu, \"agree\": %zu, \"sat\": %zu, \"unsat\": %zu, \"units_fed\": %ld, \"cubes_filtered\": %zu, \"filter_wrong\": %zu}\n",
-           queries.size(), agree, sat, unsat, fed, filtered, filter_wrong);
+    if (drat.is_open()) drat.close();
+    printf("{\"queries\": %zu, \"agree\": %zu, \"sat\": %zu, \"unsat\": %zu, \"units_fed\": %ld, \"cubes_filtered\": %zu, \"filter_wrong\": %zu, \"learnts_taken\": %llu, \"in_solve_passes\": %llu, \"units_total\": %llu}\n",
+           queries.size(), agree, sat, unsat, fed, filtered, filter_wrong, (unsigned long long)bridge.LearntsTaken(), (unsigned long long)bridge.InSolvePasses(),
+           (unsigned long long)bridge.UnitsFed());
     return agree == queries.size() && filter_wrong == 0 ? 0 : 1;
 }
