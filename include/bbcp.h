@@ -63,6 +63,11 @@ enum {
                                   costs on the way back are that one literal and its offset). bbcp_probe_lits_to_host then
                                   copies offsets back only from the first chunk on that stores a set: when info.n_implied
                                   == 0 the offsets are all zero and are not written at all */
+    BBCP_OPT_BINARY_ONLY = 256u, /* propagate through the binary clauses only: the closure of the binary implication graph
+                                  (what bbcp_probe_hbr compares the full pass with) */
+    BBCP_OPT_STORE_SETS = 512u, /* without BBCP_OPT_IMPLIED: keep the implied sets on the device for the duration of the batch all the
+                                  same, so that probes adopt each other's finished results (closure reuse); only flags and bitmaps
+                                  come back. Costs the pool memory, saves most of the propagation on deep instances */
     BBCP_OPT_OFF32 = 4u        /* produce impl_off as uint32 (fetch with bbcp_fetch_implied32): halves the offset
                                   read-back; the batch fails with BBCP_ERR_ARG if it implies >= 2^32 literals */
 };
@@ -209,6 +214,13 @@ int bbcp_probe_products(bbcp_handle *h, uint32_t *necessary, uint64_t *n_necessa
  * O(database) per item, on the device. */
 int bbcp_check_fixpoints(bbcp_handle *h, uint64_t first_item, uint64_t count, uint64_t stride, uint64_t *violations, uint64_t *clauses_checked,
                          uint64_t *items_checked);
+
+/* hyper-binary resolvents ("next" row N4; not in the reference, defined on the implied sets the reference would produce): for
+ * every literal v whose probe reaches a fixpoint, every x implied by v but not through binary clauses alone, as pairs
+ * (v, x) of external literals in no particular order -- the binary clause (not-v or x) follows from the database and is new
+ * to its binary implication graph. Runs an all-literal pass and a binary-clauses-only pass on the device. *n_pairs may exceed
+ * pair_cap (then only pair_cap pairs were stored). */
+int bbcp_probe_hbr(bbcp_handle *h, int32_t *pairs /* 2 * pair_cap */, uint64_t pair_cap, uint64_t *n_pairs);
 
 /* ---- results of the last batch, device -> caller buffers */
 int bbcp_fetch_flags(bbcp_handle *h, uint8_t *flag /* n */);

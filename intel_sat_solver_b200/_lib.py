@@ -62,6 +62,7 @@ _SIGS = {
     "bbcp_probe_to_fixpoint": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "bbcp_probe_products": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "bbcp_check_fixpoints": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "bbcp_probe_hbr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "bbcp_fetch_flags": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bbcp_fetch_implied": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bbcp_fetch_implied32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -435,7 +435,10 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     const bool implied = (opts.flags & BBCP_OPT_IMPLIED) != 0;
     const bool off32 = (opts.flags & BBCP_OPT_OFF32) != 0;
     const bool want_kernel_times = (opts.flags & BBCP_OPT_KERNEL_TIMES) != 0 || !(h->lean & 2);
-    uint64_t out_cap = implied ? (opts.out_capacity ? opts.out_capacity : std::max<uint64_t>({(uint64_t)1 << 20, 4 * n, h->out_cap_hint + h->out_cap_hint / 4})) : 0;
+    // BBCP_OPT_STORE_SETS: the implied sets are kept in the pool for closure reuse (a probe adopts the finished sets of the
+    // literals it reaches) although the caller does not want them: flags + bitmaps come back, nothing is compacted
+    const bool store = implied || (opts.flags & BBCP_OPT_STORE_SETS) != 0;
+    uint64_t out_cap = store ? (opts.out_capacity ? opts.out_capacity : std::max<uint64_t>({(uint64_t)1 << 20, 4 * n, h->out_cap_hint + h->out_cap_hint / 4})) : 0;
 
     DbView dbv = db_view(h);
     LargeState ls{nullptr, nullptr};
@@ -459,7 +462,7 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     b.off_base = h->off_base;
     b.tile_sum = h->d_tiles.as<unsigned long long>();
     b.zero_words = MISC_WORDS64;
-    b.opts = opts.flags;
+    b.opts = opts.flags | (store ? (uint32_t)BBCP_OPT_IMPLIED : 0u);
     // rows older than the level-0 facts: a ternary clause may have shrunk to a binary one, so the triage cannot tell from the
     // row shape which probes imply only themselves
     if (h->l0_dirty) b.opts |= BBCP_OPT_NO_LEN_PRUNE;
@@ -1115,7 +1118,8 @@ int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds
     std::vector<int32_t> cube, lits;
     for (; max_rounds == 0 || round < max_rounds; ++round) {
         bbcp_opts o;
-        memset(&o, 0, sizeof(o));   // flags and bitmaps only
+        memset(&o, 0, sizeof(o));   // flags and bitmaps only; the sets stay on the device for closure reuse
+        o.flags = BBCP_OPT_STORE_SETS;
         if ((rc = bbcp_clear_bitmaps(h)) != BBCP_OK) return rc;
         if ((rc = bbcp_probe_all(h, &o, nullptr)) != BBCP_OK) return rc;
         unit.assign(bbcp_bitmap_words(h), 0);
@@ -1230,6 +1234,47 @@ int bbcp_check_fixpoints(bbcp_handle *h, uint64_t first_item, uint64_t count, ui
     if (violations) *violations = res[0];
     if (clauses_checked) *clauses_checked = res[1];
     if (items_checked) *items_checked = res[2];
+    return BBCP_OK;
+}
+
+// Hyper-binary resolvents of an all-literal pass (survey "next" row N4; not in the reference: defined on the implied sets
+// the reference would produce). Two passes on the device -- the full one and one through the binary clauses only -- and the
+// per-probe set difference.
+int bbcp_probe_hbr(bbcp_handle *h, int32_t *pairs, uint64_t pair_cap, uint64_t *n_pairs)
+{
+    if (n_pairs) *n_pairs = 0;
+    int rc = need_final(h);
+    if (rc) return rc;
+    if (pair_cap && !pairs) return h->fail(BBCP_ERR_ARG, "bbcp_probe_hbr: null pair buffer");
+    if (h->l0_dirty) return h->fail(BBCP_ERR_STATE, "bbcp_probe_hbr: level-0 facts are newer than the rows (bbcp_finalize first)");
+    cudaSetDevice(h->device);
+    const uint64_t n = 2ull * (uint64_t)h->db.max_var;
+    bbcp_opts o;
+    memset(&o, 0, sizeof(o));
+    o.flags = BBCP_OPT_IMPLIED;
+    h->rb = 1;                                  // the full pass keeps its results in the second result set
+    rc = run_batch(h, nullptr, nullptr, 0, n, &o, nullptr);
+    h->rb = 0;
+    if (rc != BBCP_OK) return rc;
+    o.flags = BBCP_OPT_IMPLIED | BBCP_OPT_BINARY_ONLY;
+    rc = run_batch(h, nullptr, nullptr, 0, n, &o, nullptr);
+    if (rc != BBCP_OK) return rc;
+    if (!h->d_products.reserve(16 + pair_cap * 8)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (hyper-binary resolvents)");
+    cudaMemsetAsync(h->d_products.p, 0, 16, h->stream);
+    unsigned long long *count = h->d_products.as<unsigned long long>();
+    int32_t *d_pairs = reinterpret_cast<int32_t *>(count + 2);
+    launch_hbr(h->rs[1].flag.as<uint8_t>(), h->rs[1].off.as<uint64_t>(), h->rs[1].impl.as<int32_t>(), h->rs[0].flag.as<uint8_t>(), h->rs[0].off.as<uint64_t>(),
+               h->rs[0].impl.as<int32_t>(), n, 0, d_pairs, pair_cap, count, h->sm_count, h->stream);
+    unsigned long long hc = 0;
+    cudaMemcpyAsync(&hc, count, 8, cudaMemcpyDeviceToHost, h->stream);
+    if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "hyper-binary resolvents")) return BBCP_ERR_CUDA;
+    const uint64_t ne = std::min<uint64_t>(hc, pair_cap);
+    if (ne) {
+        cudaMemcpyAsync(pairs, d_pairs, ne * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (!h->cuda_ok(cudaStreamSynchronize(h->stream), "hyper-binary resolvents")) return BBCP_ERR_CUDA;
+    }
+    if (n_pairs) *n_pairs = hc;     // may exceed pair_cap: call again with a larger buffer
+    h->have_batch = false;          // (the device holds the binary-only pass: not something to fetch as "the last batch")
     return BBCP_OK;
 }
 

@@ -87,6 +87,7 @@ constexpr uint32_t OPT_IMPLIED = 1u;
 constexpr uint32_t OPT_NO_LEN_PRUNE = 2u;
 constexpr uint32_t OPT_OFF32 = 4u;
 constexpr uint32_t OPT_COMPACT_SELF = 128u;
+constexpr uint32_t OPT_BINARY_ONLY = 256u;   // propagate through the binary clauses only (the binary-implication closure; bbcp_probe_hbr)
 constexpr uint8_t FLAG_SELF = 0x80;         // OPT_COMPACT_SELF: flag OK + "the implied set is the probe's own literal" (not stored)
 constexpr uint8_t FLAG_OK = 0, FLAG_CONFLICT = 1, FLAG_TRIVIAL_L0 = 2, FLAG_FALSE_L0 = 3, FLAG_UNMAPPED = 4;
 constexpr uint8_t FLAG_OVERFLOW = 250;      // internal: outgrew the first tier, queued for the second (global hash state)
@@ -135,6 +136,9 @@ void set_debug_buffer(unsigned long long *mapped);
 void build_order_device(const DbView &db, uint32_t nl, uint8_t *d_height, uint32_t *d_order, int sm_count, cudaStream_t s);
 bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s, bool pdl);
 int scan_gather_max_blocks(int sm_count);
+// hyper-binary resolvents: x in full[i] \ bin[i] for every item i that reached a fixpoint in both passes
+void launch_hbr(const uint8_t *flag_full, const uint64_t *off_full, const int32_t *impl_full, const uint8_t *flag_bin, const uint64_t *off_bin, const int32_t *impl_bin,
+                uint64_t n, uint64_t first, int32_t *pairs, unsigned long long cap, unsigned long long *count, int sm_count, cudaStream_t s);
 void launch_products(bool off32, const uint8_t *flag, const void *off, const int32_t *impl, uint64_t npairs, uint64_t var_base, uint32_t *necessary, int32_t *equiv,
                      unsigned long long equiv_cap, unsigned long long *counts, int sm_count, cudaStream_t s);
 struct MergeArgs {

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
     __shared__ unsigned int s_cnt[4];  // ok, skipped, props_ref
     __shared__ uint16_t s_lut[32];
     pdl_trigger();   // k_deep's CTAs may take their places; they wait for this grid to complete before they read anything
-    const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
+    const bool prune = !(b.opts & OPT_NO_LEN_PRUNE) || (b.opts & OPT_BINARY_ONLY);
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x < 32) {
         const uint32_t li = threadIdx.x;
@@ -538,7 +538,7 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
                         }
                         if (ra) break;
                     }
-                    if (process_batch<G>(db, st, tl, e, B, prune && end == 1, wc)) break;
+                    if (process_batch<G>(db, st, tl, e, B, (b.opts & OPT_BINARY_ONLY) || (prune && end == 1), wc)) break;
                     hcur += B;
                 }
                 if (lane == 0) ctl[7] = hcur;
@@ -590,7 +590,7 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
             // (CTA-uniform: a warp that got past this point may latch a conflict before a slower thread has looked)
             if (__syncthreads_or((vctl[1] | vctl[2]) != 0)) continue;   // the loop head sees the latch and stops
         }
-        const bool bins_only = prune && level_end == 1;
+        const bool bins_only = (b.opts & OPT_BINARY_ONLY) || (prune && level_end == 1);
         for (uint32_t bse = head + warp * 32; bse < level_end; bse += nwarps * 32) {
             const uint32_t B = min(32u, level_end - bse);
             const uint32_t e = lane < (int)B ? st.tget(bse + lane) : 0u;
@@ -1447,7 +1447,49 @@ __global__ void __launch_bounds__(256) k_order_scatter(const uint8_t *__restrict
     }
 }
 
+// ---------------------------------------------------------------- hyper-binary resolvents (survey "next" row N4)
+// x is implied by probe v, but not through binary clauses alone: (not-v or x) is a hyper-binary resolvent -- a binary
+// clause the database does not entail by its binary clauses, learnt for free from the probe. full = the implied sets of
+// an all-literal pass, bin = the same pass restricted to the binary clauses (OPT_BINARY_ONLY); both sorted by variable,
+// bin[i] a subset of full[i]. One warp per probe: the lanes take the literals of full[i] and binary-search bin[i].
+__global__ void __launch_bounds__(256) k_hbr(const uint8_t *__restrict__ flag_full, const uint64_t *__restrict__ off_full, const int32_t *__restrict__ impl_full,
+                                             const uint8_t *__restrict__ flag_bin, const uint64_t *__restrict__ off_bin, const int32_t *__restrict__ impl_bin,
+                                             const uint64_t n, const uint64_t first, int32_t *__restrict__ pairs, const unsigned long long cap,
+                                             unsigned long long *__restrict__ count)
+{
+    const uint64_t warp = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * 256) >> 5;
+    const int lane = lane_id();
+    for (uint64_t i = warp; i < n; i += nwarps) {
+        if (flag_full[i] != FLAG_OK || flag_bin[i] != FLAG_OK) continue;
+        const int32_t *A = impl_full + off_full[i], *B = impl_bin + off_bin[i];
+        const uint64_t na = off_full[i + 1] - off_full[i], nb = off_bin[i + 1] - off_bin[i];
+        if (na == nb) continue;
+        const uint64_t idx = first + i;
+        const int32_t pv = (int32_t)(idx / 2 + 1), probe = (idx & 1) ? -pv : pv;
+        for (uint64_t k = lane; k < na; k += 32) {
+            const int32_t x = A[k];
+            const int32_t ax = x < 0 ? -x : x;
+            uint64_t lo = 0, hi = nb;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                const int32_t y = B[mid];
+                if ((y < 0 ? -y : y) < ax) lo = mid + 1; else hi = mid;
+            }
+            if (lo < nb && B[lo] == x) continue;
+            const unsigned long long e = atomicAdd(count, 1ull);
+            if (e < cap) { pairs[2 * e] = probe; pairs[2 * e + 1] = x; }
+        }
+    }
+}
+
 }  // namespace
+
+void launch_hbr(const uint8_t *flag_full, const uint64_t *off_full, const int32_t *impl_full, const uint8_t *flag_bin, const uint64_t *off_bin, const int32_t *impl_bin,
+                uint64_t n, uint64_t first, int32_t *pairs, unsigned long long cap, unsigned long long *count, int sm_count, cudaStream_t s)
+{
+    const int blocks = (int)std::min<uint64_t>(std::max<uint64_t>((n + 7) / 8, 1), (uint64_t)sm_count * 8);
+    k_hbr<<<blocks, 256, 0, s>>>(flag_full, off_full, impl_full, flag_bin, off_bin, impl_bin, n, first, pairs, cap, count);
+}
 
 // d_height: 2 * nl bytes + 1028 bytes of scratch (ping-pong heights, changed flag, histogram); d_order: nl - 2 words
 void build_order_device(const DbView &db, uint32_t nl, uint8_t *d_height, uint32_t *d_order, int sm_count, cudaStream_t s)

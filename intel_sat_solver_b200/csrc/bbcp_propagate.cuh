@@ -756,7 +756,7 @@ __device__ int propagate(const DbView &db, const BatchView &b, S &st, GroupTail 
             const int r = expand_closures<G>(b, st, tl, e, B, head, tier, wc);
             if (r) return r;
         }
-        const int r = process_batch<G>(db, st, tl, e, B, prune && first_step, wc);
+        const int r = process_batch<G>(db, st, tl, e, B, (b.opts & OPT_BINARY_ONLY) || (prune && first_step), wc);
         if (r) return r;
         if (tl.hot_pending) {
             // a hot row was left out: the members walked before this batch get their second walk

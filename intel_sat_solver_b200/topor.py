@@ -26,6 +26,7 @@ OPT_MERGE = 16
 OPT_RENDEZVOUS = 32
 OPT_NO_REUSE = 64
 OPT_COMPACT_SELF = 128
+OPT_BINARY_ONLY = 256
 FLAG_SELF = 0x80
 
 
@@ -133,11 +134,11 @@ class BatchedTopor:
 
     @staticmethod
     def _opts(implied=True, small_trail=0, out_capacity=0, no_len_prune=False, mid_trail=0, off32=False, kernel_times=False,
-              merge=0, rendezvous=False, no_reuse=False, compact_self=False) -> Opts:
+              merge=0, rendezvous=False, no_reuse=False, compact_self=False, binary_only=False) -> Opts:
         """merge: 0, or the bitmap words owned by each rank (sharding.Shard.words_per_rank) to all-gather the slices in the batch"""
         return Opts((OPT_IMPLIED if implied else 0) | (OPT_NO_LEN_PRUNE if no_len_prune else 0) | (OPT_OFF32 if off32 else 0)
                     | (OPT_KERNEL_TIMES if kernel_times else 0) | (OPT_MERGE if merge else 0) | (OPT_RENDEZVOUS if rendezvous else 0)
-                    | (OPT_NO_REUSE if no_reuse else 0) | (OPT_COMPACT_SELF if compact_self else 0),
+                    | (OPT_NO_REUSE if no_reuse else 0) | (OPT_COMPACT_SELF if compact_self else 0) | (OPT_BINARY_ONLY if binary_only else 0),
                     small_trail, out_capacity, mid_trail, int(merge))
 
     def _fetch(self, info: BatchInfo, implied: bool, fetch: bool, off32: bool = False) -> BatchResult:
@@ -216,6 +217,16 @@ class BatchedTopor:
         o = self._opts(implied=implied, **kw)
         self._check(self._L.bbcp_propagate_batch(self._h, lits.ctypes.data, off.ctypes.data, off.size - 1, C.byref(o), C.byref(info)))
         return self._fetch(info, implied, fetch, kw.get("off32", False))
+
+    def ProbeHbr(self, pair_cap: int = 1 << 20) -> np.ndarray:
+        """Hyper-binary resolvents of an all-literal pass (bbcp_probe_hbr): an (m, 2) array of (v, x), sorted."""
+        n = C.c_uint64(0)
+        pairs = np.zeros((max(pair_cap, 1), 2), dtype=np.int32)
+        self._check(self._L.bbcp_probe_hbr(self._h, pairs.ctypes.data, pair_cap, C.byref(n)))
+        if n.value > pair_cap:
+            return self.ProbeHbr(int(n.value))
+        p = pairs[: n.value]
+        return p[np.lexsort((p[:, 1], p[:, 0]))] if p.size else p
 
     def CheckFixpoints(self, first: int = 0, count: int = 1 << 62, stride: int = 1) -> dict:
         """No-missed-implication check of the last batch's fixpoints on the device (bbcp_check_fixpoints)."""

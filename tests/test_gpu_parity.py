@@ -617,3 +617,47 @@ def test_no_missed_implication_checker(golden, tmp_path):
     dev[last] = dev[firsts]
     torch.cuda.synchronize()
     assert t.CheckFixpoints()["violations"] > 0
+
+
+def test_hyper_binary_resolvents_against_the_golden_implied_sets(golden):
+    """N4: (v, x) is reported iff x is in the REFERENCE's implied set of probe v (golden) and x is not reachable from v
+    through the binary clauses of the level-0-simplified database alone (a plain CPU closure over the engine's host rows)."""
+    total = 0
+    for name in ["fuzz_10", "fuzz_5", "fuzz_3", "regr_47", "regr_72", "regr_20", "hand_long", "ddtbug_32499"]:
+        g = lambda k: golden[f"{name}/{k}"]
+        t, rc = engine_for(g("words"))
+        assert rc == 0
+        got = {(int(a), int(b)) for a, b in t.ProbeHbr()}
+        nl = 2 * t.max_var + 2
+        succ = {}
+        for l in range(2, nl):
+            row = t.HostRow(l ^ 1).tolist()        # the row walked when l becomes true
+            succ[l] = row[3:3 + row[0]]
+        ext = lambda il: -(il >> 1) if il & 1 else il >> 1
+        flag, off, lits = g("probe_flag"), g("probe_off"), g("probe_lits")
+        expect = set()
+        for i in range(flag.size):
+            if flag[i] != 0:
+                continue
+            v = i // 2 + 1
+            root = 2 * v + (i & 1)
+            seen, stack, conflict = {root}, [root], False
+            while stack:
+                p = stack.pop()
+                for q in succ[p]:
+                    if q ^ 1 in seen:
+                        conflict = True
+                    if q not in seen:
+                        seen.add(q); stack.append(q)
+            assert not conflict, (name, i)          # a probe that reaches a fixpoint cannot fail through binaries alone
+            for x in lits[int(off[i]):int(off[i + 1])].tolist():
+                il = 2 * abs(x) + (x < 0)
+                if il not in seen:
+                    expect.add((ext(root), x))
+        assert got == expect, (name, len(got), len(expect))
+        total += len(expect)
+        # the binary-only pass on its own: its sets are the closures computed above
+        rb = t.ProbeAll(binary_only=True)
+        for i in np.nonzero(flag == 0)[0][:50]:
+            assert rb.flag[i] == 0 and set(rb.implied(int(i)).tolist()) <= set(lits[int(off[i]):int(off[i + 1])].tolist())
+    assert total > 100
