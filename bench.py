@@ -295,7 +295,7 @@ def workload_block(key, scale_cpu_seconds, clocks, cores, pre=None):
     unit = "cubes/s" if cubes else "probes/s"
     line = {"workload": w["name"], "value": n_items / sec, "unit": unit, "props_per_sec": info["props_ref"] / sec, "ms_per_step": 1e3 * sec,
             "steps": len(ms), "step_ms": ms, "n_items": n_items, "n_ok": info["n_ok"], "n_conflict": info["n_conflict"], "n_skipped": info["n_skipped"],
-            "n_implied": info["n_implied"], "tiers": {"queued": info["n_deep"], "cta_tiers": info["n_mid"], "dense_tier": info["n_large"]},
+            "n_implied": info["n_implied"], "tiers": {"queued": info["n_deep"], "second_tier": info["n_mid"], "last_tier": info["n_large"]},
             "closure_reuse": {k: info[k] for k in ("adopted", "adopt_lits", "inherited")},
             "counters": {k: info[k] for k in ("props_all", "props_ref", "assignments", "bcps", "slots", "clause_fetches")},
             "db": {k: dbi[k] for k in ("n_bin", "n_tern", "n_long", "row_slots", "device_bytes")}, "gen_s": round(t1 - t0, 1), "db_build_s": round(t2 - t1, 1),
@@ -541,7 +541,7 @@ def ours_arm(args, rank, local_rank, world):
     barrier()
     # clocks under this load: the timed steps are ~30 us each, so the same step keeps running (untimed, all ranks) until the
     # sampler has a few rows
-    for _ in range(8000):      # (a fixed count: with peers every rank must make the same sequence of merging calls)
+    for _ in range(30000):     # (a fixed count: with peers every rank must make the same sequence of merging calls)
         rc = L.bbcp_probe_range(h, first, last, C.byref(opts), C.byref(info))
         assert rc == 0, eng.GetStatusExplanation()
     barrier()
