@@ -1118,8 +1118,10 @@ int bbcp_probe_to_fixpoint(bbcp_handle *h, uint32_t max_rounds, uint32_t *rounds
     std::vector<int32_t> cube, lits;
     for (; max_rounds == 0 || round < max_rounds; ++round) {
         bbcp_opts o;
-        memset(&o, 0, sizeof(o));   // flags and bitmaps only; the sets stay on the device for closure reuse
-        o.flags = BBCP_OPT_STORE_SETS;
+        // flags and bitmaps only. (BBCP_OPT_STORE_SETS -- keeping the sets on the device so that probes adopt each other's
+        // results -- was measured here and is NOT used: on the Tseitin shape a pass writes 64 GB of sets and the first pass of
+        // a handle runs twice to size the pool: 8.6 s per round against 3.4 s with conflict / overflow inheritance alone)
+        memset(&o, 0, sizeof(o));
         if ((rc = bbcp_clear_bitmaps(h)) != BBCP_OK) return rc;
         if ((rc = bbcp_probe_all(h, &o, nullptr)) != BBCP_OK) return rc;
         unit.assign(bbcp_bitmap_words(h), 0);

@@ -661,3 +661,26 @@ def test_hyper_binary_resolvents_against_the_golden_implied_sets(golden):
         for i in np.nonzero(flag == 0)[0][:50]:
             assert rb.flag[i] == 0 and set(rb.implied(int(i)).tolist()) <= set(lits[int(off[i]):int(off[i + 1])].tolist())
     assert total > 100
+
+
+def test_refinalize_with_more_variables_after_a_last_tier_batch(golden):
+    """the last tier's slabs are sized by the variable range. A batch that used them, then clauses that raise
+    max_var plus more level-0 units than the second tier holds (so that the internal level-0 unit batch of the next
+    Finalize reaches the last tier), must not index the old, smaller slabs."""
+    from oracle_lib import Oracle
+    words = golden["fuzz_10/words"]
+    t, rc = engine_for(words)
+    res = t.ProbeAll(small_trail=32, mid_trail=32)
+    assert res.info["n_large"] > 0                      # the last tier ran: slabs exist for the old variable range
+    mv = t.max_var
+    extra = np.stack([np.arange(mv + 1, mv + 9001, dtype=np.int32), np.zeros(9000, dtype=np.int32)], axis=1).ravel()   # 9000 new unit clauses
+    chain = np.asarray([-(mv + 1), mv + 9001, 0, -(mv + 9001), mv + 9002, 0], dtype=np.int32)                           # and something they propagate into
+    t.AddClauses(extra)
+    t.AddClauses(chain)
+    assert t.Finalize() == 0
+    w2 = np.concatenate([words, extra, chain])
+    o = Oracle(w2)
+    assert o.status == 0 and np.array_equal(t.Level0(), o.level0())
+    flag, _, off, lits = o.run()
+    res = t.ProbeAll(small_trail=32, mid_trail=32)
+    gpu_util.assert_same_results(res, flag, off, lits, "after re-finalize with a larger variable range")

@@ -279,3 +279,23 @@ def test_probe_schedule_is_children_first(golden, name):
                 cross += 1
                 assert pos[q] < pos[p], (p, q)
     assert edges == nbin and cross > 0
+
+
+def test_literals_beyond_the_engine_range_are_refused():
+    """Internal literals are 2*var+neg in 30 bits (the two bits above are the trail-entry mode): |literal| >= 2^29 is refused
+    with BBCP_ERR_INDEX_TOO_NARROW (the reference's STATUS_INDEX_TOO_NARROW), sticky, and nothing is allocated for it."""
+    import ctypes as C
+    lib = _lib.load()
+    for bad in (1 << 29, -(1 << 29), (1 << 31) - 1, -(1 << 31)):
+        h = lib.bbcp_create(0)
+        a = (C.c_int32 * 2)(1, 2)
+        assert lib.bbcp_add_clause(h, a, 2) == 0
+        assert lib.bbcp_add(h, bad) == -3
+        assert lib.bbcp_status(h) == -3 and b"2^29" in lib.bbcp_error_string(h)
+        b = (C.c_int32 * 3)(3, bad, 0)
+        assert lib.bbcp_add_clause(h, b, 3) == -3 and lib.bbcp_add_clauses(h, b, 3) == -3
+        lib.bbcp_release(h)
+    h = lib.bbcp_create(0)
+    ok = (C.c_int32 * 3)((1 << 29) - 1, -5, 0)
+    assert lib.bbcp_add_clauses(h, ok, 3) == 0 and lib.bbcp_status(h) == 0
+    lib.bbcp_release(h)
