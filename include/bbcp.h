@@ -244,6 +244,10 @@ void *bbcp_device_impl_lits(bbcp_handle *h);
 void *bbcp_stream(bbcp_handle *h);
 /* blocks until the handle's stream is idle */
 int bbcp_sync(bbcp_handle *h);
+/* diagnostic builds only (make checks; zeros otherwise): clock ticks the CTA tiers spent per phase since the last call, summed
+ * over CTAs: [0] narrow-frontier mode, [1] closure look-up + adoption, [2] row walks, [3] load, [4] emission, [5] clean-up +
+ * publication + ticket */
+void bbcp_debug_phase_ticks(bbcp_handle *h, uint64_t *out8);
 /* measurement aid: enqueue, on the handle's stream, a write of `bytes` (0 = 256 MiB, twice the L2) that evicts the L2
  * before the next batch; returns at once. Because the next call's kernels queue up behind it, the host is done launching
  * them before the device starts on them: the batch's device time does not depend on how fast the host issues launches. */

@@ -76,6 +76,7 @@ _SIGS = {
     "bbcp_device_impl_lits": (C.c_void_p, [C.c_void_p]),
     "bbcp_stream": (C.c_void_p, [C.c_void_p]),
     "bbcp_sync": (C.c_int, [C.c_void_p]),
+    "bbcp_debug_phase_ticks": (None, [C.c_void_p, C.c_void_p]),
     "bbcp_l2_flush": (C.c_int, [C.c_void_p, C.c_uint64]),
     "bbcp_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bbcp_peer_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -1331,6 +1331,15 @@ int bbcp_clear_bitmaps(bbcp_handle *h)
     return h->cuda_ok(cudaStreamSynchronize(h->stream), "clear bitmaps") ? BBCP_OK : BBCP_ERR_CUDA;
 }
 
+void bbcp_debug_phase_ticks(bbcp_handle *h, uint64_t *out8)
+{
+    if (!h || !out8) return;
+    if (h->device_ready) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+    unsigned long long t[8];
+    read_phase_ticks(t);
+    for (int i = 0; i < 8; ++i) out8[i] = t[i];
+}
+
 int bbcp_l2_flush(bbcp_handle *h, uint64_t bytes)
 {
     if (!h) return BBCP_ERR_ARG;

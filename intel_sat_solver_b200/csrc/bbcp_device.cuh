@@ -133,6 +133,7 @@ size_t small_smem_bytes(uint32_t trail_cap, int width);
 int small_blocks_per_sm(uint32_t trail_cap, int width);
 struct MergeArgs;
 void set_debug_buffer(unsigned long long *mapped);
+void read_phase_ticks(unsigned long long *out);
 void build_order_device(const DbView &db, uint32_t nl, uint8_t *d_height, uint32_t *d_order, int sm_count, cudaStream_t s);
 bool launch_scan_gather(const BatchView &b, int pass, int max_blocks, bool giant_sets_possible, const MergeArgs &mg, cudaStream_t s, bool pdl);
 int scan_gather_max_blocks(int sm_count);

@@ -41,6 +41,26 @@
 namespace bbcp {
 
 // diagnostic builds: where a failed check leaves its record (mapped host memory); a no-op in the product build
+#ifdef BBCP_CHECKS
+__device__ __forceinline__ unsigned long long &bbcp_sweep_words() { return g_phase[7]; }
+#else
+__device__ unsigned long long g_unused_sweep;
+__device__ __forceinline__ unsigned long long &bbcp_sweep_words() { return g_unused_sweep; }
+#endif
+// diagnostic builds: clock64 ticks per phase of the CTA tiers, summed over CTAs, since the last call
+// [0] narrow-frontier mode, [1] closure look-up + adoption (whole CTA), [2] row walks (whole CTA), [3] load, [4] emission,
+// [5] clean-up + publication, [6] ticket / idle
+void read_phase_ticks(unsigned long long *out)
+{
+#ifdef BBCP_CHECKS
+    cudaMemcpyFromSymbol(out, g_phase, 64);
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_phase, z, 64);
+#else
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+#endif
+}
+
 void set_debug_buffer(unsigned long long *mapped)
 {
 #ifdef BBCP_CHECKS
@@ -500,6 +520,7 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
     const volatile uint32_t *vctl = ctl;
     uint32_t head = 0;
     BBCP_WATCH_BEGIN();
+    BBCP_PHASE_DECL();
     for (;;) {
         BBCP_WATCH(head, ctl[0]);
         __syncthreads();
@@ -545,6 +566,7 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
             }
             __syncthreads();
             head = vctl[7];
+            BBCP_PHASE(0);
             continue;
         }
         if (b.reuse && level_end > 1) {
@@ -588,7 +610,9 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
                 if (warp == (int)(k % nwarps) && lane == 0) { ++wc.adopted; wc.adopt_lits += n; wc.bytes += 4ull * n; }
             }
             // (CTA-uniform: a warp that got past this point may latch a conflict before a slower thread has looked)
-            if (__syncthreads_or((vctl[1] | vctl[2]) != 0)) continue;   // the loop head sees the latch and stops
+            const bool ab = __syncthreads_or((vctl[1] | vctl[2]) != 0);
+            BBCP_PHASE(1);
+            if (ab) continue;   // the loop head sees the latch and stops
         }
         const bool bins_only = (b.opts & OPT_BINARY_ONLY) || (prune && level_end == 1);
         for (uint32_t bse = head + warp * 32; bse < level_end; bse += nwarps * 32) {
@@ -598,15 +622,17 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
         }
         if (threadIdx.x == 0) ctl[6] = 0;   // (read again only behind the barrier at the loop head)
         head = level_end;
+        BBCP_PHASE(2);
     }
 }
 
-__global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const BatchView b, const LargeState ls, const int from_huge)
+constexpr int SWEEP_WORDS = 4;
+__global__ void __launch_bounds__(BIG_THREADS, 5) k_big(const DbView db, const BatchView b, const LargeState ls, const int from_huge)
 {
     using G = Grp<32>;
     __shared__ uint32_t ctl[12];     // 0 tail, 1 conflict, 2 overflow, 3 load result, 4 ticket, 5 vmin, 6 vmax / whole-CTA level, 7 head, 8 second-walk entries
     __shared__ unsigned long long s_off;
-    __shared__ uint32_t s_warp[BIG_THREADS / 32 + 1];
+    __shared__ uint32_t s_sweep[SWEEP_WORDS][BIG_THREADS / 32];
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     // the last tier takes what outgrew the tier before it: the third tier's hand-over list, or the second tier's when the
     // warp-per-probe second tier (k_deep2, BBCP_TIER2=warp) ran instead of the two CTA-per-probe tiers
@@ -621,8 +647,10 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
     gs.trail = ls.trail + (size_t)blockIdx.x * gs.cap;
     const bool prune = !(b.opts & OPT_NO_LEN_PRUNE);
     WorkCounters wc;
+    BBCP_PHASE_DECL();
     for (;;) {
         __syncthreads();
+        BBCP_PHASE(5);
         if (threadIdx.x == 0) {
             ctl[4] = atomicAdd(ticket, 1u);
             ctl[0] = ctl[1] = ctl[2] = ctl[8] = 0;
@@ -643,8 +671,10 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
         }
         __syncthreads();
         const uint32_t f = ctl[3];
+        BBCP_PHASE(3);
         if (f == 0xff) block_propagate(db, b, gs, ctl, prune, 4, wc);
         __syncthreads();
+        BBCP_PHASE_DECL2();
         const uint32_t tail = min(ctl[0], gs.cap);
         const uint32_t nmem = tail - min(ctl[8], tail);     // members of the implied set (the trail also holds second-walk entries)
         const bool conflict = ctl[1] != 0 || f == FLAG_CONFLICT;
@@ -681,33 +711,51 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
                         }
                         if (lane == 0) { atomicMin(&ctl[5], vmin); atomicMax(&ctl[6], vmax); }
                         __syncthreads();
+                        BBCP_PHASE(6);
                         const uint32_t w0 = ctl[5] >> 4, w1 = ctl[6] >> 4;
+                        if (threadIdx.x == 0) atomicAdd(&bbcp_sweep_words(), (unsigned long long)(w1 - w0 + 1));
+                        // The range is wide and sparse (on the Tseitin shape ~100 K words for ~18 K literals: a cone spans many
+                        // frames), and a step of the sweep is a dependent DRAM load + two barriers: SWEEP_WORDS loads per thread
+                        // are in flight per step. (Eight of them cost registers, a resident CTA, and more than they saved.)
                         unsigned long long w = off;
-                        for (uint32_t wbase = w0; wbase <= w1; wbase += blockDim.x) {
-                            const uint32_t wi = wbase + threadIdx.x;
-                            const uint32_t word = wi <= w1 ? __ldcg(&gs.bits[wi]) : 0u;
-                            const uint32_t nz = (word | (word >> 1)) & 0x55555555u;  // one bit per assigned var
-                            const uint32_t c = __popc(nz);
-                            uint32_t incl = c;
+                        for (uint32_t wbase = w0; wbase <= w1; wbase += SWEEP_WORDS * blockDim.x) {
+                            uint32_t word[SWEEP_WORDS], excl[SWEEP_WORDS];
 #pragma unroll
-                            for (int d = 1; d < 32; d <<= 1) {
-                                const uint32_t x = __shfl_up_sync(FULL, incl, d);
-                                if (lane >= d) incl += x;
+                            for (int k = 0; k < SWEEP_WORDS; ++k) {
+                                const uint32_t wi = wbase + k * blockDim.x + threadIdx.x;
+                                word[k] = wi <= w1 ? __ldcg(&gs.bits[wi]) : 0u;
                             }
-                            if (lane == 31) s_warp[warp] = incl;
+#pragma unroll
+                            for (int k = 0; k < SWEEP_WORDS; ++k) {
+                                const uint32_t c = __popc((word[k] | (word[k] >> 1)) & 0x55555555u);  // one bit per assigned var
+                                uint32_t incl = c;
+#pragma unroll
+                                for (int d = 1; d < 32; d <<= 1) {
+                                    const uint32_t x = __shfl_up_sync(FULL, incl, d);
+                                    if (lane >= d) incl += x;
+                                }
+                                if (lane == 31) s_sweep[k][warp] = incl;
+                                excl[k] = incl - c;
+                            }
                             __syncthreads();
-                            uint32_t before = 0, total = 0;
-                            for (int k = 0; k < nwarps; ++k) { const uint32_t x = s_warp[k]; total += x; if (k < warp) before += x; }
-                            unsigned long long o = w + before + (incl - c);
-                            uint32_t m = nz;
-                            while (m) {
-                                const int bpos = __ffs(m) - 1;
-                                m &= m - 1;
-                                const uint32_t var = wi * 16u + (uint32_t)(bpos >> 1);
-                                const bool isneg = ((word >> bpos) & 3u) == 2u;
-                                b.out_lits[o++] = (int32_t)(2u * var + (isneg ? 1u : 0u));   // internal literals, as every set in the pool
+                            uint32_t run = 0;
+#pragma unroll
+                            for (int k = 0; k < SWEEP_WORDS; ++k) {
+                                uint32_t before = 0, total = 0;
+                                for (int q = 0; q < nwarps; ++q) { const uint32_t x = s_sweep[k][q]; total += x; if (q < warp) before += x; }
+                                unsigned long long o = w + run + before + excl[k];
+                                const uint32_t wi = wbase + k * blockDim.x + threadIdx.x;
+                                uint32_t m = (word[k] | (word[k] >> 1)) & 0x55555555u;
+                                while (m) {
+                                    const int bpos = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const uint32_t var = wi * 16u + (uint32_t)(bpos >> 1);
+                                    const bool isneg = ((word[k] >> bpos) & 3u) == 2u;
+                                    b.out_lits[o++] = (int32_t)(2u * var + (isneg ? 1u : 0u));   // internal literals, as every set in the pool
+                                }
+                                run += total;
                             }
-                            w += total;
+                            w += run;
                             __syncthreads();
                         }
                         wc.bytes += warp == 0 ? 4ull * tail + 4ull * (w1 - w0 + 1) : 0ull;
@@ -716,6 +764,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_big(const DbView db, const Batc
             }
         }
         __syncthreads();
+        BBCP_PHASE(4);
         // leave the state empty for the next probe
         for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
             const uint32_t var = (gs.tget(i) & TRAIL_LIT) >> 1;

@@ -22,12 +22,20 @@ namespace bbcp { __device__ unsigned long long *g_dbg = nullptr; }   // (this he
         __threadfence_system(); } __trap(); } while (0)
 #define BBCP_CHECK(cond, ...) do { if (!(cond)) { printf("BBCP_CHECK failed: " #cond " | " __VA_ARGS__); BBCP_FAIL(0, 0); } } while (0)
 #define BBCP_MARK(id) do { if (bbcp::g_dbg && blockIdx.x < 480 && blockDim.x == 256 && (threadIdx.x & 31) == 0) bbcp::g_dbg[256 + blockIdx.x * 8 + (threadIdx.x >> 5)] = ((unsigned long long)(id) << 32) | __LINE__; } while (0)
+// phase timers of the CTA tiers (thread 0 of a CTA, clock64 ticks summed over all CTAs; read with bbcp_debug_phase_ticks)
+namespace bbcp { __device__ unsigned long long g_phase[8]; }
+#define BBCP_PHASE_DECL() long long bbcp_ph_t = clock64()
+#define BBCP_PHASE_DECL2() bbcp_ph_t = clock64()
+#define BBCP_PHASE(i) do { if (threadIdx.x == 0) { const long long bbcp_ph_n = clock64(); atomicAdd(&bbcp::g_phase[i], (unsigned long long)(bbcp_ph_n - bbcp_ph_t)); bbcp_ph_t = bbcp_ph_n; } } while (0)
 #define BBCP_WATCH_BEGIN() const unsigned long long bbcp_watch_t0 = bbcp::watch_ns()
 #define BBCP_WATCH(v0, v1) do { if (bbcp::watch_ns() - bbcp_watch_t0 > 4000000000ull) BBCP_FAIL(v0, v1); } while (0)
 namespace bbcp { __device__ __forceinline__ unsigned long long watch_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; } }
 #else
 #define BBCP_CHECK(cond, ...) do { } while (0)
 #define BBCP_MARK(id) do { } while (0)
+#define BBCP_PHASE_DECL() do { } while (0)
+#define BBCP_PHASE_DECL2() do { } while (0)
+#define BBCP_PHASE(i) do { } while (0)
 #define BBCP_WATCH_BEGIN() do { } while (0)
 #define BBCP_WATCH(v0, v1) do { } while (0)
 #endif
@@ -364,6 +372,18 @@ struct GroupTail {
         tail += nnew;
         return any_conf ? 1 : 0;
     }
+    // second half of an ADOPT commit whose inserts were issued by the caller (several at a time: closure_adopt)
+    template <class G, class S>
+    __device__ __forceinline__ int append_adopted(S &st, uint32_t cand, int r, uint32_t mark)
+    {
+        const bool any_conf = G::any(r == 2);
+        const unsigned newm = G::ballot(r == 0);
+        const uint32_t nnew = __popc(newm);
+        if (tail + nnew > st.cap) return 2;
+        if (r == 0) st.tset(tail + __popc(newm & G::lt()), cand | mark, 0xffffu);
+        tail += nnew;
+        return any_conf ? 1 : 0;
+    }
     // Second walks (one TRAIL_RESCAN entry each) for the members among the trail entries [0, upto) that will not get a
     // walk of their own any more: the ones before `head` (walked already) and the TRAIL_SKIP ones. Returns 2 when they
     // do not fit.
@@ -419,6 +439,23 @@ struct BlockTail {
             pos = G::shfl(pos, 0);
             if (pos + nnew > st.cap) { if (G::lane() == 0) ctl[2] = 1; ret = 2; }
             else if (leader && r == 0) st.tset(pos + __popc(newm & G::lt()), ADOPT ? (cand | mark) : cand, slot);
+        }
+        if (any_conf) { if (G::lane() == 0) ctl[1] = 1; if (!ret) ret = 1; }
+        return ret;
+    }
+    template <class G, class S>
+    __device__ __forceinline__ int append_adopted(S &st, uint32_t cand, int r, uint32_t mark)
+    {
+        const bool any_conf = G::any(r == 2);
+        const unsigned newm = G::ballot(r == 0);
+        const uint32_t nnew = __popc(newm);
+        int ret = 0;
+        if (nnew) {
+            uint32_t pos = 0;
+            if (G::lane() == 0) pos = atomicAdd(&ctl[0], nnew);
+            pos = G::shfl(pos, 0);
+            if (pos + nnew > st.cap) { if (G::lane() == 0) ctl[2] = 1; ret = 2; }
+            else if (r == 0) st.tset(pos + __popc(newm & G::lt()), cand | mark, 0xffffu);
         }
         if (any_conf) { if (G::lane() == 0) ctl[1] = 1; if (!ret) ret = 1; }
         return ret;
@@ -693,7 +730,35 @@ __device__ __forceinline__ int closure_adopt(const BatchView &b, S &st, T &tl, u
     const int lane = G::lane();
     BBCP_CHECK(src + n <= b.out_cap, "adopting off %llu len %u of %llu\n", src, n, (unsigned long long)b.out_cap);
     BBCP_WATCH_BEGIN();
-    for (uint32_t i = first; i < n; i += stride) {
+    // ADOPT_ILP literals per lane and step: their loads, then their inserts, are in flight together (on the global-memory
+    // states an insert is a DRAM atomic; one per step left the adoption bound by that round trip). The first tier's state
+    // records a slot index per trail entry at insert time, so it keeps the one-at-a-time form.
+    constexpr int ADOPT_ILP = 4;
+    uint32_t i = first;
+    if constexpr (!Staging<S>::available) {
+        for (; (unsigned long long)i + (ADOPT_ILP - 1ull) * stride < n; i += ADOPT_ILP * stride) {
+            BBCP_WATCH(n, i);
+            uint32_t c[ADOPT_ILP];
+            int r[ADOPT_ILP];
+#pragma unroll
+            for (int k = 0; k < ADOPT_ILP; ++k) c[k] = i + k * stride + lane < n ? (uint32_t)__ldcg(&b.out_lits[src + i + k * stride + lane]) : 0u;
+#pragma unroll
+            for (int k = 0; k < ADOPT_ILP; ++k) { uint32_t slot; r[k] = c[k] ? st.insert(c[k], slot) : 1; }
+            // (a conflict does not cut this short: every literal that was inserted must reach the trail, the clean-up of the
+            // state goes by the trail; an overflow wipes the state anyway)
+            int ret = 0;
+#pragma unroll
+            for (int k = 0; k < ADOPT_ILP; ++k) {
+                const int rr = tl.template append_adopted<G>(st, c[k], r[k], mark);
+                if (rr == 2) return 2;
+                if (rr) ret = rr;
+            }
+            if (ret) return ret;
+            if (tl.aborted()) return 1;
+            st.template maybe_grow<G>(tl.get());
+        }
+    }
+    for (; i < n; i += stride) {
         BBCP_WATCH(n, i);
         const uint32_t c = i + lane < n ? (uint32_t)__ldcg(&b.out_lits[src + i + lane]) : 0u;
         BBCP_CHECK(c == 0 || (c >= 2 && !(c & TRAIL_SKIP)), "adopted literal %u (off %llu + %u of %u)\n", c, src, i + lane, n);
@@ -705,14 +770,6 @@ __device__ __forceinline__ int closure_adopt(const BatchView &b, S &st, T &tl, u
     return 0;
 }
 
-// `head` = trail entries [0, head) have had their row walked, [head, tail) are waiting for theirs.
-// SKIP mode. Let S be the state (all trail members) when a finished set A is entered, and suppose A is several times
-// larger than S. A is closed under unit propagation on its own, so a clause can only become unit now if it has false
-// literals on BOTH sides, in A \ S and in S. Every such clause is seen from the S side: the members of S whose walk is
-// still to come see all of A when it comes, and the members already walked get a second walk (TRAIL_RESCAN, ternary /
-// long part: the binary clauses of a walked literal are satisfied). So the literals of A need no walk at all
-// (TRAIL_SKIP): |S| row walks instead of |A|. Later sets are treated the same way against the then-current state, which
-// contains A's members as ordinary members (they are rescanned if a still larger set arrives).
 template <class G, class S, class T>
 __device__ int expand_closures(const BatchView &b, S &st, T &tl, uint32_t e, uint32_t B, uint32_t head, int tier, WorkCounters &wc)
 {

@@ -663,12 +663,14 @@ def test_hyper_binary_resolvents_against_the_golden_implied_sets(golden):
     assert total > 100
 
 
-def test_refinalize_with_more_variables_after_a_last_tier_batch(golden):
+def test_refinalize_with_more_variables_after_a_last_tier_batch():
     """the last tier's slabs are sized by the variable range. A batch that used them, then clauses that raise
     max_var plus more level-0 units than the second tier holds (so that the internal level-0 unit batch of the next
     Finalize reaches the last tier), must not index the old, smaller slabs."""
     from oracle_lib import Oracle
-    words = golden["fuzz_10/words"]
+    with tempfile.TemporaryDirectory() as d:
+        inst, _ = gpu_util.gen("aig", d, frames=2, gates=1500, inputs=60, latches=60, window=200, seed=2)   # implied sets of hundreds of literals
+        words = fileio.read_bcnf(inst)
     t, rc = engine_for(words)
     res = t.ProbeAll(small_trail=32, mid_trail=32)
     assert res.info["n_large"] > 0                      # the last tier ran: slabs exist for the old variable range
