@@ -86,7 +86,8 @@ struct bbcp_handle {
     DevBuf d_hdr, d_slots, d_arena, d_litinfo, d_order;
     uint32_t order_n = 0;   // entries of the probe schedule on the device (0: none)
     // ONE allocation shared with peer GPUs (CUDA IPC): [failed: bm_stride words][unit: bm_stride words]
-    // [arrival flags: one u32 per rank][push-done counter], see bbcp_merge_bitmaps
+    // [256 control words: arrival epoch per rank, finished-CTA count, time-out latch, pull-done epoch per rank, empty-slice
+    // hints], see merge_signal in bbcp_kernels.cu
     DevBuf d_bitmaps;
     uint64_t bm_stride = 0;
     uint32_t *failed_p() const { return d_bitmaps.as<uint32_t>(); }
@@ -397,11 +398,11 @@ bool ensure_slabs(bbcp_handle *h, const DbView &dbv)
 // The whole device-side batch. Input arrays already on the device: (d_lits, d_off) cubes in CSR form,
 // (d_lits, nullptr) a list of probe literals, (nullptr, nullptr) the probe universe from `first`.
 // One stream, no memset nodes, one host synchronisation in the common case:
-//     k_triage -> k_deep -> k_scan_gather -> 200-byte counter read-back -> sync
+//     k_triage -> k_deep -> k_scan_gather -> counters through mapped host memory -> sync
 // Only if some probe outgrew the warp-private shared-memory state (the read-back says so; k_scan_gather saw it
-// too and returned at once) a second sequence runs: k_block<smem> -> k_block<gmem> -> k_scan_gather
-// (-> k_gather_long) -> read-back -> sync. Each tier hands what it cannot hold to the next through a
-// device-side list.
+// too and returned at once) a second sequence runs: k_deep2 -> k_big -> k_sort_sets -> k_scan_gather
+// (-> k_gather_long) -> read-back -> sync (BBCP_TIER2=block: k_block x 2 -> k_big instead). Each tier hands what it
+// cannot hold to the next through a device-side list.
 int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint64_t first, uint64_t n,
               const bbcp_opts *uopts, bbcp_batch_info *info)
 {

@@ -1,6 +1,7 @@
 // bbcp_kernels.cu -- batched BCP to fixpoint on sm_100a. Hand-written CUDA; no tensor cores (there is no
-// dense contraction on this path); what bounds the kernels is dependent-load latency (propagation) and launch /
-// first-load latency (the streaming kernels), see DESIGN.md section 4 and profiles/r01.
+// dense contraction on this path); what bounds the kernels (profiles/r02): instruction issue in
+// the first tier, random 4-byte accesses to the per-probe state in the later tiers, launch / first-load latency in the
+// streaming kernels.
 //
 // What one probe/cube does here replaces one NewDecLevel/Assign/BCP()/Backtrack(0) round of the reference
 // (TopiBcp.cc:103-410, TopiAsg.cc:46-139, TopiBacktrack.cc:18-53):
@@ -27,6 +28,12 @@
 //     binary clause ends right there. That triage is its own streaming kernel (k_triage: eight probes per
 //     thread, one byte of per-literal facts each, a table look-up, flag + set size written, one atomic per
 //     warp only where probes are queued); only the probes that can propagate are queued for k_deep;
+//   * in an all-literal pass a probe ADOPTS the finished results of the literals it reaches (closure reuse: conflicts
+//     and tier overflows are inherited, fixpoints are entered 32 literals per step from the result pool), probes are
+//     taken in the order of their height in the binary implication graph, an adopted set larger than the state it is
+//     entered into is not walked at all (the smaller side gets second walks instead), and a row several times longer
+//     than everything walked so far is left out the same way -- expand_closures / process_batch in bbcp_propagate.cuh,
+//     DESIGN.md section 2 for why the fixpoint is unchanged;
 //   * k_scan_gather turns the set sizes into CSR offsets and moves every set to its canonical place in one
 //     pass (the per-tile sums it needs are produced on the way by k_triage and the propagate kernels), and
 //     carries the multi-GPU merge of the bitmaps when peers are attached.
@@ -1061,7 +1068,7 @@ __global__ void k_merge_drain(const MergeArgs m)
 }
 
 // ---------------------------------------------------------------- result compaction into canonical CSR order
-// One pass: sizes -> exclusive prefix sum (single-pass scan with decoupled look-back over 2048-item tiles)
+// One pass: sizes -> exclusive prefix sum (every CTA derives its first offset from the per-tile sums, see below)
 // -> CSR offsets written, every implied set copied from its allocation-order position in the pool to its
 // canonical position, self-implied literals regenerated from the item index. Sets above GATHER_GIANT are cut
 // into chunks for k_gather_long so that no CTA is stuck with one of them.

@@ -6,8 +6,9 @@
 // built to put more probes in flight on structured instances, whose rows keep ~10 % of a warp's lanes busy, and
 // measured on the Tseitin/BMC shape on a B200: 2.3x SLOWER at W = 8, 1.5x slower at W = 16 -- divergent groups of one
 // warp are issued one after the other, so the instruction stream per warp quadruples while the latency it was
-// meant to hide does not overlap any better -- and it showed a rare fault under divergence that full warps
-// never showed. Rejected; the template parameter stays because the code reads no worse for it.
+// meant to hide does not overlap any better. (The "rare fault under divergence" noted then was found in round 2: lanes
+// of one warp read a CTA-wide abort latch at different moments and the warp split; see BlockTail::aborted.) Rejected;
+// the template parameter stays because the code reads no worse for it.
 #pragma once
 #include "bbcp_device.cuh"
 

@@ -249,7 +249,7 @@ def test_probe_list_and_u32_offsets(golden):
 
 
 def test_large_batch_scan_and_giant_sets():
-    """Many tiles of the single-pass scan (decoupled look-back across > 100 tiles), sets copied by thread / warp /
+    """Many tiles of the single-pass compaction (per-tile sums across > 100 tiles), sets copied by thread / warp /
     CTA / chunked, against the checker on a chain instance whose probes imply thousands of literals."""
     with tempfile.TemporaryDirectory() as d:
         # x1 -> x2 -> ... -> xN chain: probing x_i implies N-i+1 literals; plus noise ternaries
