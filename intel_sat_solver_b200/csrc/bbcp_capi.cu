@@ -594,10 +594,12 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
                 launch_mid(dbv, b, h->d_mid_slab.as<uint32_t>(), cap_mid, width, (int)mid_blocks, h->stream);
                 if (!dbg_check(h, "k_deep2")) return BBCP_ERR_CUDA;
                 cudaEventRecord(h->ev[7], h->stream);
+                // (the second tier's sets are sorted BEFORE the last tier runs: it adopts them, and its bulk adoption looks
+                // literals up in a set by binary search)
+                if (store) { launch_sort_sets(b, cap_mid, h->sm_count, h->stream); ++bi.launches; }
+                if (!dbg_check(h, "k_sort_sets")) return BBCP_ERR_CUDA;
                 launch_big(dbv, b, ls, (int)h->big_slabs, false, h->stream);
                 if (!dbg_check(h, "k_big")) return BBCP_ERR_CUDA;
-                if (implied) { launch_sort_sets(b, cap_mid, h->sm_count, h->stream); ++bi.launches; }
-                if (!dbg_check(h, "k_sort_sets")) return BBCP_ERR_CUDA;
             } else {
                 // second tier: 256-thread CTAs, several per SM; third tier: 1024-thread CTAs on (nearly) all of an SM's
                 // shared memory; last tier: dense state, any size. Each hands what it cannot hold to the next through a list.

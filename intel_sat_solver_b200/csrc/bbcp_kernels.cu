@@ -44,6 +44,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace bbcp {
 
@@ -513,6 +514,7 @@ constexpr uint32_t ADOPT_MAX = 64;   // finished sets adopted CTA-wide per level
 // barrier per level -- a deep implication chain costs a CTA five barriers per literal otherwise); it hands back to the
 // whole CTA when the frontier widens beyond NARROW_OUT or a finished set of more than NARROW_ADOPT literals shows up
 constexpr uint32_t NARROW_IN = 32, NARROW_OUT = 128, NARROW_ADOPT = 512;
+constexpr uint32_t BULK_MEMBERS = 64;   // bulk SKIP adoption: at most this many trail entries before the set (one thread each looks its literal up)
 
 // ctl: [0] tail, [1] conflict latch, [2] overflow latch, [6] "the next level is for the whole CTA", [7] head handed back by warp 0
 template <class S>
@@ -521,7 +523,8 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
     using G = Grp<32>;
     __shared__ unsigned long long s_src[ADOPT_MAX];
     __shared__ uint32_t s_len[ADOPT_MAX];
-    __shared__ uint32_t s_na;
+    __shared__ uint32_t s_na, s_ndup, s_base;
+    __shared__ uint32_t s_dup[BULK_MEMBERS];
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     BlockTail tl{ctl};
     const volatile uint32_t *vctl = ctl;
@@ -609,7 +612,58 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
             const bool skip = na && !((vctl[1] | vctl[2]) != 0) && s_len[best] >= 4u * t0 && 2ull * t0 + s_len[best] <= st.cap;
             __syncthreads();   // everybody has t0 before anyone appends
             if (skip && tl.template append_rescan<G>(st, t0, head, warp * 32, nwarps * 32)) { /* overflow latched */ }
-            for (uint32_t k = 0; k < na && !tl.aborted(); ++k) {
+            // BULK form of the SKIP adoption (dense state, few members so far): the set is sorted, so whether a member of the
+            // state is in it -- or its negation: a conflict -- is a binary search per member; after that no insert needs its
+            // answer: the set is copied to the trail as it is (a literal that was a member already is entered as a second
+            // walk, which does not count as a member) and the bits are set with fire-and-forget reductions. A streaming copy
+            // instead of a DRAM atomic round trip per 32 literals.
+            bool bulk_done = false;
+            if constexpr (std::is_same<S, GmemState>::value) {
+                if (skip && t0 <= BULK_MEMBERS) {
+                    const uint32_t n = s_len[best];
+                    const unsigned long long src = s_src[best];
+                    const uint32_t *A = reinterpret_cast<const uint32_t *>(b.out_lits) + src;
+                    if (threadIdx.x == 0) s_ndup = 0;
+                    __syncthreads();
+                    if (threadIdx.x < t0) {
+                        const uint32_t e0 = st.tget(threadIdx.x);
+                        if ((e0 & TRAIL_SKIP) != TRAIL_RESCAN) {
+                            const uint32_t lit = e0 & TRAIL_LIT, v2 = lit & ~1u;     // the set holds at most one literal of a variable
+                            uint32_t lo = 0, hi = n;
+                            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((__ldcg(&A[mid]) & ~1u) < v2) lo = mid + 1; else hi = mid; }
+                            if (lo < n) {
+                                const uint32_t x = __ldcg(&A[lo]);
+                                if (x == lit) s_dup[atomicAdd(&s_ndup, 1u)] = lo;
+                                else if (x == (lit ^ 1u)) ctl[1] = 1;               // the set holds the negation of a member
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    const uint32_t ndup = s_ndup;
+                    if (!(vctl[1] | vctl[2])) {
+                        if (threadIdx.x == 0) { s_base = atomicAdd(&ctl[0], n); atomicAdd(&ctl[8], ndup); }
+                        __syncthreads();
+                        const uint32_t base0 = s_base;
+                        if ((unsigned long long)base0 + n > st.cap) { if (threadIdx.x == 0) ctl[2] = 1; }
+                        else {
+                            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                                const uint32_t c = __ldcg(&A[i]);
+                                bool dup = false;
+                                for (uint32_t q = 0; q < ndup; ++q) dup |= s_dup[q] == i;
+                                st.tset(base0 + i, c | (dup ? TRAIL_RESCAN : TRAIL_SKIP), 0xffffu);
+                                if (!dup) {
+                                    const uint32_t var = c >> 1;
+                                    atomicOr(&st.bits[var >> 4], ((c & 1u) ? 2u : 1u) << ((var & 15u) * 2u));   // result unused: a reduction
+                                }
+                            }
+                            if (threadIdx.x == 0) { ++wc.adopted; wc.adopt_lits += n; wc.bytes += 8ull * n; }
+                        }
+                    }
+                    bulk_done = true;
+                    __syncthreads();
+                }
+            }
+            for (uint32_t k = bulk_done ? 1u : 0u; k < na && !tl.aborted(); ++k) {
                 const uint32_t a = k == 0 ? best : (k == best ? 0 : k);    // the largest first
                 const uint32_t n = s_len[a];
                 // successive sets start at successive warps, so that many short sets spread over the CTA as well
