@@ -11,6 +11,7 @@
 #include <ctime>
 #include <new>
 #include <unistd.h>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -107,6 +108,10 @@ struct bbcp_handle {
     struct ResultSet { DevBuf flag, off, impl; } rs[2];
     int rb = 0;
     uint64_t off_base = 0;       // added to the offsets a batch writes (chunked calls)
+    const int32_t *e2e_lits = nullptr;   // bbcp_probe_lits_to_host: the chunk's probe list / flag buffer in the caller's pinned memory
+    uint8_t *e2e_flag = nullptr;         // (device addresses of mapped host memory; the triage kernel reads / writes them)
+    uint32_t e2e_hint_flags = 0;         // options (+1) and stored literals of the last bbcp_probe_lits_to_host call: sizes the next call's chunks
+    uint64_t e2e_hint_implied = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[16] = {}, ev_out[2] = {};
     DevBuf d_raw_off, d_len, d_out, d_cube_lits, d_cube_off, d_overflow, d_big, d_huge, d_deep, d_chunks, d_misc, d_lbits, d_ltrail, d_tiles;
@@ -365,7 +370,7 @@ DbView db_view(const bbcp_handle *h)
     v.max_var = h->db.max_var;
     v.n_slots = (uint32_t)h->db.slots.size();
     v.n_arena_units = (uint32_t)(h->db.arena.size() / 4);
-    v.nvars_words16 = (uint32_t)(((uint64_t)h->db.max_var + 1 + 15) / 16);
+    v.nvars_words16 = (uint32_t)((((uint64_t)h->db.max_var + 1 + 15) / 16 + 3) & ~3ull);   // whole 16-byte vectors: the last tier sweeps with 128-bit loads
     v.l0_dirty = h->l0_dirty ? 1u : 0u;
     return v;
 }
@@ -448,6 +453,8 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     memset(&b, 0, sizeof(b));
     b.cube_lits = d_lits;
     b.cube_off = d_off;
+    b.host_lits = d_off ? nullptr : h->e2e_lits;
+    b.host_flag = d_off ? nullptr : h->e2e_flag;
     b.first = first;
     b.n = n;
     b.flag = h->rs[h->rb].flag.as<uint8_t>();
@@ -1015,9 +1022,28 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
     opts.flags &= ~(uint32_t)(BBCP_OPT_MERGE | BBCP_OPT_RENDEZVOUS);
     const bool off32 = (opts.flags & BBCP_OPT_OFF32) != 0;
     const size_t osz = off32 ? 4 : 8;
-    // chunks: whole compaction tiles, at most 16 of them, not smaller than 512 K probes (every chunk pays the fixed
-    // ~40 us of a batch; the chunks' kernel time line must stay shorter than the read-back it hides behind)
-    uint64_t nchunks = std::min<uint64_t>(16, std::max<uint64_t>(1, n / (512 * 1024)));
+    // How the probe list reaches the device and the flags reach the host (BBCP_E2E=pull|mirror|dma, default pull):
+    //   pull    caller buffers in pinned memory are used in place: the triage kernel reads the list over PCIe with 16-byte loads
+    //           (and leaves a device copy for the kernels after it) and writes the flags it decides into the caller's flag
+    //           buffer, so input, compute and flag read-back of a batch overlap inside one kernel
+    //   mirror  the list is uploaded by the copy engine (chunks on their own stream), the flags are written as in pull
+    //   dma     uploads and read-backs are all copy-engine transfers (the round-1 path; also what pageable buffers get)
+    enum { E2E_DMA, E2E_MIRROR, E2E_PULL };
+    int mode = E2E_PULL;
+    if (const char *e = getenv("BBCP_E2E")) mode = !strcmp(e, "dma") ? E2E_DMA : !strcmp(e, "mirror") ? E2E_MIRROR : E2E_PULL;
+    auto mapped = [](const void *p) -> void * {
+        cudaPointerAttributes a;
+        if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+    };
+    const int32_t *m_lits = mode == E2E_PULL && n ? static_cast<const int32_t *>(mapped(lits)) : nullptr;
+    uint8_t *m_flag = mode != E2E_DMA && n && (reinterpret_cast<uintptr_t>(flag_out) & 7u) == 0 ? static_cast<uint8_t *>(mapped(flag_out)) : nullptr;
+    const bool pull = m_lits != nullptr;
+    // chunks: whole compaction tiles, at most 16 of them, not smaller than 1 M probes (every chunk pays the fixed ~35 us of
+    // a batch, about twice that while an upload is in flight). Pulling, a call that brings back little more than flags
+    // (as its predecessor with the same options did) is one batch: there is no transfer to hide behind another chunk.
+    uint64_t nchunks = std::min<uint64_t>(16, std::max<uint64_t>(1, n / 1000000));
+    if (pull && h->e2e_hint_flags == opts.flags + 1u && h->e2e_hint_implied * 4 < n) nchunks = 1;
     if (const char *e = getenv("BBCP_CHUNKS")) nchunks = std::min<uint64_t>(16, std::max<uint64_t>(1, (uint64_t)atoi(e)));
     uint64_t csize = ((n + nchunks - 1) / nchunks + SG_TILE - 1) / SG_TILE * SG_TILE;
     if (csize == 0) csize = SG_TILE;
@@ -1029,12 +1055,18 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
         for (auto &e : h->ev_out) if (!h->cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return BBCP_ERR_CUDA;
     }
     if (!h->d_cube_lits.reserve(std::max<uint64_t>(n, 4) * 4)) return h->fail(BBCP_ERR_ALLOC, "device allocation failed (probe list)");
+    // BBCP_E2E_TRACE: host time line of the call on stderr (us since entry: uploads queued, every chunk's batch done, read-back done)
+    const bool trace = getenv("BBCP_E2E_TRACE") != nullptr;
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto us_now = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enter).count(); };
+    double t_up = 0, t_chunk[16] = {};
     // all input chunks go out at once on their own stream; each batch waits for its chunk only
-    for (uint64_t k = 0; k < nchunks; ++k) {
+    for (uint64_t k = 0; k < nchunks && !pull; ++k) {
         const uint64_t lo = k * csize, cnt = std::min(csize, n - lo);
         cudaMemcpyAsync(h->d_cube_lits.as<int32_t>() + lo, lits + lo, cnt * 4, cudaMemcpyHostToDevice, h->s_in);
         cudaEventRecord(h->ev_in[k], h->s_in);
     }
+    if (trace) t_up = us_now();
     bbcp_batch_info tot;
     memset(&tot, 0, sizeof(tot));
     uint64_t base = 0;
@@ -1045,14 +1077,19 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
         h->rb = (int)(k & 1);
         h->off_base = base;
         if (k >= 2) cudaStreamWaitEvent(h->stream, h->ev_out[k & 1], 0);   // this result set is still being read back
-        cudaStreamWaitEvent(h->stream, h->ev_in[k], 0);
+        if (!pull) cudaStreamWaitEvent(h->stream, h->ev_in[k], 0);
         bbcp_batch_info bi;
+        h->e2e_lits = pull ? m_lits + lo : nullptr;
+        h->e2e_flag = m_flag ? m_flag + lo : nullptr;
         ret = run_batch(h, h->d_cube_lits.as<int32_t>() + lo, nullptr, 0, cnt, &opts, &bi);
+        h->e2e_lits = nullptr;
+        h->e2e_flag = nullptr;
         if (ret != BBCP_OK) break;
         if (base + bi.n_implied > impl_cap) { ret = h->fail(BBCP_ERR_ARG, "bbcp_probe_lits_to_host: implied-literal buffer too small"); break; }
         // the batch is complete (run_batch synchronises): its results leave on the output stream while the next
         // chunk computes into the other result set
-        cudaMemcpyAsync(flag_out + lo, h->rs[h->rb].flag.p, cnt, cudaMemcpyDeviceToHost, h->s_out);
+        // (flags the triage wrote into the caller's buffer are final when it queued nothing for the propagation tiers)
+        if (!(m_flag && bi.n_deep == 0)) cudaMemcpyAsync(flag_out + lo, h->rs[h->rb].flag.p, cnt, cudaMemcpyDeviceToHost, h->s_out);
         // compact read-back: while no chunk has stored a set, every offset is zero and nothing but the flags travels
         const bool compact = (opts.flags & BBCP_OPT_COMPACT_SELF) != 0;
         if (compact && bi.n_implied && !any_stored && lo) memset(off_out, 0, lo * osz);   // the chunks skipped so far
@@ -1060,6 +1097,7 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
         if (!compact || any_stored) cudaMemcpyAsync(static_cast<char *>(off_out) + lo * osz, h->rs[h->rb].off.p, cnt * osz, cudaMemcpyDeviceToHost, h->s_out);
         if (bi.n_implied) cudaMemcpyAsync(impl_out + base, h->rs[h->rb].impl.p, bi.n_implied * 4, cudaMemcpyDeviceToHost, h->s_out);
         cudaEventRecord(h->ev_out[k & 1], h->s_out);
+        if (trace) t_chunk[k] = us_now();
         base += bi.n_implied;
         tot.n += bi.n; tot.n_implied += bi.n_implied; tot.n_ok += bi.n_ok; tot.n_conflict += bi.n_conflict; tot.n_skipped += bi.n_skipped;
         tot.n_large += bi.n_large; tot.n_mid += bi.n_mid; tot.props_all += bi.props_all; tot.props_ref += bi.props_ref; tot.slots += bi.slots;
@@ -1072,7 +1110,15 @@ int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, con
     h->rb = 0;
     h->off_base = 0;
     h->have_batch = false;   // the results are in the caller's buffers, not in one device-side batch
+    h->e2e_hint_flags = opts.flags + 1u;
+    h->e2e_hint_implied = base;
     const bool ok = h->cuda_ok(cudaStreamSynchronize(h->s_out), "result read-back") && h->cuda_ok(cudaStreamSynchronize(h->s_in), "probe upload");
+    if (trace) {
+        fprintf(stderr, "bbcp_probe_lits_to_host (%s%s): n %llu, %llu chunks of %llu; uploads queued %.1f us; batches done", pull ? "pull" : "upload",
+                m_flag ? ", flags in place" : "", (unsigned long long)n, (unsigned long long)nchunks, (unsigned long long)csize, t_up);
+        for (uint64_t k = 0; k < nchunks; ++k) fprintf(stderr, " %.1f", t_chunk[k]);
+        fprintf(stderr, "; read-back done %.1f us; kernels %.1f us\n", us_now(), 1e3 * tot.total_ms);
+    }
     if (ret != BBCP_OK) return ret;
     if (!ok) return BBCP_ERR_CUDA;
     if (off32) {

@@ -40,6 +40,11 @@ struct BatchView {
     // (cube_lits[i] is item i); or, when both are nullptr, the probe universe starting at `first`
     const int32_t *cube_lits;
     const uint64_t *cube_off;
+    // bbcp_probe_lits_to_host with pinned caller buffers: the triage reads the probe list straight out of the caller's
+    // (mapped) host memory and leaves the device copy `cube_lits` for the kernels after it; it also writes the flags it
+    // decides into the caller's flag buffer. Both nullptr otherwise.
+    const int32_t *host_lits;
+    uint8_t *host_flag;
     uint64_t first;             // universe index of item 0 (probe mode)
     uint64_t n;                 // items in the batch
     // output

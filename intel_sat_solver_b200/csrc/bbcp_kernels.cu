@@ -194,6 +194,25 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
                 q[k] = (full || base + k < n) ? s_lut[li] : TQ_NONE;
             }
         } else {
+            int32_t pulled[TRIAGE_ITEMS];
+            if (MODE == TM_LIST) {
+                // the list is in the caller's pinned memory (two 16-byte loads per thread over PCIe, the device copy written
+                // for the kernels after this one) or already on the device
+                const int32_t *src = b.host_lits ? b.host_lits : b.cube_lits;
+                int32_t *copy = const_cast<int32_t *>(b.cube_lits);
+                if (full && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(copy)) & 15u) == 0) {
+                    const int4 a = __ldcs(reinterpret_cast<const int4 *>(src + base)), c = __ldcs(reinterpret_cast<const int4 *>(src + base) + 1);
+                    pulled[0] = a.x; pulled[1] = a.y; pulled[2] = a.z; pulled[3] = a.w;
+                    pulled[4] = c.x; pulled[5] = c.y; pulled[6] = c.z; pulled[7] = c.w;
+                    if (b.host_lits) { reinterpret_cast<int4 *>(copy + base)[0] = a; reinterpret_cast<int4 *>(copy + base)[1] = c; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TRIAGE_ITEMS; ++k) {
+                        pulled[k] = (full || base + k < n) ? src[base + k] : 0;
+                        if (b.host_lits && (full || base + k < n)) copy[base + k] = pulled[k];
+                    }
+                }
+            }
 #pragma unroll
             for (int k = 0; k < TRIAGE_ITEMS; ++k) {
                 const uint32_t item = base + k;
@@ -201,7 +220,7 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
                 if (full || item < n) {
                     int32_t lit;
                     bool single = true;
-                    if (MODE == TM_LIST) lit = b.cube_lits[item];
+                    if (MODE == TM_LIST) lit = pulled[k];
                     else {
                         const uint64_t o = b.cube_off[item];
                         single = b.cube_off[item + 1] - o == 1;
@@ -226,16 +245,21 @@ __global__ void __launch_bounds__(256) k_triage(const DbView db, const BatchView
         }
         if (full) {
             // deep items get their flag / size from the propagate kernels; the placeholder written here is overwritten
-            *reinterpret_cast<uint2 *>(b.flag + base) =
-                make_uint2((q[0] & 0xffu) | ((q[1] & 0xffu) << 8) | ((q[2] & 0xffu) << 16) | (q[3] << 24),
-                           (q[4] & 0xffu) | ((q[5] & 0xffu) << 8) | ((q[6] & 0xffu) << 16) | (q[7] << 24));
+            const uint2 fv = make_uint2((q[0] & 0xffu) | ((q[1] & 0xffu) << 8) | ((q[2] & 0xffu) << 16) | (q[3] << 24),
+                                        (q[4] & 0xffu) | ((q[5] & 0xffu) << 8) | ((q[6] & 0xffu) << 16) | (q[7] << 24));
+            *reinterpret_cast<uint2 *>(b.flag + base) = fv;
             uint4 *lp = reinterpret_cast<uint4 *>(b.len + base);
             lp[0] = make_uint4((q[0] & TQ_SELF) ? selflen : 0u, (q[1] & TQ_SELF) ? selflen : 0u, (q[2] & TQ_SELF) ? selflen : 0u, (q[3] & TQ_SELF) ? selflen : 0u);
             lp[1] = make_uint4((q[4] & TQ_SELF) ? selflen : 0u, (q[5] & TQ_SELF) ? selflen : 0u, (q[6] & TQ_SELF) ? selflen : 0u, (q[7] & TQ_SELF) ? selflen : 0u);
+            // the caller's flag buffer gets the same eight bytes (final unless an item was queued: the host checks the queue count)
+            if (MODE == TM_LIST && b.host_flag) *reinterpret_cast<uint2 *>(b.host_flag + base) = fv;
         } else {
 #pragma unroll
             for (int k = 0; k < TRIAGE_ITEMS; ++k)
-                if (base + k < n) { b.flag[base + k] = (uint8_t)q[k]; b.len[base + k] = (q[k] & TQ_SELF) ? selflen : 0u; }
+                if (base + k < n) {
+                    b.flag[base + k] = (uint8_t)q[k]; b.len[base + k] = (q[k] & TQ_SELF) ? selflen : 0u;
+                    if (MODE == TM_LIST && b.host_flag) b.host_flag[base + k] = (uint8_t)q[k];
+                }
         }
         // the tile's sum of set sizes so far (one literal per self-implying probe): stored, not added, so the array needs
         // no clearing between batches; the propagate kernels add the sizes of the sets they store
@@ -687,13 +711,13 @@ __device__ void block_propagate(const DbView &db, const BatchView &b, S &st, uin
     }
 }
 
-constexpr int SWEEP_WORDS = 4;
+constexpr int SWEEP_WORDS = 4;   // words of the dense assignment one thread sweeps per step: one 16-byte load
 __global__ void __launch_bounds__(BIG_THREADS, 5) k_big(const DbView db, const BatchView b, const LargeState ls, const int from_huge)
 {
     using G = Grp<32>;
     __shared__ uint32_t ctl[12];     // 0 tail, 1 conflict, 2 overflow, 3 load result, 4 ticket, 5 vmin, 6 vmax / whole-CTA level, 7 head, 8 second-walk entries
     __shared__ unsigned long long s_off;
-    __shared__ uint32_t s_sweep[SWEEP_WORDS][BIG_THREADS / 32];
+    __shared__ uint32_t s_sweep[2][BIG_THREADS / 32];
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     // the last tier takes what outgrew the tier before it: the third tier's hand-over list, or the second tier's when the
     // warp-per-probe second tier (k_deep2, BBCP_TIER2=warp) ran instead of the two CTA-per-probe tiers
@@ -773,51 +797,47 @@ __global__ void __launch_bounds__(BIG_THREADS, 5) k_big(const DbView db, const B
                         if (lane == 0) { atomicMin(&ctl[5], vmin); atomicMax(&ctl[6], vmax); }
                         __syncthreads();
                         BBCP_PHASE(6);
-                        const uint32_t w0 = ctl[5] >> 4, w1 = ctl[6] >> 4;
+                        const uint32_t w0 = (ctl[5] >> 4) & ~(uint32_t)(SWEEP_WORDS - 1), w1 = ctl[6] >> 4;
                         if (threadIdx.x == 0) atomicAdd(&bbcp_sweep_words(), (unsigned long long)(w1 - w0 + 1));
                         // The range is wide and sparse (on the Tseitin shape ~100 K words for ~18 K literals: a cone spans many
-                        // frames), and a step of the sweep is a dependent DRAM load + two barriers: SWEEP_WORDS loads per thread
-                        // are in flight per step. (Eight of them cost registers, a resident CTA, and more than they saved.)
+                        // frames). A thread takes SWEEP_WORDS consecutive words with one 16-byte load, so that one warp scan and
+                        // one barrier order a whole step (the partial sums alternate between two buffers); the next step's load
+                        // is in flight while this one is scanned and written out.
                         unsigned long long w = off;
-                        for (uint32_t wbase = w0; wbase <= w1; wbase += SWEEP_WORDS * blockDim.x) {
-                            uint32_t word[SWEEP_WORDS], excl[SWEEP_WORDS];
+                        const uint4 *bits4 = reinterpret_cast<const uint4 *>(gs.bits);     // slabs are whole 16-byte vectors (nvars_words16)
+                        const uint32_t stride = SWEEP_WORDS * blockDim.x;
+                        uint32_t wi = w0 + SWEEP_WORDS * threadIdx.x;
+                        uint4 cur = wi <= w1 ? __ldcg(&bits4[wi >> 2]) : make_uint4(0, 0, 0, 0);
+                        for (uint32_t wbase = w0, par = 0; wbase <= w1; wbase += stride, wi += stride, par ^= 1u) {
+                            const uint4 nxt = wi + stride <= w1 ? __ldcg(&bits4[(wi + stride) >> 2]) : make_uint4(0, 0, 0, 0);
+                            const uint32_t word[SWEEP_WORDS] = {cur.x, cur.y, cur.z, cur.w};
+                            uint32_t c = 0;
 #pragma unroll
-                            for (int k = 0; k < SWEEP_WORDS; ++k) {
-                                const uint32_t wi = wbase + k * blockDim.x + threadIdx.x;
-                                word[k] = wi <= w1 ? __ldcg(&gs.bits[wi]) : 0u;
+                            for (int k = 0; k < SWEEP_WORDS; ++k) c += __popc((word[k] | (word[k] >> 1)) & 0x55555555u);  // one bit per assigned var
+                            uint32_t incl = c;
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const uint32_t x = __shfl_up_sync(FULL, incl, d);
+                                if (lane >= d) incl += x;
                             }
-#pragma unroll
-                            for (int k = 0; k < SWEEP_WORDS; ++k) {
-                                const uint32_t c = __popc((word[k] | (word[k] >> 1)) & 0x55555555u);  // one bit per assigned var
-                                uint32_t incl = c;
-#pragma unroll
-                                for (int d = 1; d < 32; d <<= 1) {
-                                    const uint32_t x = __shfl_up_sync(FULL, incl, d);
-                                    if (lane >= d) incl += x;
-                                }
-                                if (lane == 31) s_sweep[k][warp] = incl;
-                                excl[k] = incl - c;
-                            }
+                            if (lane == 31) s_sweep[par][warp] = incl;
                             __syncthreads();
-                            uint32_t run = 0;
+                            uint32_t before = 0, total = 0;
+                            for (int q = 0; q < nwarps; ++q) { const uint32_t x = s_sweep[par][q]; total += x; if (q < warp) before += x; }
+                            unsigned long long o = w + before + incl - c;
 #pragma unroll
                             for (int k = 0; k < SWEEP_WORDS; ++k) {
-                                uint32_t before = 0, total = 0;
-                                for (int q = 0; q < nwarps; ++q) { const uint32_t x = s_sweep[k][q]; total += x; if (q < warp) before += x; }
-                                unsigned long long o = w + run + before + excl[k];
-                                const uint32_t wi = wbase + k * blockDim.x + threadIdx.x;
                                 uint32_t m = (word[k] | (word[k] >> 1)) & 0x55555555u;
                                 while (m) {
                                     const int bpos = __ffs(m) - 1;
                                     m &= m - 1;
-                                    const uint32_t var = wi * 16u + (uint32_t)(bpos >> 1);
+                                    const uint32_t var = (wi + k) * 16u + (uint32_t)(bpos >> 1);
                                     const bool isneg = ((word[k] >> bpos) & 3u) == 2u;
                                     b.out_lits[o++] = (int32_t)(2u * var + (isneg ? 1u : 0u));   // internal literals, as every set in the pool
                                 }
-                                run += total;
                             }
-                            w += run;
-                            __syncthreads();
+                            w += total;
+                            cur = nxt;
                         }
                         wc.bytes += warp == 0 ? 4ull * tail + 4ull * (w1 - w0 + 1) : 0ull;
                     }

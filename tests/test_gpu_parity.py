@@ -321,6 +321,73 @@ def test_pipelined_host_call_matches_plain_call():
         assert empty.impl_off.tolist() == [0]
 
 
+def test_pinned_caller_buffers_are_used_in_place():
+    """bbcp_probe_lits_to_host with PINNED caller buffers: the triage kernel pulls the probe list out of the caller's memory
+    and writes the flags it decides straight into the caller's flag buffer (BBCP_E2E=pull, the default; mirror: uploaded list,
+    flags in place). Same bytes as the copy-engine path (BBCP_E2E=dma) and as the goldens: with and without queued probes,
+    compact and standard format, aligned and misaligned views, lengths that are not multiples of the triage's vector width."""
+    import torch
+    g = np.load(os.path.join(gpu_util.ROOT, "tests", "golden", "golden.npz"))
+    cases = []
+    with tempfile.TemporaryDirectory() as d:
+        # (a) random 3-SAT: every probe is decided by the triage (no binary clause): the flags never leave through a copy
+        inst, _ = gpu_util.gen("3sat", d, n=40000, m=168000, seed=3)
+        cases.append(("3sat", fileio.read_bcnf(inst)))
+        # (b) community instance with binary clauses: queued probes, all tiers
+        inst, _ = gpu_util.gen("comm", d, n=60000, m=240000, comms=60, seed=12)
+        cases.append(("comm", fileio.read_bcnf(inst)))
+    cases.append(("fuzz_10", g["fuzz_10/words"]))
+    try:
+        for name, words in cases:
+            t, rc = engine_for(words)
+            assert rc == 0
+            n_all = 2 * t.max_var
+            rng = np.random.default_rng(7)
+            idx = rng.permutation(n_all)
+            lits_all = np.where(idx & 1, -(idx // 2 + 1), idx // 2 + 1).astype(np.int32)
+            lits_all[::97] = 0                      # zeros name no variable: reported as unmapped
+            for n, shift in ((n_all, 0), (n_all - 3, 0), (n_all - 5, 1), (min(n_all, 1001), 2)):
+                lits = lits_all[:n]
+                for compact in (False, True):
+                    os.environ["BBCP_E2E"] = "dma"
+                    ref = t.ProbeLitsToHost(lits, compact_self=compact, off32=True)
+                    for mode, chunks in (("pull", None), ("pull", "3"), ("mirror", "2")):
+                        os.environ["BBCP_E2E"] = mode
+                        if chunks:
+                            os.environ["BBCP_CHUNKS"] = chunks
+                        # pinned buffers; `shift` moves the views off their 16-byte (list) and 8-byte (flags) alignment
+                        p_lits = torch.empty(n + 8, dtype=torch.int32).pin_memory()
+                        p_flag = torch.full((n + 16,), 0x55, dtype=torch.uint8).pin_memory()
+                        p_off = torch.zeros(n + 1, dtype=torch.int32).pin_memory()
+                        p_impl = torch.empty(max(int(ref.info["n_implied"]), 1), dtype=torch.int32).pin_memory()
+                        v_lits = p_lits.numpy()[shift:shift + n]
+                        v_lits[:] = lits
+                        v_flag = p_flag.numpy()[shift:shift + n]
+                        for rep in range(2):        # the second call sizes its chunks from the first one's result
+                            res = t.ProbeLitsToHost(v_lits, flag_out=v_flag, off_out=p_off.numpy().view(np.uint32), impl_out=p_impl.numpy(),
+                                                    compact_self=compact, off32=True)
+                            assert np.array_equal(res.flag, ref.flag), (name, n, shift, compact, mode, rep)
+                            if ref.info["n_implied"]:
+                                assert np.array_equal(res.impl_off, ref.impl_off) and np.array_equal(res.impl_lits, ref.impl_lits)
+                            assert res.info["n_implied"] == ref.info["n_implied"]
+                        assert (p_flag.numpy()[:shift] == 0x55).all() and (p_flag.numpy()[shift + n:] == 0x55).all()   # nothing written past the view
+                        os.environ.pop("BBCP_CHUNKS", None)
+            if name == "3sat":
+                assert ref.info["n_deep"] == 0
+            else:
+                assert ref.info["n_deep"] > 0
+    finally:
+        os.environ.pop("BBCP_E2E", None)
+        os.environ.pop("BBCP_CHUNKS", None)
+    # against the golden results of the reference
+    n = 2 * t.max_var
+    idx = np.arange(n)
+    lits = torch.from_numpy(np.where(idx & 1, -(idx // 2 + 1), idx // 2 + 1).astype(np.int32)).pin_memory()
+    flag = torch.empty(n, dtype=torch.uint8).pin_memory()
+    res = t.ProbeLitsToHost(lits.numpy(), flag_out=flag.numpy())
+    gpu_util.assert_same_results(res, g["fuzz_10/probe_flag"], g["fuzz_10/probe_off"], g["fuzz_10/probe_lits"], "fuzz_10")
+
+
 def test_probe_to_fixpoint_matches_checker_rounds(golden):
     """Unit-feedback rounds (survey 'next' row N2): probe all, add the negations of the failed literals as units,
     re-finalize, repeat. The same loop driven through the CPU checker gives the same number of rounds, the same
