@@ -498,22 +498,48 @@ k_deep2(const DbView db, const BatchView b, uint32_t *slab, const uint32_t log_h
 }
 
 // Sorts the implied sets the second tier left unsorted in the pool (ascending internal literal = ascending
-// variable). One CTA per set, in shared memory.
+// variable). One CTA per set (dynamic tickets: the sets differ 16-fold in size), bitonic network in shared memory; the
+// compare-exchange steps at distances below 32 run on warp shuffles (a warp owns 32 consecutive keys), so a merge of
+// 2^m keys costs m - 5 CTA barriers instead of m.
 constexpr int SORT_THREADS = 256;
+__device__ __forceinline__ uint32_t sort_cex(uint32_t x, uint32_t j, bool up, int lane)
+{
+    const uint32_t y = __shfl_xor_sync(FULL, x, j);
+    const bool lower = (lane & j) == 0;
+    return (lower == up) ? min(x, y) : max(x, y);
+}
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_sets(const BatchView b, const uint32_t cap)
 {
     extern __shared__ uint32_t s_keys[];
+    __shared__ uint32_t s_e;
     const uint32_t count = *b.sort_count;
-    for (uint32_t e = blockIdx.x; e < count; e += gridDim.x) {
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    constexpr uint32_t NW = SORT_THREADS / 32;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_e = atomicAdd(b.ticket + 2, 1u);   // (the CTA-per-probe tiers that own this ticket do not run beside the warp-per-probe second tier)
+        __syncthreads();
+        const uint32_t e = s_e;
+        if (e >= count) break;
         const uint32_t item = b.sort_list[e];
         const uint32_t len = b.len[item] & 0x7fffffffu;
         int32_t *set = b.out_lits + b.raw_off[item];
-        uint32_t n2 = 1;
+        uint32_t n2 = 32;
         while (n2 < len) n2 <<= 1;
-        for (uint32_t i = threadIdx.x; i < n2; i += SORT_THREADS) s_keys[i] = i < len ? (uint32_t)set[i] : 0xffffffffu;
+        // load + the merges up to 32 keys, all inside a warp's block of 32 keys
+        for (uint32_t i = threadIdx.x; i < n2; i += SORT_THREADS) {
+            uint32_t x = i < len ? (uint32_t)set[i] : 0xffffffffu;
+#pragma unroll
+            for (uint32_t k = 2; k <= 32; k <<= 1) {
+                const bool up = (i & k) == 0;
+#pragma unroll
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) x = sort_cex(x, j, up, lane);
+            }
+            s_keys[i] = x;
+        }
         __syncthreads();
-        for (uint32_t k = 2; k <= n2; k <<= 1) {
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t k = 64; k <= n2; k <<= 1) {
+            for (uint32_t j = k >> 1; j >= 32; j >>= 1) {
                 for (uint32_t t = threadIdx.x; t < n2 / 2; t += SORT_THREADS) {
                     const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                     const uint32_t ixj = i | j;
@@ -523,9 +549,17 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_sets(const BatchView b, c
                 }
                 __syncthreads();
             }
+            for (uint32_t blk = warp; blk < n2 / 32; blk += NW) {
+                const uint32_t i = blk * 32 + lane;
+                const bool up = (i & k) == 0;
+                uint32_t x = s_keys[i];
+#pragma unroll
+                for (uint32_t j = 16; j > 0; j >>= 1) x = sort_cex(x, j, up, lane);
+                s_keys[i] = x;
+            }
+            __syncthreads();
         }
         for (uint32_t i = threadIdx.x; i < len; i += SORT_THREADS) set[i] = (int32_t)s_keys[i];
-        __syncthreads();
     }
 }
 
@@ -766,6 +800,7 @@ __global__ void __launch_bounds__(BIG_THREADS, 5) k_big(const DbView db, const B
         uint8_t flag = (uint8_t)f;
         uint32_t len = 0;
         unsigned long long off = 0;
+        bool swept = false;   // the emission sweep cleared the dense assignment
         if (f == 0xff || f == FLAG_CONFLICT) {
             if (conflict) {
                 flag = FLAG_CONFLICT;
@@ -783,6 +818,7 @@ __global__ void __launch_bounds__(BIG_THREADS, 5) k_big(const DbView db, const B
                     else {
                         // ordered emission: sweep the dense assignment between the smallest and largest assigned var
                         len = nmem;
+                        swept = true;
                         uint32_t vmin = 0xffffffffu, vmax = 0;
                         for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
                             const uint32_t var = (gs.tget(i) & TRAIL_LIT) >> 1;
@@ -811,6 +847,8 @@ __global__ void __launch_bounds__(BIG_THREADS, 5) k_big(const DbView db, const B
                         for (uint32_t wbase = w0, par = 0; wbase <= w1; wbase += stride, wi += stride, par ^= 1u) {
                             const uint4 nxt = wi + stride <= w1 ? __ldcg(&bits4[(wi + stride) >> 2]) : make_uint4(0, 0, 0, 0);
                             const uint32_t word[SWEEP_WORDS] = {cur.x, cur.y, cur.z, cur.w};
+                            // the sweep also leaves the state empty for the next probe (every assigned variable lies in its range)
+                            if (cur.x | cur.y | cur.z | cur.w) __stcg(reinterpret_cast<uint4 *>(gs.bits) + (wi >> 2), make_uint4(0, 0, 0, 0));
                             uint32_t c = 0;
 #pragma unroll
                             for (int k = 0; k < SWEEP_WORDS; ++k) c += __popc((word[k] | (word[k] >> 1)) & 0x55555555u);  // one bit per assigned var
@@ -847,7 +885,7 @@ __global__ void __launch_bounds__(BIG_THREADS, 5) k_big(const DbView db, const B
         __syncthreads();
         BBCP_PHASE(4);
         // leave the state empty for the next probe
-        for (uint32_t i = threadIdx.x; i < tail; i += blockDim.x) {
+        for (uint32_t i = threadIdx.x; i < tail && !swept; i += blockDim.x) {
             const uint32_t var = (gs.tget(i) & TRAIL_LIT) >> 1;
             atomicAnd(&gs.bits[var >> 4], ~(3u << ((var & 15u) * 2u)));
         }
@@ -1714,9 +1752,10 @@ void launch_mid(const DbView &db, const BatchView &b, uint32_t *slab, uint32_t c
 
 void launch_sort_sets(const BatchView &b, uint32_t cap, int sm_count, cudaStream_t s)
 {
-    const size_t smem = (size_t)cap * 4;
+    const size_t smem = (size_t)std::max<uint32_t>(cap, 32) * 4;
     cudaFuncSetAttribute(k_sort_sets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_sort_sets<<<sm_count * 4, SORT_THREADS, smem, s>>>(b, cap);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 64)));   // as many CTAs as the shared memory holds: barrier-bound
+    k_sort_sets<<<sm_count * per_sm, SORT_THREADS, smem, s>>>(b, cap);
 }
 
 void launch_big(const DbView &db, const BatchView &b, const LargeState &ls, int blocks, bool from_huge, cudaStream_t s)
