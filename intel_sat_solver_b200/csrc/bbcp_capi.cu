@@ -479,6 +479,10 @@ int run_batch(bbcp_handle *h, const int32_t *d_lits, const uint64_t *d_off, uint
     if (!d_lits && !d_off && !no_reuse && !(opts.flags & BBCP_OPT_NO_REUSE)) {
         b.reuse = 1;
         if (h->order_n) { b.order = h->d_order.as<uint32_t>(); b.order_n = h->order_n; }
+        // with closure reuse a probe beyond ~1000 literals is mostly adoption of finished sets, which the CTA-per-probe last
+        // tier does with all its warps: the warp-per-probe second tier keeps only what is just above the first tier's capacity
+        // (full-size C3, second-tier capacity 8192 / 4096 / 2048 / 1024 / 512: 1191 / 1034 / 1004 / 986 / 1001 ms per pass)
+        if (!opts.mid_trail && !getenv("BBCP_MID_TRAIL")) cap_mid = 1024;
     }
 
     const int bps = small_blocks_per_sm(cap, width);

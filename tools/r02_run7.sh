@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_g.log 2>&1; tail -4 gpurun_out/r02_pytest_g.log
 ( time timeout 900 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err ) 2> gpurun_out/r02_bench_n1.time
 tail -3 gpurun_out/r02_bench_n1.err | cut -c1-300; cat gpurun_out/r02_bench_n1.time
+timeout 120 python -c 'import __graft_entry__ as g; g.smoke(); print("smoke ok")' 2>&1 | tail -2
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err
 python - <<'PY'
 import json
