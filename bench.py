@@ -671,6 +671,8 @@ def ours_arm(args, rank, local_rank, world):
             "failed_literals": int(n_conflict),
             "e2e": {"value": e2e_value, "unit": "probes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_sum / args.steps, "format": "compact read-back (BBCP_OPT_COMPACT_SELF): flags with a self-implied bit; offsets + literals only for stored sets",
+                    "transport": "pinned host buffers used in place by bbcp_probe_lits_to_host: the triage kernel reads the probe list over PCIe "
+                                 "(h2d bytes) and writes the flags into the caller's buffer (d2h bytes); BBCP_E2E=dma selects copy-engine transfers",
                     "full_format": {"value": float(probes.item()) * args.steps / full_total, "ms_per_step": 1e3 * full_total / args.steps, "d2h_bytes_per_step": d2h_full,
                                     "format": "flags + u32 CSR offsets + implied literals"}},
             "gpu_launches": launches,

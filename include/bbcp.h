@@ -175,9 +175,15 @@ int bbcp_probe_all(bbcp_handle *h, const bbcp_opts *opts, bbcp_batch_info *info)
 /* explicit list of depth-1 probes: item i is the single literal lits[i] (4 bytes per probe instead of a CSR
  * cube; a 0 entry is reported BBCP_FLAG_UNMAPPED). Same results as one-literal cubes. */
 int bbcp_probe_lits(bbcp_handle *h, const int32_t *lits, uint64_t n, const bbcp_opts *opts, bbcp_batch_info *info);
-/* The same, results straight into HOST buffers, pipelined: the list is cut into chunks, all chunks are uploaded on
- * one stream, each chunk's kernels start when its part has arrived, and its flags / offsets / literals travel back
- * on a third stream while the next chunk computes (PCIe both ways and the kernels overlap; pass pinned buffers).
+/* The same, results straight into HOST buffers.
+ * PINNED caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are used IN PLACE: the first kernel of
+ * the batch reads `lits` out of the caller's memory over PCIe and writes the flags it decides into `flag_out`, so no
+ * staging copy runs for either (flag_out is copied only when a probe needed the propagation tiers); offsets and
+ * literals travel back on a copy stream while the next chunk computes. The buffers must stay untouched until the call
+ * returns (it returns after the last byte has arrived).
+ * Pageable buffers (or BBCP_E2E=dma in the environment) take the copy-engine path: the list is cut into chunks, all
+ * chunks are uploaded on one stream, each chunk's kernels start when its part has arrived, and its flags / offsets /
+ * literals travel back on a third stream while the next chunk computes.
  * flag_out[n]; off_out[n+1] uint64, or uint32 with BBCP_OPT_OFF32 (offsets run through the whole list);
  * impl_out[impl_cap] (BBCP_ERR_ARG if the list implies more). Bitmaps accumulate as usual. */
 int bbcp_probe_lits_to_host(bbcp_handle *h, const int32_t *lits, uint64_t n, const bbcp_opts *opts, uint8_t *flag_out, void *off_out,

@@ -172,8 +172,10 @@ class BatchedTopor:
         return self.ProbeRange(0, 2 * self.max_var, implied=implied, fetch=fetch, **kw)
 
     def ProbeLitsToHost(self, lits, impl_cap=None, flag_out=None, off_out=None, impl_out=None, **kw) -> BatchResult:
-        """Pipelined form of ProbeLits + fetch (bbcp_probe_lits_to_host): upload, kernels and read-back of successive
-        chunks overlap. Output arrays may be passed in (e.g. views of pinned memory); impl_cap = literals they hold."""
+        """ProbeLits + fetch in one call (bbcp_probe_lits_to_host). Arrays in PINNED memory (views of torch pin_memory()
+        tensors) are used in place: the first kernel reads the list and writes the flags over PCIe, no staging copies;
+        otherwise upload, kernels and read-back of successive chunks overlap on copy streams. Output arrays may be
+        passed in; impl_cap = literals they hold."""
         a = np.ascontiguousarray(lits, dtype=np.int32)
         off32 = kw.get("off32", False)
         n = a.size
