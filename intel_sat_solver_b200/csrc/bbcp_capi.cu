@@ -847,9 +847,17 @@ static int host_prepare_impl(bbcp_handle *h)
 {
     if (!h) return BBCP_ERR_ARG;
     if (h->status < 0) return h->status;
+    // BBCP_HOST_TRACE: seconds of the two host phases on stderr
+    const bool trace = getenv("BBCP_HOST_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     h->db.normalise();
+    const auto t1 = std::chrono::steady_clock::now();
     if (h->db.contradictory) { h->prepared = true; return h->fail(BBCP_CONTRADICTORY, "AddClause: the clause set is contradictory at intake"); }
     const std::string e = h->db.build_rows();
+    if (trace)
+        fprintf(stderr, "bbcp host prepare: normalise %.3f s (%s), build_rows %.3f s (%zu words in, %zu slots)\n", std::chrono::duration<double>(t1 - t0).count(),
+                h->db.intake_by_chunk ? "by chunk" : "stream order", std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(), h->db.raw.size(),
+                h->db.slots.size());
     if (!e.empty()) return h->fail(BBCP_ERR_INDEX_TOO_NARROW, e);
     h->prepared = true;
     if (h->status == BBCP_CONTRADICTORY) h->status = BBCP_OK;

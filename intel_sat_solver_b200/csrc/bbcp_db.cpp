@@ -8,6 +8,11 @@
 
 namespace bbcp {
 
+namespace {
+unsigned host_threads(size_t work_words);
+template <class F> void parallel(unsigned T, F f);
+}  // namespace
+
 void HostDb::add_words(const int32_t *w, uint64_t n)
 {
     raw.insert(raw.end(), w, w + n);
@@ -28,6 +33,12 @@ void HostDb::add_words(const int32_t *w, uint64_t n)
 //     later (590-619); otherwise the clause is kept (621).
 // A variable is "mapped" iff some kept (or unit) clause mentions it.
 void HostDb::normalise()
+{
+    intake_by_chunk = normalise_parallel();
+    if (!intake_by_chunk) normalise_serial();
+}
+
+void HostDb::normalise_serial()
 {
     const size_t nv = (size_t)max_var + 1;
     varinfo.assign(nv, 0);
@@ -130,6 +141,99 @@ void parallel(unsigned T, F f)
 }
 
 }  // namespace
+
+// The order-free case of normalise(), by clause chunk. Without unit clauses in the stream nothing a clause goes through
+// depends on the clauses before it: no literal is ever false at level 0, a clause is kept iff it is no tautology, its
+// literals stay in first-occurrence order, and a variable ends up mapped iff some non-tautological clause mentions it
+// (the serial pass un-maps exactly the variables first seen in a tautology, and any later kept clause maps them again).
+// Every thread normalises one contiguous chunk of the stream into its own buffer; the buffers are concatenated in chunk
+// order, so `cls` is byte-identical to the serial result. The first unit clause (or empty clause) anywhere abandons the
+// attempt: the caller then runs the serial pass, whose "units so far" semantics is order-dependent.
+bool HostDb::normalise_parallel()
+{
+    const size_t n = raw.size();
+    const unsigned T = host_threads(n);
+    if (T < 2 || n < 2) return false;
+    const size_t nv = (size_t)max_var + 1;
+    // chunk boundaries right after a terminating 0
+    std::vector<size_t> lo(T + 1, n);
+    lo[0] = 0;
+    for (unsigned t = 1; t < T; ++t) {
+        size_t p = std::max(lo[t - 1], n / T * t);
+        while (p < n && (p == 0 || raw[p - 1] != 0)) ++p;
+        lo[t] = p;
+    }
+    varinfo.assign(nv, 0);
+    std::vector<std::vector<uint32_t>> out(T);
+    std::vector<uint64_t> kept(T, 0);
+    std::vector<uint8_t> bail(T, 0);
+    uint8_t *vi = varinfo.data();
+    parallel(T, [&](unsigned t) {
+        std::vector<uint32_t> &o = out[t];
+        o.reserve((lo[t + 1] - lo[t]) + (lo[t + 1] - lo[t]) / 8 + 16);
+        std::vector<uint32_t> table;   // long clauses: open-addressed set of the literals seen
+        size_t s = lo[t];
+        const size_t end = lo[t + 1];
+        while (s < end) {
+            size_t e = s;
+            while (e < end && raw[e] != 0) ++e;
+            if (e == s || e == end) { bail[t] = 1; return; }   // empty clause (contradictory) / unterminated tail: the serial pass decides
+            const size_t len = e - s, hdr_pos = o.size();
+            o.push_back(0);
+            bool taut = false;
+            if (len <= 16) {
+                for (size_t i = s; i < e && !taut; ++i) {
+                    const int32_t l = raw[i];
+                    const uint32_t il = 2u * (uint32_t)(l < 0 ? -l : l) + (l < 0);
+                    bool dup = false;
+                    for (size_t k = hdr_pos + 1; k < o.size(); ++k) {
+                        if (o[k] == il) { dup = true; break; }
+                        if (o[k] == (il ^ 1u)) { taut = true; break; }
+                    }
+                    if (!dup && !taut) o.push_back(il);
+                }
+            } else {
+                size_t cap = 32;
+                while (cap < 2 * len) cap <<= 1;
+                table.assign(cap, 0);
+                for (size_t i = s; i < e && !taut; ++i) {
+                    const int32_t l = raw[i];
+                    const uint32_t il = 2u * (uint32_t)(l < 0 ? -l : l) + (l < 0);
+                    bool dup = false;
+                    // one table for both polarities, keyed by variable: the entry holds the literal seen
+                    size_t h = ((il >> 1) * 0x9E3779B1u) & (cap - 1);
+                    for (;; h = (h + 1) & (cap - 1)) {
+                        const uint32_t x = table[h];
+                        if (x == 0) { table[h] = il; break; }
+                        if (x == il) { dup = true; break; }
+                        if (x == (il ^ 1u)) { taut = true; break; }
+                    }
+                    if (!dup && !taut) o.push_back(il);
+                }
+            }
+            s = e + 1;
+            if (taut) { o.resize(hdr_pos); continue; }
+            const size_t cnt = o.size() - hdr_pos - 1;
+            if (cnt < 2) { bail[t] = 1; return; }   // a unit clause: later clauses depend on it
+            o[hdr_pos] = (uint32_t)cnt;
+            ++kept[t];
+            for (size_t k = hdr_pos + 1; k < o.size(); ++k) {
+                uint8_t *b = vi + (o[k] >> 1);
+                if (!(__atomic_load_n(b, __ATOMIC_RELAXED) & 4)) __atomic_fetch_or(b, (uint8_t)4, __ATOMIC_RELAXED);
+            }
+        }
+    });
+    for (unsigned t = 0; t < T; ++t) if (bail[t]) return false;
+    std::vector<size_t> at(T + 1, 0);
+    for (unsigned t = 0; t < T; ++t) at[t + 1] = at[t] + out[t].size();
+    cls.resize(at[T]);
+    parallel(T, [&](unsigned t) { if (!out[t].empty()) std::memcpy(cls.data() + at[t], out[t].data(), out[t].size() * 4); });
+    units.clear();
+    ncls = 0;
+    for (unsigned t = 0; t < T; ++t) ncls += kept[t];
+    contradictory = false;
+    return true;
+}
 
 // Flattening, multi-threaded by OWNER-COMPUTES: thread t owns the literals l with (l / 256) % T == t (blocks of 256
 // literals dealt round-robin, so that the hot low-numbered variables of a power-law instance are spread). Every thread

@@ -23,6 +23,7 @@ struct HostDb {
     std::vector<uint8_t> varinfo;     // [max_var+1] bits 0-1: level-0 value (1 true, 2 false), bit 2: mapped
     std::vector<uint32_t> cls;        // kept clauses of size >= 2, internal literals, [len, lits...]*
     uint64_t ncls = 0;
+    bool intake_by_chunk = false;     // the last normalise() took the order-free multi-threaded path
     std::vector<uint32_t> units;      // internal literals assigned directly by unit clauses, in order
 
     // ---- after build_rows()
@@ -39,6 +40,8 @@ struct HostDb {
     void add_words(const int32_t *w, uint64_t n);
     // AddUserClause semantics over the whole raw stream; fills varinfo (mapped + direct units), cls, units
     void normalise();
+    void normalise_serial();     // the defining pass, in stream order
+    bool normalise_parallel();   // the same result by clause chunk when no clause is (or becomes) a unit; false = not applicable, nothing decided
     // drop clauses satisfied / strip literals false under varinfo's level-0 values (the
     // level-0-simplified DB); returns false if a clause becomes empty (cannot happen after a level-0 fixpoint)
     bool simplify_level0();

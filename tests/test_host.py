@@ -218,6 +218,51 @@ def test_row_build_does_not_depend_on_the_thread_count(golden):
     assert sum(len(r) for r in rows["1"]["fuzz_10"]) > 10000
 
 
+def test_intake_by_chunk_equals_the_pass_in_stream_order():
+    """The multi-threaded intake (clause chunks normalised independently; applicable when no clause is or becomes a
+    unit) gives the same database as the defining pass in stream order: counts, mapped variables and every row, on
+    streams with duplicate literals, tautologies (incl. variables that occur in nothing else), clauses beyond the
+    quadratic-dedupe length. Streams with unit or empty clauses must fall back."""
+    import subprocess, sys, json
+    prog = r"""
+import sys, json, os, numpy as np
+sys.path.insert(0, %r)
+from intel_sat_solver_b200 import BatchedTopor
+rng = np.random.default_rng(77)
+out = []
+for trial in range(40):
+    nv = int(rng.integers(20, 400))
+    words = []
+    for _ in range(int(rng.integers(50, 600))):
+        k = int(rng.choice([2, 2, 3, 3, 3, 4, 6, 20, 40]))
+        lits = [int(rng.integers(1, nv + 1)) * (1 if rng.random() < 0.5 else -1) for _ in range(k)]
+        if rng.random() < 0.2: lits.append(lits[0])
+        if rng.random() < 0.1: lits.insert(int(rng.integers(0, len(lits))), -lits[-1])
+        if rng.random() < 0.05: lits = [nv + 1 + len(words) %% 7, -(nv + 1 + len(words) %% 7)] + lits[:1]   # tautology on an otherwise unused variable
+        words += lits + [0]
+    kind = trial %% 4
+    if kind == 2: words[len(words) // 2:len(words) // 2] = [5, 0]   # a unit clause in the middle
+    if kind == 3 and trial %% 8 == 3: words[10:10] = [0]    # an empty clause (or a split one)
+    t = BatchedTopor(); t.AddClauses(np.asarray(words, dtype=np.int32))
+    rc = t.HostPrepare()
+    rec = {"rc": rc, "info": {k: v for k, v in t.DbInfo().items() if k != "device_bytes"}}
+    if rc == 0:
+        rec["rows"] = [t.HostRow(l).tolist() for l in range(2, 2 * t.max_var + 2)]
+    out.append(rec)
+print(json.dumps(out))
+""" % ROOT
+    res, traces = {}, {}
+    for th in ("1", "2", "8"):
+        env = dict(os.environ, BBCP_HOST_THREADS=th, BBCP_HOST_TRACE="1")
+        r = subprocess.run([sys.executable, "-c", prog], check=True, capture_output=True, text=True, env=env)
+        res[th] = json.loads(r.stdout)
+        traces[th] = r.stderr
+    assert res["1"] == res["2"] == res["8"]
+    assert "by chunk" not in traces["1"]
+    assert traces["8"].count("by chunk") >= 15 and traces["8"].count("stream order") >= 10   # both paths were exercised
+    assert sum(r["rc"] == 0 for r in res["1"]) >= 30
+
+
 def _scc_ids(nl, succ):
     """Tarjan, recursive-free reference (small inputs): component id per literal."""
     import sys
