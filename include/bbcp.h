@@ -76,7 +76,8 @@ typedef struct {
     uint32_t flags;            /* BBCP_OPT_* ; default BBCP_OPT_IMPLIED */
     uint32_t small_trail;      /* trail capacity of the first tier, shared memory (0 = 512) */
     uint64_t out_capacity;     /* device capacity for implied literals per launch, in literals (0 = auto) */
-    uint32_t mid_trail;        /* trail capacity of the second tier, hash + trail in a global slab (0 = 8192) */
+    uint32_t mid_trail;        /* trail capacity of the second tier, hash + trail in a global slab (0 = 1024 for all-literal
+                                  batches, where finished probes' sets are adopted and the last tier does that faster; 8192 otherwise) */
     uint32_t merge_words_per_rank; /* BBCP_OPT_MERGE: bitmap words owned by each rank (as in bbcp_merge_bitmaps) */
 } bbcp_opts;
 
