@@ -167,5 +167,8 @@ void launch_merge_drain(const MergeArgs &m, cudaStream_t s);
 constexpr int SMALL_THREADS = 128;  // first tier: SMALL_THREADS / W probes in flight per CTA (W lanes per probe)
 constexpr int MID2_THREADS = 256;   // second tier: MID2_THREADS / W probes per CTA, state in a global slab
 constexpr int BIG_THREADS = 256;   // third tier: 8 warps share one probe, state in a global slab
+// (Other shapes were tried on the full-size Tseitin workload at the end of round 2: 128 threads x 8 CTAs per SM is 10 % slower;
+// 128 x 10 and 64 x 16 did not finish their pass and the cause was not found -- re-validate with tools/bench_workloads.py c3
+// before changing this or the launch bound of k_big.)
 
 }  // namespace bbcp
